@@ -1,0 +1,466 @@
+"""Host-side mirror of the reference's R API for the cell-clustering hot path.
+
+Same function names, argument names / order / defaults, error conditions and return-object
+shapes as the reference's R closures (R is not installed in this image, so the host side
+above the C ABI is Python; INTEGRATION.md shows the equivalent R `.Call` shim).  Everything
+that is arithmetic runs on the device through `libclonalscope_b200.so`; what stays here is
+what stays in the R shim: argument defaulting and validation, name matching, dimnames.
+
+R objects map to Python as: named list -> dict, matrix -> 2-D numpy array (+ `rownames` /
+`colnames` entries next to it), list of matrices -> list of arrays, NA_real_ -> NaN.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from .intervals import gene_sites, overlap_map, r_as_character, sort_bins
+
+
+class ClonalscopeError(RuntimeError):
+    """A nonzero status from the C ABI (the R shim would raise it with stop())."""
+
+    def __init__(self, status, message):
+        super().__init__(f"[cs status {status}] {message}")
+        self.status = status
+
+
+def _check(rc):
+    if rc != 0:
+        raise ClonalscopeError(rc, _lib.lib().cs_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class NamedMatrix:
+    """A matrix with dimnames (what the reference returns as a sparse `Matrix` or data.frame)."""
+
+    def __init__(self, values, rownames, colnames):
+        self.values = values
+        self.rownames = list(rownames)
+        self.colnames = list(colnames)
+
+    @property
+    def shape(self):
+        return self.values.shape
+
+
+# --------------------------------------------------------------------------- a1
+def _first_column(obj):
+    if hasattr(obj, "iloc"):
+        return list(obj.iloc[:, 0])
+    if isinstance(obj, dict):
+        return list(next(iter(obj.values())))
+    a = np.asarray(obj, dtype=object)
+    return list(a[:, 0] if a.ndim == 2 else a)
+
+
+def _bed_columns(bed):
+    if hasattr(bed, "iloc"):
+        return list(bed.iloc[:, 0]), list(bed.iloc[:, 1]), list(bed.iloc[:, 2])
+    a = np.asarray(bed, dtype=object)
+    return list(a[:, 0]), list(a[:, 1]), list(a[:, 2])
+
+
+def gene_bin_map(bin_bed, genes, gtf):
+    """Bin order, names and the gene->bin CSR overlap map (host integer logic of
+    R/Gene_bin_cell_rna_filtered.R:28-64)."""
+    chrom, start, end = _bed_columns(bin_bed)
+    chrom, start, end, _ = sort_bins(chrom, start, end)
+    gene_ids = _first_column(genes)
+    gtf_cols = {k: (gtf[k] if k in gtf else None) for k in ("V1", "V3", "V4", "V5", "V9", "gene_id")} \
+        if isinstance(gtf, dict) else {k: (gtf[k] if k in gtf.columns else None)
+                                       for k in ("V1", "V3", "V4", "V5", "V9", "gene_id")}
+    gtf_cols = {k: v for k, v in gtf_cols.items() if v is not None}
+    seq, gs, ge = gene_sites(gene_ids, gtf_cols)
+    map_ptr, map_bin = overlap_map(chrom, start, end, seq, gs, ge)
+    rownames = [f"chr{c}-{r_as_character(s)}-{r_as_character(e)}" for c, s, e in zip(chrom, start, end)]
+    return rownames, map_ptr, map_bin
+
+
+def bin_counts_csc(G, N, B, colptr, rowidx, x, map_ptr, map_bin):
+    """cs_bin_counts_begin / cs_bin_counts_fetch on dgCMatrix-style slots."""
+    L = _lib.lib()
+    colptr = np.ascontiguousarray(colptr, dtype=np.int32)
+    rowidx = np.ascontiguousarray(rowidx, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    map_ptr = np.ascontiguousarray(map_ptr, dtype=np.int32)
+    map_bin = np.ascontiguousarray(map_bin, dtype=np.int32)
+    job = C.c_void_p()
+    nnz = C.c_int64(0)
+    _check(L.cs_bin_counts_begin(G, N, B, _ptr(colptr, C.c_int32), _ptr(rowidx, C.c_int32),
+                                 _ptr(x, C.c_double), _ptr(map_ptr, C.c_int32), _ptr(map_bin, C.c_int32),
+                                 C.byref(job), C.byref(nnz)))
+    ocp = np.zeros(N + 1, dtype=np.int32)
+    ori = np.zeros(max(nnz.value, 1), dtype=np.int32)
+    ox = np.zeros(max(nnz.value, 1), dtype=np.float64)
+    _check(L.cs_bin_counts_fetch(job, _ptr(ocp, C.c_int32), _ptr(ori, C.c_int32), _ptr(ox, C.c_double)))
+    return ocp, ori[:nnz.value], ox[:nnz.value]
+
+
+def Gen_bin_cell_rna_filtered(bin_bed=None, barcodes=None, gene_matrix=None, genes=None, gtf=None):
+    """Generate the bin-by-cell count matrix (reference R/Gene_bin_cell_rna_filtered.R:16-85).
+
+    `gene_matrix` is a gene x cell scipy.sparse matrix (the reference's dgCMatrix);
+    returns a NamedMatrix whose `.values` is a bin x cell scipy.sparse.csc_matrix with
+    rownames `chr{chr}-{start}-{end}` and colnames = barcodes.
+    """
+    import scipy.sparse as sp
+
+    barcodes = _first_column(barcodes)
+    print("Read gene by cell matrix...")
+    n_genes = len(_first_column(genes))
+    print(f"Total {len(barcodes)} cells.")
+    print(f"Total {n_genes} genes.")
+    rownames, map_ptr, map_bin = gene_bin_map(bin_bed, genes, gtf)
+    m = sp.csc_matrix(gene_matrix)
+    m.sum_duplicates()
+    m.sort_indices()
+    G, N = m.shape
+    if G != n_genes:
+        raise ValueError(f"gene_matrix has {G} rows but genes has {n_genes}")
+    B = len(rownames)
+    print("Generate bin-by-cell matrix...", end="")
+    ocp, ori, ox = bin_counts_csc(G, N, B, m.indptr, m.indices, m.data.astype(np.float64), map_ptr, map_bin)
+    out = sp.csc_matrix((ox, ori, ocp), shape=(B, N))
+    print("\nThe bin-by-cell matrix has beed successfully generated!")
+    return NamedMatrix(out, rownames, barcodes)
+
+
+# --------------------------------------------------------------------------- a2
+def PrepCovMatrix(deltas_all=None, ngene_filter=200, ncell_filter=None, prep_mode="intersect"):
+    """Filter the output of EstRegionCov and assemble the cell x segment matrix
+    (reference R/PrepCovMatrix.R:11-58; no arithmetic).
+
+    deltas_all: dict(deltas_all=list of (names, values) pairs — one named vector per
+    segment —, ngenes=array, seg_table_filtered=dict of equal-length columns incl.
+    chr/start/end).  Returns dict(df=NamedMatrix N x R, ngene_filter, ncell_filter,
+    seg_table_filtered).
+    """
+    df = list(deltas_all["deltas_all"])
+    ngenes = np.asarray(deltas_all["ngenes"])
+    seg = {k: np.asarray(v) for k, v in deltas_all["seg_table_filtered"].items()}
+    if ncell_filter is None:
+        ncells = np.array([len(n) for n, _ in df], dtype=np.float64)
+        ncell_filter = ncells.max() - ncells.max() * 0.1
+    print(f"Selecting regions with > {r_as_character(ngene_filter)} genes \n")
+    print(f"Selecting regions with > {r_as_character(ncell_filter)} cells \n")
+    keep = np.array([len(n) > ncell_filter for n, _ in df], dtype=bool)
+    df = [d for d, k in zip(df, keep) if k]
+    ngenes = ngenes[keep]
+    seg = {k: v[keep] for k, v in seg.items()}
+    if prep_mode == "union":
+        seen, cells = set(), []
+        for names, _ in df:
+            for b in names:
+                if b not in seen:
+                    seen.add(b)
+                    cells.append(b)
+    elif prep_mode == "intersect":
+        cells = list(df[0][0]) if df else []
+        for names, _ in df[1:]:
+            s = set(names)
+            cells = [b for b in cells if b in s]
+    else:
+        raise ValueError("Please specify the prep_mode as either union or intersect!")
+    pos = {b: i for i, b in enumerate(cells)}
+    mat = np.full((len(cells), len(df)), np.nan)
+    for j, (names, vals) in enumerate(df):
+        vals = np.asarray(vals, dtype=np.float64)
+        seen = set()
+        for b, v in zip(names, vals):  # match() takes the first occurrence of a name
+            i = pos.get(b)
+            if i is not None and b not in seen:
+                mat[i, j] = v
+                seen.add(b)
+    sel = ngenes > ngene_filter
+    mat = mat[:, sel]
+    seg = {k: v[sel] for k, v in seg.items()}
+    colnames = [f"chr{r_as_character(c)}-{r_as_character(s)}-{r_as_character(e)}"
+                for c, s, e in zip(seg["chr"], seg["start"], seg["end"])]
+    print("Matrix generated!")
+    return dict(df=NamedMatrix(mat, cells, colnames), ngene_filter=ngene_filter, ncell_filter=ncell_filter,
+                seg_table_filtered=seg)
+
+
+# --------------------------------------------------------------------------- log-likelihood matrix
+def loglik_matrix(Xir, U, sigmas):
+    """LL[i,k] = sum_r dnorm(Xir[i,r], U[k,r], sigmas[r], log=TRUE), NA skipped (device)."""
+    X = np.asfortranarray(np.asarray(Xir, dtype=np.float64))
+    U = np.asfortranarray(np.atleast_2d(np.asarray(U, dtype=np.float64)))
+    N, R = X.shape
+    K = U.shape[0]
+    if U.shape[1] != R:
+        raise ValueError("U must have as many columns as Xir")
+    sig = np.ascontiguousarray(np.broadcast_to(np.asarray(sigmas, dtype=np.float64), (R,)))
+    LL = np.zeros((N, K), dtype=np.float64, order="F")
+    _check(_lib.lib().cs_loglik_matrix(N, R, K, _ptr(X, C.c_double), _ptr(U, C.c_double), _ptr(sig, C.c_double),
+                                       _ptr(LL, C.c_double)))
+    return LL
+
+
+# --------------------------------------------------------------------------- a3
+def _values(obj):
+    if isinstance(obj, NamedMatrix):
+        return np.asarray(obj.values, dtype=np.float64), obj.rownames, obj.colnames
+    if hasattr(obj, "to_numpy"):
+        return obj.to_numpy(dtype=np.float64), [str(i) for i in obj.index], [str(c) for c in obj.columns]
+    a = np.asarray(obj, dtype=np.float64)
+    return a, None, None
+
+
+def _expand_U(kt, R, labels, rows):
+    U = np.full((kt, R), np.nan)
+    if len(labels):
+        U[np.asarray(labels) - 1] = rows
+    return U
+
+
+def BayesNonparCluster(Xir=None, cna_states_WGS=None, alpha=2, beta=2, niter=200, sigmas0=None, U0=None,
+                       Z0=None, clust_mode="all", seed=200, verbose=False, *, rng="philox", device=None,
+                       kcap=None, _flags=0):
+    """Nested-CRP Gibbs clustering on coverage (reference R/BayesNonparCluster.R:21-289).
+
+    Same arguments and return object as the reference; the trailing keyword-only options
+    are additions: rng="R" consumes base R's Mersenne-Twister stream exactly like the
+    reference (bit-identical Zall for the same seed), rng="philox" (default) is the fast
+    counter-based stream.
+    Returns dict(results=dict(Zall, Uall, sigma_all, Likelihood), priors=dict(...), data).
+    """
+    X, rownames, colnames = _values(Xir)
+    if X.ndim != 2:
+        raise ValueError("Xir must be a matrix")
+    N, R = X.shape
+    cna = None if cna_states_WGS is None else np.asarray(cna_states_WGS, dtype=np.float64).ravel()
+    # priors (:32-59)
+    if U0 is None:
+        wU0 = False
+        if cna is not None and cna.size:
+            U0m = np.vstack([np.ones(R), cna])  # matrix(c(rep(1,R), cna), byrow=T, ncol=R)
+            if cna.size != R:
+                raise ValueError("cna_states_WGS must have one value per column of Xir")
+        else:
+            U0m = np.ones((1, R))
+            cna = U0m[0].copy()
+    else:
+        U0m = np.atleast_2d(np.asarray(_values(U0)[0], dtype=np.float64))
+        if U0m.shape[1] != R:
+            raise ValueError("Please specify a U0 matrix with ncol the same as that of Xir!")
+        wU0 = True
+        nn = np.nonzero(~np.isnan(U0m[:, 0]))[0]
+        U0m = U0m[: nn.max() + 1]
+        if cna is None or cna.size != R:
+            print("Invalid/no cna_states_WGS detected. Use the one the same as that in the U0.")
+            cna = U0m[nn[1]].copy() if U0m.shape[0] != 1 else U0m[0].copy()
+    if sigmas0 is not None:
+        s0 = np.asarray(sigmas0, dtype=np.float64).ravel()
+        if s0.size == 1:
+            s0 = np.repeat(s0, R)
+        elif s0.size != R:
+            raise ValueError("Please specify sigmas0 with length R or length 1.")
+    else:
+        s0 = np.full(R, 0.25)
+    # Z0 (:91-112)
+    if Z0 is None:
+        live = np.nonzero(~np.isnan(U0m[:, 0]))[0]
+        PP = np.full((N, U0m.shape[0]), np.nan)
+        PP[:, live] = loglik_matrix(X, U0m[live], s0)
+        Z0v = (np.nanargmax(PP, axis=1) + 1).astype(np.int32)
+    else:
+        Z0v = np.asarray(Z0).ravel()
+        if Z0v.size != N:
+            raise ValueError("Please specify a vector with length the same as the number of cells!")
+        Z0v = np.where(np.isnan(Z0v.astype(np.float64)), 0, Z0v).astype(np.int32)
+    if np.isnan(U0m).any():
+        raise ClonalscopeError(_lib.CS_ERR_STATE, "U0 holds NA rows below its last non-NA row")
+
+    K0 = U0m.shape[0]
+    Xf = np.asfortranarray(X)
+    U0f = np.asfortranarray(U0m)
+    Zall = np.zeros((niter, N), dtype=np.int32, order="F")
+    sigma_all = np.zeros((R, niter), dtype=np.float64, order="F")
+    LL = np.zeros(niter, dtype=np.float64)
+    L0 = C.c_double(0.0)
+    kt_all = np.zeros(niter, dtype=np.int32)
+    ucap = int(niter) * 160 + 4096
+    u_off = np.zeros(niter + 1, dtype=np.int64)
+    u_labels = np.zeros(ucap, dtype=np.int32)
+    u_rows = np.zeros((ucap, R), dtype=np.float64)
+    nrej = C.c_int64(0)
+    opts = _lib.GibbsOpts()
+    opts.rng_mode = {"r": _lib.RNG_R, "philox": _lib.RNG_PHILOX}[str(rng).lower()]
+    opts.device = -1 if device is None else int(device)
+    opts.kcap = 0 if kcap is None else int(kcap)
+    opts.flags = int(_flags)
+    rng_state = np.zeros(625, dtype=np.int32)
+    _check(_lib.lib().cs_ncrp_gibbs(
+        N, R, _ptr(Xf, C.c_double), K0, _ptr(U0f, C.c_double), _ptr(Z0v, C.c_int), _ptr(s0, C.c_double),
+        C.c_double(alpha), C.c_double(beta), int(niter), C.c_uint32(int(seed) & 0xFFFFFFFF), C.byref(opts),
+        _ptr(Zall, C.c_int), _ptr(sigma_all, C.c_double), _ptr(LL, C.c_double), C.byref(L0),
+        _ptr(kt_all, C.c_int), C.c_int64(ucap), _ptr(u_off, C.c_int64), _ptr(u_labels, C.c_int),
+        _ptr(u_rows, C.c_double), C.byref(nrej), _ptr(rng_state, C.c_int32)))
+    Uall = []
+    for t in range(niter):
+        a, b = int(u_off[t]), int(u_off[t + 1])
+        Uall.append(_expand_U(int(kt_all[t]), R, u_labels[a:b], u_rows[a:b]))
+        if verbose:
+            print(f"Iteration:{t + 1}")
+            print(f"nclusters={int(kt_all[t])}")
+        elif (t + 1) % 20 == 0:
+            print(f"Iteration:{t + 1}")
+    single = np.unique(Z0v).size == 1
+    results = dict(Zall=np.ascontiguousarray(Zall), Uall=Uall,
+                   sigma_all=[sigma_all[:, t].copy() for t in range(niter)], Likelihood=LL,
+                   dimnames=dict(Zall=([f"Iter{t + 1}" for t in range(niter)], rownames),
+                                 U_cols=[f"R{r + 1}" for r in range(R)]))
+    priors = dict(Z0=Z0v, U0=(np.ones((1, R)) if single else U0m), sigmas0=s0, alpha=alpha, beta=beta,
+                  cna_states_WGS=cna, L0=L0.value, wU0=wU0, seed=seed)
+    out = dict(results=results, priors=priors, data=Xir if Xir is not None else X)
+    out["diagnostics"] = dict(n_reject=int(nrej.value), rng=str(rng),
+                              rng_state=rng_state if opts.rng_mode == _lib.RNG_R else None)
+    return out
+
+
+# --------------------------------------------------------------------------- a4
+def BayesNonparAlleleCluster(Xir_cov=None, Xir_allele=None, cna_states_WGS=None, alpha=1, beta=1, niter=200,
+                             sigmas0_cov=None, sigmas0_allele=None, U0=None, Z0=None, maxcp=6, seed=200, *,
+                             rng="philox", device=None, kcap=None):
+    """Allele-aware nested-CRP Gibbs clustering (reference R/BayesNonparAlleleCluster.R:20-307).
+    Parity of this path is unpinned by the reference (never called, no fixture)."""
+    Xc, rownames, colnames = _values(Xir_cov)
+    Xa = _values(Xir_allele)[0]
+    if Xc.shape != Xa.shape:
+        raise ValueError("Xir_cov and Xir_allele must have the same shape")
+    N, R = Xc.shape
+    ngrid = sum(c + 1 for c in range(maxcp + 1))  # (copies, major copies) states, :26-30
+    if U0 is None:
+        if cna_states_WGS is not None:
+            U0m = np.vstack([np.full(R, 4), np.asarray(cna_states_WGS).ravel()]).astype(np.int32)
+        else:
+            U0m = np.full((1, R), 4, dtype=np.int32)
+    else:
+        U0m = np.atleast_2d(np.asarray(U0)).astype(np.int32)
+    if U0m.shape[1] != R:
+        raise ValueError("Please specify a U0 matrix with ncol the same as that of Xir!")
+    if U0m.min() < 1 or U0m.max() > ngrid:
+        raise ValueError(f"U0 state ids must lie in 1..{ngrid}")
+
+    def _sig(s, default):
+        if s is None:
+            return np.full(R, default)
+        s = np.asarray(s, dtype=np.float64).ravel()
+        if s.size == 1:
+            return np.repeat(s, R)
+        if s.size != R:
+            raise ValueError("Please specify sigmas0 with length R or length 1.")
+        return s
+
+    sc, sa = _sig(sigmas0_cov, 0.3), _sig(sigmas0_allele, 0.15)
+    if Z0 is None:
+        Z0v = np.ones(N, dtype=np.int32)
+        Z0_given = 0
+    else:
+        Z0v = np.asarray(Z0).astype(np.int32).ravel()
+        if Z0v.size != N:
+            raise ValueError("Please specify a vector with length the same as the number of cells!")
+        Z0_given = 1
+    K0 = U0m.shape[0]
+    Zall = np.zeros((niter, N), dtype=np.int32, order="F")
+    sig_cov_all = np.zeros((R, niter), order="F")
+    sig_all_all = np.zeros((R, niter), order="F")
+    LL = np.zeros(niter)
+    L0 = C.c_double(0.0)
+    kt_all = np.zeros(niter, dtype=np.int32)
+    ucap = int(niter) * 160 + 4096
+    u_off = np.zeros(niter + 1, dtype=np.int64)
+    u_labels = np.zeros(ucap, dtype=np.int32)
+    u_state = np.zeros((ucap, R), dtype=np.int32)
+    u_cov = np.zeros((ucap, R))
+    u_allele = np.zeros((ucap, R))
+    opts = _lib.GibbsOpts()
+    opts.rng_mode = {"r": _lib.RNG_R, "philox": _lib.RNG_PHILOX}[str(rng).lower()]
+    opts.device = -1 if device is None else int(device)
+    opts.kcap = 0 if kcap is None else int(kcap)
+    opts.flags = Z0_given << 8
+    Xcf, Xaf, U0f = np.asfortranarray(Xc), np.asfortranarray(Xa), np.asfortranarray(U0m)
+    _check(_lib.lib().cs_ncrp_gibbs_allele(
+        N, R, _ptr(Xcf, C.c_double), _ptr(Xaf, C.c_double), K0, _ptr(U0f, C.c_int), _ptr(Z0v, C.c_int),
+        _ptr(sc, C.c_double), _ptr(sa, C.c_double), C.c_double(alpha), C.c_double(beta), int(niter),
+        C.c_uint32(int(seed) & 0xFFFFFFFF), int(maxcp), C.byref(opts), _ptr(Zall, C.c_int),
+        _ptr(sig_cov_all, C.c_double), _ptr(sig_all_all, C.c_double), _ptr(LL, C.c_double), C.byref(L0),
+        _ptr(kt_all, C.c_int), C.c_int64(ucap), _ptr(u_off, C.c_int64), _ptr(u_labels, C.c_int),
+        _ptr(u_state, C.c_int), _ptr(u_cov, C.c_double), _ptr(u_allele, C.c_double)))
+    Uall, Ucov, Uallele = [], [], []
+    for t in range(niter):
+        a, b = int(u_off[t]), int(u_off[t + 1])
+        kt = int(kt_all[t])
+        Uall.append(_expand_U(kt, R, u_labels[a:b], u_state[a:b].astype(np.float64)))
+        Ucov.append(_expand_U(kt, R, u_labels[a:b], u_cov[a:b]))
+        Uallele.append(_expand_U(kt, R, u_labels[a:b], u_allele[a:b]))
+        print(f"Iteration:{t + 1}")
+    results = dict(Zall=np.ascontiguousarray(Zall), Uall=Uall, Ucov=Ucov, Uallele=Uallele,
+                   sigma_cov_all=[sig_cov_all[:, t].copy() for t in range(niter)],
+                   sigma_allele_all=[sig_all_all[:, t].copy() for t in range(niter)], Likelihood=LL)
+    priors = dict(Z0=Z0v, U0=U0m, sigmas0_cov=sc, sigmas0_allele=sa, alpha=alpha, beta=beta,
+                  cna_states_WGS=cna_states_WGS, L0=L0.value, seed=seed)
+    return dict(results=results, priors=priors, data=dict(Xir_cov=Xir_cov, Xir_allele=Xir_allele))
+
+
+# --------------------------------------------------------------------------- a5 / a6
+def MCMCtrim(clusteringObj=None, burnin=None, thinning=1, allele=False):
+    """Drop burn-in sweeps and thin (reference R/MCMCtrim.R:14-65).
+
+    Kept for parity: Zall is thinned first and the ALREADY-thinned nrow(Zall) is then used
+    to index the per-sweep lists (:33-36), so with thinning > 1 those lists come out shorter
+    than Zall; a no-op for the default thinning = 1.
+    """
+    res = dict(clusteringObj["results"])
+    nrow = res["Zall"].shape[0]
+    if burnin is None:
+        burnin = min(100, nrow / 2)
+    if burnin >= nrow:
+        raise ValueError("burnin values is too large! Please specify a number < number of iterations.")
+    b = int(burnin)  # -c(1:burnin) with a fractional burnin truncates like R's integer indexing
+    lists = ["Uall", "Ucov", "Uallele", "sigma_cov_all", "sigma_allele_all", "Likelihood"] if allele \
+        else ["Uall", "sigma_all", "Likelihood"]
+    res["Zall"] = res["Zall"][b:]
+    for k in lists:
+        res[k] = res[k][b:]
+
+    def thin_idx(n):
+        return [i * thinning for i in range(int(math.ceil(n / thinning)))]
+
+    res["Zall"] = res["Zall"][thin_idx(res["Zall"].shape[0])]
+    idx = thin_idx(res["Zall"].shape[0])  # reference quirk: nrow of the thinned Zall
+    for k in lists:
+        v = res[k]
+        if isinstance(v, np.ndarray):
+            res[k] = v[[i for i in idx if i < len(v)]]
+        else:
+            res[k] = [v[i] for i in idx if i < len(v)]
+    if "dimnames" in res:
+        dn = dict(res["dimnames"])
+        it, cells = dn["Zall"]
+        it = it[b:]
+        dn["Zall"] = ([it[i] for i in thin_idx(len(it))], cells)
+        res["dimnames"] = dn
+    out = dict(clusteringObj)
+    out["results"] = res
+    out["trim"] = dict(burnin=burnin, thinning=thinning)
+    print("Object was succefully trimmed and thinned!")
+    return out
+
+
+def majority_vote(Zall):
+    """Per-cell most frequent label over the kept sweeps, ties -> smallest label
+    (reference R/AssignCluster.R:37; the posterior assignment tally)."""
+    Z = np.asfortranarray(np.asarray(Zall, dtype=np.int32))
+    T, N = Z.shape
+    out = np.zeros(N, dtype=np.int32)
+    _check(_lib.lib().cs_majority_vote(T, N, _ptr(Z, C.c_int), _ptr(out, C.c_int)))
+    return out

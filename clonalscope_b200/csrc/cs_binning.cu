@@ -1,0 +1,623 @@
+// cs_binning.cu — gene -> bin aggregation of a sparse gene x cell count matrix.
+//
+// Replaces the hot loop of Gen_bin_cell_rna_filtered (reference
+// R/Gene_bin_cell_rna_filtered.R:63-81): the reference densifies genes x cells (:69)
+// and then, for every bin, sums the rows of the genes overlapping it (:71-77) before
+// converting back to a sparse Matrix (:79-81).  Here each CSC column (cell) is
+// aggregated independently on one CTA:
+//
+//   pass 1  bin_count_kernel   rowidx only (4 B/nz): marks touched bins in a shared
+//                              bitmap, popcounts -> upper bound of nnz per column
+//   scan    exclusive scan of the per-column counts -> out_colptr
+//   pass 2  bin_fill_kernel    128-bit loads of rowidx/x, gene->bin lookup through a
+//                              packed per-gene word (first_bin | nhits<<20), shared
+//                              memory integer accumulators (ATOMS.ADD), bitmap
+//                              compaction with a warp-shuffle scan, coalesced stores
+//
+// Integer counts carried in doubles are summed exactly in int32 accumulators; every
+// value is checked for integrality / range and every column for overflow, and any
+// violation re-runs the column set through the FP64-accumulator instantiation.
+// A touched bin whose sum is zero (explicit zeros, cancelling negatives) is dropped
+// as Matrix(sparse=TRUE) does; that rare case triggers a compaction pass.
+#include "cs_common.cuh"
+
+#include <vector>
+
+namespace {
+
+constexpr uint32_t GMAP_ESC = 0xFFFFFFFFu;
+constexpr int FILL_THREADS = 512;
+constexpr int COUNT_THREADS = 128;
+
+enum { FLAG_INEXACT = 0, FLAG_SHRUNK = 1, FLAG_CAP = 2, NFLAGS = 4 };
+
+// ---- pass 1 ---------------------------------------------------------------
+__global__ void __launch_bounds__(COUNT_THREADS)
+bin_count_kernel(int N, int B, const int64_t *__restrict__ colptr,
+                 const int32_t *__restrict__ rowidx, const uint32_t *__restrict__ gmap,
+                 const int32_t *__restrict__ map_ptr, const int32_t *__restrict__ map_bin,
+                 int *__restrict__ counts)
+{
+    extern __shared__ uint32_t s_bits[];
+    __shared__ int s_warp[COUNT_THREADS / 32];
+    const int words = (B + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += COUNT_THREADS) s_bits[w] = 0;
+    __syncthreads();
+    for (int c = blockIdx.x; c < N; c += gridDim.x) {
+        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += COUNT_THREADS) {
+            const int g = rowidx[e];
+            const uint32_t w = __ldg(gmap + g);
+            if (w != GMAP_ESC) {
+                const int b0 = w & 0xFFFFF, nh = w >> 20;
+                for (int t = 0; t < nh; t++) {
+                    const int b = b0 + t;
+                    atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+                }
+            } else {
+                for (int m = map_ptr[g]; m < map_ptr[g + 1]; m++) {
+                    const int b = map_bin[m];
+                    atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+                }
+            }
+        }
+        __syncthreads();
+        int cnt = 0;
+        for (int w = threadIdx.x; w < words; w += COUNT_THREADS) {
+            cnt += __popc(s_bits[w]);
+            s_bits[w] = 0;
+        }
+        for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(CS_FULL, cnt, off);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int i = 0; i < COUNT_THREADS / 32; i++) t += s_warp[i];
+            counts[c] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- exclusive scan int32[N] -> int64[N+1] ---------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *s_warp, int64_t &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t inc = v;
+    for (int off = 1; off < 32; off <<= 1) {
+        int64_t t = __shfl_up_sync(CS_FULL, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+        int64_t winc = w;
+        for (int off = 1; off < 32; off <<= 1) {
+            int64_t t = __shfl_up_sync(CS_FULL, winc, off);
+            if (lane >= off) winc += t;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    int64_t r = s_warp[wid] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tiles_kernel(int N, const int *__restrict__ counts, int64_t *__restrict__ out,
+                  int64_t *__restrict__ tile_sums)
+{
+    __shared__ int64_t s_warp[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = (base + i < N) ? counts[base + i] : 0;
+        s += v[i];
+    }
+    int64_t total;
+    int64_t ex = block_exclusive_scan(s, s_warp, total);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < N) out[base + i] = ex;
+        ex += v[i];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_sums_kernel(int ntiles, int64_t *__restrict__ tile_sums, int64_t *__restrict__ grand)
+{
+    __shared__ int64_t s_warp[33];
+    int64_t carry = 0;
+    for (int base = 0; base < ntiles; base += SCAN_THREADS) {
+        const int i = base + threadIdx.x;
+        int64_t v = (i < ntiles) ? tile_sums[i] : 0, total;
+        int64_t ex = block_exclusive_scan(v, s_warp, total);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_add_kernel(int N, int64_t *__restrict__ out, const int64_t *__restrict__ tile_sums,
+                const int64_t *__restrict__ grand)
+{
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int64_t add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < N) out[base + i] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[N] = *grand;
+}
+
+// ---- pass 2 ---------------------------------------------------------------
+template <typename Acc>
+struct AccOps;
+template <>
+struct AccOps<int> {
+    // returns false when v cannot be accumulated exactly as an int32
+    static __device__ __forceinline__ bool conv(double v, int &iv)
+    {
+        iv = (int)v; // saturating cvt.rzi
+        return (double)iv == v && v < 1073741824.0 && v > -1073741824.0;
+    }
+    static __device__ __forceinline__ bool add(int *a, int iv) { return atomicAdd(a, iv) == 0; }
+    static __device__ __forceinline__ double mag(int iv) { return fabs((double)iv); }
+};
+template <>
+struct AccOps<double> {
+    static __device__ __forceinline__ bool conv(double v, double &iv)
+    {
+        iv = v;
+        return true;
+    }
+    // the "first toucher" test cannot rely on the old value for doubles (a partial sum
+    // may pass through zero), so the bitmap bit is set unconditionally
+    static __device__ __forceinline__ bool add(double *a, double v)
+    {
+        atomicAdd(a, v);
+        return true;
+    }
+    static __device__ __forceinline__ double mag(double) { return 0.0; }
+};
+
+template <typename Acc>
+__device__ __forceinline__ void scatter_entry(int g, double v, Acc *s_acc, uint32_t *s_bits,
+                                              const uint32_t *__restrict__ gmap,
+                                              const int32_t *__restrict__ map_ptr,
+                                              const int32_t *__restrict__ map_bin, bool &inexact,
+                                              double &magsum)
+{
+    Acc iv;
+    if (!AccOps<Acc>::conv(v, iv)) inexact = true;
+    const uint32_t w = __ldg(gmap + g);
+    if (w != GMAP_ESC) {
+        const int b0 = w & 0xFFFFF, nh = w >> 20;
+        for (int t = 0; t < nh; t++) {
+            const int b = b0 + t;
+            if (AccOps<Acc>::add(&s_acc[b], iv)) atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+        }
+        magsum += AccOps<Acc>::mag(iv) * nh;
+    } else {
+        const int m0 = map_ptr[g], m1 = map_ptr[g + 1];
+        for (int m = m0; m < m1; m++) {
+            const int b = map_bin[m];
+            if (AccOps<Acc>::add(&s_acc[b], iv)) atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+        }
+        magsum += AccOps<Acc>::mag(iv) * (m1 - m0);
+    }
+}
+
+template <typename Acc>
+__global__ void __launch_bounds__(FILL_THREADS)
+bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
+                const int32_t *__restrict__ rowidx, const double *__restrict__ x,
+                const uint32_t *__restrict__ gmap, const int32_t *__restrict__ map_ptr,
+                const int32_t *__restrict__ map_bin, const int64_t *__restrict__ out_colptr,
+                int32_t *__restrict__ out_rowidx, double *__restrict__ out_x, int64_t out_cap,
+                int *__restrict__ counts_actual, int *__restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int words = (B + 31) >> 5;
+    Acc *s_acc = reinterpret_cast<Acc *>(s_raw);
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_acc + B);
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_bits + words);
+    __shared__ int s_warp[FILL_THREADS / 32 + 1];
+    __shared__ double s_mag[FILL_THREADS / 32];
+
+    if (out_colptr[N] > out_cap) { // caller's buffers too small: report, write nothing
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[FLAG_CAP] = 1;
+        return;
+    }
+    for (int b = threadIdx.x; b < B; b += FILL_THREADS) s_acc[b] = 0;
+    for (int w = threadIdx.x; w < words; w += FILL_THREADS) s_bits[w] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wpt = (words + FILL_THREADS - 1) / FILL_THREADS; // bitmap words per thread
+
+    for (int c = blockIdx.x; c < N; c += gridDim.x) {
+        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+        bool inexact = false;
+        double magsum = 0.0;
+        // 128-bit body: 4 row indices + 4 values per thread per step
+        const int64_t eb = min((e0 + 3) & ~(int64_t)3, e1), ee = max(eb, e1 & ~(int64_t)3);
+        for (int64_t e = eb + 4 * (int64_t)threadIdx.x; e < ee; e += 4 * FILL_THREADS) {
+            const int4 g4 = __ldcs(reinterpret_cast<const int4 *>(rowidx + e));
+            const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(x + e));
+            const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(x + e + 2));
+            scatter_entry<Acc>(g4.x, v01.x, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
+            scatter_entry<Acc>(g4.y, v01.y, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
+            scatter_entry<Acc>(g4.z, v23.x, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
+            scatter_entry<Acc>(g4.w, v23.y, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
+        }
+        { // unaligned head and tail (at most 3 + 3 entries)
+            const int nhead = (int)(eb - e0), ntail = (int)(e1 - ee);
+            if ((int)threadIdx.x < nhead + ntail) {
+                const int64_t e = ((int)threadIdx.x < nhead) ? e0 + threadIdx.x
+                                                             : ee + (threadIdx.x - nhead);
+                scatter_entry<Acc>(rowidx[e], x[e], s_acc, s_bits, gmap, map_ptr, map_bin, inexact,
+                                   magsum);
+            }
+        }
+        // exactness guard: every value integral and the column cannot overflow int32
+        for (int off = 16; off >= 1; off >>= 1) magsum += __shfl_xor_sync(CS_FULL, magsum, off);
+        if (lane == 0) s_mag[wid] = magsum;
+        if (inexact) flags[FLAG_INEXACT] = 1;
+        __syncthreads();
+
+        // compaction: drop zero sums, count, scan, list ascending bins
+        int cnt = 0;
+        const int w0 = threadIdx.x * wpt;
+        for (int j = 0; j < wpt; j++) {
+            const int w = w0 + j;
+            if (w >= words) break;
+            uint32_t bits = s_bits[w], keep = bits;
+            while (bits) {
+                const int t = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (s_acc[(w << 5) + t] == (Acc)0) keep &= ~(1u << t);
+            }
+            s_bits[w] = keep;
+            cnt += __popc(keep);
+        }
+        int inc = cnt;
+        for (int off = 1; off < 32; off <<= 1) {
+            int t = __shfl_up_sync(CS_FULL, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = (lane < FILL_THREADS / 32) ? s_warp[lane] : 0, winc = w;
+            for (int off = 1; off < 32; off <<= 1) {
+                int t = __shfl_up_sync(CS_FULL, winc, off);
+                if (lane >= off) winc += t;
+            }
+            if (lane < FILL_THREADS / 32) s_warp[lane] = winc - w;
+            if (lane == FILL_THREADS / 32 - 1) s_warp[FILL_THREADS / 32] = winc;
+            double m = (lane < FILL_THREADS / 32) ? s_mag[lane] : 0.0;
+            for (int off = 16; off >= 1; off >>= 1) m += __shfl_xor_sync(CS_FULL, m, off);
+            if (lane == 0 && m >= 2147483647.0) flags[FLAG_INEXACT] = 1;
+        }
+        __syncthreads();
+        int rank = s_warp[wid] + inc - cnt;
+        const int total = s_warp[FILL_THREADS / 32];
+        for (int j = 0; j < wpt; j++) {
+            const int w = w0 + j;
+            if (w >= words) break;
+            uint32_t bits = s_bits[w];
+            s_bits[w] = 0;
+            while (bits) {
+                const int t = __ffs(bits) - 1;
+                bits &= bits - 1;
+                s_list[rank++] = (uint16_t)((w << 5) + t);
+            }
+        }
+        __syncthreads();
+        const int64_t o = out_colptr[c];
+        for (int i = threadIdx.x; i < total; i += FILL_THREADS) {
+            const int b = s_list[i];
+            __stcs(out_rowidx + o + i, b);
+            __stcs(out_x + o + i, (double)s_acc[b]);
+        }
+        // re-zero every accumulator this column touched (incl. dropped zero sums)
+        if (total == (int)(out_colptr[c + 1] - o)) {
+            for (int i = threadIdx.x; i < total; i += FILL_THREADS) s_acc[s_list[i]] = 0;
+        } else {
+            for (int b = threadIdx.x; b < B; b += FILL_THREADS) s_acc[b] = 0;
+            if (threadIdx.x == 0) flags[FLAG_SHRUNK] = 1;
+        }
+        if (threadIdx.x == 0) counts_actual[c] = total;
+        __syncthreads();
+    }
+}
+
+// moves column c from the padded offsets (old_colptr) to the compact ones
+__global__ void compact_columns_kernel(int N, const int64_t *__restrict__ old_colptr,
+                                       const int64_t *__restrict__ new_colptr,
+                                       const int32_t *__restrict__ src_i,
+                                       const double *__restrict__ src_x,
+                                       int32_t *__restrict__ dst_i, double *__restrict__ dst_x)
+{
+    for (int c = blockIdx.x; c < N; c += gridDim.x) {
+        const int64_t so = old_colptr[c], d0 = new_colptr[c];
+        const int n = (int)(new_colptr[c + 1] - d0);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            dst_i[d0 + i] = src_i[so + i];
+            dst_x[d0 + i] = src_x[so + i];
+        }
+    }
+}
+
+} // namespace
+
+// ----------------------------------------------------------------- plan / API
+struct cs_bin_plan {
+    int G = 0, B = 0;
+    DevBuf<uint32_t> gmap;
+    DevBuf<int32_t> map_ptr, map_bin;
+    DevBuf<int> counts, counts2, flags;
+    DevBuf<int64_t> tile_sums, grand, colptr2;
+    DevBuf<int32_t> tmp_i;
+    DevBuf<double> tmp_x;
+    int *h_pinned = nullptr; // NFLAGS ints + 1 int64 (nnz)
+    ~cs_bin_plan()
+    {
+        if (h_pinned) cudaFreeHost(h_pinned);
+    }
+};
+
+static size_t fill_smem_bytes(int B, size_t acc_size)
+{
+    const size_t words = (B + 31) / 32;
+    return (size_t)B * acc_size + words * 4 + (size_t)B * 2 + 16;
+}
+
+extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const int32_t *map_bin,
+                                  cs_bin_plan **plan_out)
+{
+    CS_REQUIRE(plan_out != nullptr, "cs_bin_plan_create: plan is NULL");
+    *plan_out = nullptr;
+    CS_REQUIRE(G >= 0 && B >= 1 && map_ptr, "cs_bin_plan_create: bad G/B/map_ptr");
+    CS_REQUIRE(B <= 65535, "cs_bin_plan_create: B=%d bins exceeds the 65535 this build supports", B);
+    if (fill_smem_bytes(B, sizeof(int)) > 227 * 1024) {
+        cs_set_error("cs_bin_plan_create: B=%d bins need more than 227 KB of shared memory", B);
+        return CS_ERR_UNSUPPORTED;
+    }
+    const int nhits = map_ptr[G];
+    for (int g = 0; g < G; g++) CS_REQUIRE(map_ptr[g] <= map_ptr[g + 1], "map_ptr not monotone at gene %d", g);
+    for (int m = 0; m < nhits; m++)
+        CS_REQUIRE(map_bin[m] >= 0 && map_bin[m] < B, "map_bin[%d]=%d outside [0,%d)", m, map_bin[m], B);
+    std::vector<uint32_t> gm((size_t)G > 0 ? G : 1);
+    for (int g = 0; g < G; g++) {
+        const int m0 = map_ptr[g], nh = map_ptr[g + 1] - m0;
+        bool contig = nh < 4096;
+        for (int t = 1; t < nh && contig; t++) contig = map_bin[m0 + t] == map_bin[m0] + t;
+        gm[g] = nh == 0 ? 0u : (contig ? ((uint32_t)nh << 20) | (uint32_t)map_bin[m0] : GMAP_ESC);
+    }
+    cs_bin_plan *p = new cs_bin_plan();
+    p->G = G;
+    p->B = B;
+    int rc = CS_OK;
+    do {
+#define TRY(call) if ((call) != cudaSuccess) { cs_set_error("cs_bin_plan_create: %s", cudaGetErrorString(cudaGetLastError())); rc = CS_ERR_CUDA; break; }
+        TRY(p->gmap.alloc(G));
+        TRY(p->map_ptr.alloc(G + 1));
+        TRY(p->map_bin.alloc(nhits));
+        TRY(p->flags.alloc(NFLAGS));
+        TRY(p->grand.alloc(1));
+        TRY(cudaMallocHost((void **)&p->h_pinned, 64));
+        TRY(cudaMemcpy(p->gmap.p, gm.data(), sizeof(uint32_t) * G, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(p->map_ptr.p, map_ptr, sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice));
+        if (nhits) TRY(cudaMemcpy(p->map_bin.p, map_bin, sizeof(int32_t) * nhits, cudaMemcpyHostToDevice));
+#undef TRY
+    } while (0);
+    if (rc != CS_OK) {
+        delete p;
+        return rc;
+    }
+    *plan_out = p;
+    return CS_OK;
+}
+
+extern "C" void cs_bin_plan_destroy(cs_bin_plan *plan) { delete plan; }
+
+template <typename Acc>
+static int launch_fill(cs_bin_plan *p, int N, const int64_t *d_colptr, const int32_t *d_rowidx,
+                       const double *d_x, const int64_t *d_out_colptr, int32_t *d_out_rowidx,
+                       double *d_out_x, int64_t out_cap, cudaStream_t st)
+{
+    const size_t smem = fill_smem_bytes(p->B, sizeof(Acc));
+    if (smem > 227 * 1024) {
+        cs_set_error("cs_bin_counts: B=%d bins with FP64 accumulators need %zu B of shared memory", p->B, smem);
+        return CS_ERR_UNSUPPORTED;
+    }
+    CS_CUDA(cudaFuncSetAttribute(bin_fill_kernel<Acc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_fill_kernel<Acc>, FILL_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = cs_num_sms() * per_sm;
+    if (grid > N) grid = N;
+    bin_fill_kernel<Acc><<<grid, FILL_THREADS, smem, st>>>(
+        N, p->B, d_colptr, d_rowidx, d_x, p->gmap.p, p->map_ptr.p, p->map_bin.p, d_out_colptr,
+        d_out_rowidx, d_out_x, out_cap, p->counts2.p, p->flags.p);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+static int run_scan(cs_bin_plan *p, int N, const int *counts, int64_t *out, cudaStream_t st)
+{
+    const int ntiles = (N + SCAN_TILE - 1) / SCAN_TILE;
+    CS_CUDA(p->tile_sums.reserve(ntiles));
+    scan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(N, counts, out, p->tile_sums.p);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(ntiles, p->tile_sums.p, p->grand.p);
+    scan_add_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(N, out, p->tile_sums.p, p->grand.p);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
+                                 const int32_t *d_rowidx, const double *d_x,
+                                 int64_t *d_out_colptr, int32_t *d_out_rowidx, double *d_out_x,
+                                 int64_t out_cap, int64_t *nnz_out, void *stream)
+{
+    CS_REQUIRE(p && N >= 0 && d_colptr && d_out_colptr && nnz_out, "cs_bin_counts_dev: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) {
+        CS_CUDA(cudaMemsetAsync(d_out_colptr, 0, sizeof(int64_t), st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        *nnz_out = 0;
+        return CS_OK;
+    }
+    CS_CUDA(p->counts.reserve(N));
+    CS_CUDA(p->counts2.reserve(N));
+    CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
+    const int words = (p->B + 31) / 32;
+    int grid1 = cs_num_sms() * 16;
+    if (grid1 > N) grid1 = N;
+    bin_count_kernel<<<grid1, COUNT_THREADS, words * 4, st>>>(
+        N, p->B, d_colptr, d_rowidx, p->gmap.p, p->map_ptr.p, p->map_bin.p, p->counts.p);
+    CS_CUDA(cudaGetLastError());
+    int rc = run_scan(p, N, p->counts.p, d_out_colptr, st);
+    if (rc) return rc;
+    int64_t *h_nnz = reinterpret_cast<int64_t *>(p->h_pinned + NFLAGS);
+    if (!d_out_rowidx) {
+        CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        *nnz_out = *h_nnz;
+        return CS_OK;
+    }
+    CS_REQUIRE(d_out_x != nullptr, "cs_bin_counts_dev: d_out_x is NULL");
+    rc = launch_fill<int>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
+    if (rc) return rc;
+    CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaMemcpyAsync(p->h_pinned, p->flags.p, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    *nnz_out = *h_nnz;
+    if (p->h_pinned[FLAG_CAP]) {
+        cs_set_error("cs_bin_counts_dev: output capacity %lld < %lld entries needed", (long long)out_cap,
+                     (long long)*h_nnz);
+        return CS_ERR_UCAP;
+    }
+    if (p->h_pinned[FLAG_INEXACT]) { // non-integer / huge values: exact-order-free FP64 accumulators
+        CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
+        rc = launch_fill<double>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
+        if (rc) return rc;
+        CS_CUDA(cudaMemcpyAsync(p->h_pinned, p->flags.p, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+    }
+    if (p->h_pinned[FLAG_SHRUNK]) { // some touched bins summed to zero: close the gaps
+        const int64_t padded = *h_nnz;
+        CS_CUDA(p->colptr2.reserve((size_t)N + 1));
+        CS_CUDA(p->tmp_i.reserve((size_t)padded));
+        CS_CUDA(p->tmp_x.reserve((size_t)padded));
+        rc = run_scan(p, N, p->counts2.p, p->colptr2.p, st);
+        if (rc) return rc;
+        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, p->colptr2.p, d_out_rowidx,
+                                                                 d_out_x, p->tmp_i.p, p->tmp_x.p);
+        CS_CUDA(cudaGetLastError());
+        CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        *nnz_out = *h_nnz;
+        CS_CUDA(cudaMemcpyAsync(d_out_colptr, p->colptr2.p, sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyDeviceToDevice, st));
+        CS_CUDA(cudaMemcpyAsync(d_out_rowidx, p->tmp_i.p, sizeof(int32_t) * (size_t)*h_nnz, cudaMemcpyDeviceToDevice, st));
+        CS_CUDA(cudaMemcpyAsync(d_out_x, p->tmp_x.p, sizeof(double) * (size_t)*h_nnz, cudaMemcpyDeviceToDevice, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+    }
+    return CS_OK;
+}
+
+// ------------------------------------------------------- host (R-layout) form
+struct cs_bin_job {
+    int N = 0;
+    int64_t nnz = 0;
+    DevBuf<int64_t> out_colptr;
+    DevBuf<int32_t> out_rowidx;
+    DevBuf<double> out_x;
+};
+
+extern "C" int cs_bin_counts_begin(int G, int N, int B, const int32_t *colptr, const int32_t *rowidx,
+                                   const double *x, const int32_t *map_ptr, const int32_t *map_bin,
+                                   cs_bin_job **job_out, int64_t *nnz_out)
+{
+    CS_REQUIRE(job_out && nnz_out, "cs_bin_counts_begin: NULL output argument");
+    *job_out = nullptr;
+    CS_REQUIRE(G >= 0 && N >= 0 && B >= 1 && colptr && map_ptr, "cs_bin_counts_begin: bad dimensions");
+    CS_REQUIRE(colptr[0] == 0, "cs_bin_counts_begin: colptr[0] must be 0");
+    const int64_t nnz = colptr[N];
+    for (int c = 0; c < N; c++) CS_REQUIRE(colptr[c] <= colptr[c + 1], "colptr not monotone at column %d", c);
+    for (int64_t e = 0; e < nnz; e++)
+        CS_REQUIRE(rowidx[e] >= 0 && rowidx[e] < G, "rowidx[%lld]=%d outside [0,%d)", (long long)e, rowidx[e], G);
+    cs_bin_plan *plan = nullptr;
+    int rc = cs_bin_plan_create(G, B, map_ptr, map_bin, &plan);
+    if (rc) return rc;
+    struct PlanGuard {
+        cs_bin_plan *p;
+        ~PlanGuard() { cs_bin_plan_destroy(p); }
+    } guard{plan};
+    std::vector<int64_t> cp64((size_t)N + 1);
+    for (int c = 0; c <= N; c++) cp64[c] = colptr[c];
+    DevBuf<int64_t> d_colptr;
+    DevBuf<int32_t> d_rowidx;
+    DevBuf<double> d_x;
+    cs_bin_job *job = new cs_bin_job();
+    struct JobGuard {
+        cs_bin_job *j;
+        ~JobGuard() { delete j; }
+    } jguard{job};
+    job->N = N;
+    CS_CUDA(d_colptr.alloc((size_t)N + 1));
+    CS_CUDA(d_rowidx.alloc((size_t)nnz));
+    CS_CUDA(d_x.alloc((size_t)nnz));
+    CS_CUDA(job->out_colptr.alloc((size_t)N + 1));
+    CS_CUDA(cudaMemcpy(d_colptr.p, cp64.data(), sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice));
+    if (nnz) {
+        CS_CUDA(cudaMemcpy(d_rowidx.p, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CS_CUDA(cudaMemcpy(d_x.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    int64_t need = 0;
+    rc = cs_bin_counts_dev(plan, N, d_colptr.p, d_rowidx.p, d_x.p, job->out_colptr.p, nullptr, nullptr, 0, &need, nullptr);
+    if (rc) return rc;
+    CS_REQUIRE(need <= 2147483647LL, "cs_bin_counts_begin: result has %lld nonzeros, more than a dgCMatrix holds", (long long)need);
+    CS_CUDA(job->out_rowidx.alloc((size_t)need));
+    CS_CUDA(job->out_x.alloc((size_t)need));
+    rc = cs_bin_counts_dev(plan, N, d_colptr.p, d_rowidx.p, d_x.p, job->out_colptr.p, job->out_rowidx.p,
+                           job->out_x.p, need, &job->nnz, nullptr);
+    if (rc) return rc;
+    *nnz_out = job->nnz;
+    *job_out = job;
+    jguard.j = nullptr;
+    return CS_OK;
+}
+
+extern "C" int cs_bin_counts_fetch(cs_bin_job *job, int32_t *out_colptr, int32_t *out_rowidx, double *out_x)
+{
+    CS_REQUIRE(job && out_colptr, "cs_bin_counts_fetch: NULL argument");
+    struct JobGuard {
+        cs_bin_job *j;
+        ~JobGuard() { delete j; }
+    } jguard{job};
+    std::vector<int64_t> cp64((size_t)job->N + 1);
+    CS_CUDA(cudaMemcpy(cp64.data(), job->out_colptr.p, sizeof(int64_t) * cp64.size(), cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < cp64.size(); c++) out_colptr[c] = (int32_t)cp64[c];
+    if (job->nnz) {
+        CS_REQUIRE(out_rowidx && out_x, "cs_bin_counts_fetch: NULL output slots");
+        CS_CUDA(cudaMemcpy(out_rowidx, job->out_rowidx.p, sizeof(int32_t) * (size_t)job->nnz, cudaMemcpyDeviceToHost));
+        CS_CUDA(cudaMemcpy(out_x, job->out_x.p, sizeof(double) * (size_t)job->nnz, cudaMemcpyDeviceToHost));
+    }
+    return CS_OK;
+}
+
+extern "C" void cs_bin_counts_free(cs_bin_job *job) { delete job; }

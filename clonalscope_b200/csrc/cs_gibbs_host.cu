@@ -1,0 +1,331 @@
+// cs_gibbs_host.cu — host side of the nested-CRP Gibbs chain: device-resident chain
+// object (cs_chain_*) and the R-layout one-shot entry point cs_ncrp_gibbs.
+// Reference boundary: BayesNonparCluster, R/BayesNonparCluster.R:21-289.
+#include "cs_gibbs.cuh"
+
+#include <limits.h>
+#include <string.h>
+#include <vector>
+
+template <typename T>
+int cs_transpose(int rows, int cols, const T *d_in, T *d_out, cudaStream_t st);
+int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, cudaStream_t st);
+int cs_total_loglik_async(const ChainDev &D, const double *U, const int *Zrows, const double *sig, double *d_out,
+                          cudaStream_t st);
+int cs_rmode_run(const ChainDev &D, int lcap, int t0, int t1, int last_sweep, double *scratch, cudaStream_t st);
+void cs_r_set_seed(uint32_t seed, uint32_t mt[624]);
+
+struct cs_chain {
+    int N = 0, R = 0, kcap = 0, niter_cap = 0, rng_mode = 0, flags = 0;
+    int sweeps_done = 0;
+    bool inited = false;
+    cudaStream_t st = nullptr;
+    ChainDev D{};
+    DevBuf<double> X, Xc, Ua, Ub, sig, isig, Q, mean, psum, sigma_all, LL, u_rows, L0;
+    DevBuf<int> Zs, np, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
+    DevBuf<long long> u_off;
+    DevBuf<uint32_t> mt;
+    DevBuf<ChainScal> scal;
+    ~cs_chain()
+    {
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+static const int kDefaultKcapPhilox = 256, kDefaultLcapR = 4096;
+
+extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mode, cs_chain **out)
+{
+    CS_REQUIRE(out != nullptr, "cs_chain_create: NULL output");
+    *out = nullptr;
+    CS_REQUIRE(N >= 1 && R >= 1 && niter_cap >= 1, "cs_chain_create: bad dimensions N=%d R=%d niter=%d", N, R, niter_cap);
+    CS_REQUIRE(rng_mode == CS_RNG_R || rng_mode == CS_RNG_PHILOX, "cs_chain_create: unknown rng_mode %d", rng_mode);
+    if (kcap <= 0) kcap = rng_mode == CS_RNG_PHILOX ? kDefaultKcapPhilox : kDefaultLcapR;
+    if (rng_mode == CS_RNG_PHILOX && R > 1024) {
+        cs_set_error("Philox sampler supports up to 1024 segments (R=%d)", R);
+        return CS_ERR_UNSUPPORTED;
+    }
+    cs_chain *c = new cs_chain();
+    struct Guard {
+        cs_chain *c;
+        ~Guard() { delete c; }
+    } guard{c};
+    c->N = N;
+    c->R = R;
+    c->kcap = kcap;
+    c->niter_cap = niter_cap;
+    c->rng_mode = rng_mode;
+    CS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    const size_t nx = (size_t)N * R;
+    const int nchunks = (N + CS_STAT_CHUNK - 1) / CS_STAT_CHUNK;
+    const bool ph = rng_mode == CS_RNG_PHILOX;
+    const long long urec_cap = (long long)niter_cap * (ph ? (kcap < 128 ? kcap : 128) : 128) + kcap;
+    CS_CUDA(c->X.alloc(nx));
+    CS_CUDA(c->Xc.alloc(nx));
+    CS_CUDA(c->Ua.alloc((size_t)kcap * R));
+    CS_CUDA(c->Ub.alloc((size_t)kcap * R));
+    CS_CUDA(c->sig.alloc(R));
+    CS_CUDA(c->isig.alloc(R));
+    CS_CUDA(c->mean.alloc((size_t)kcap * R));
+    CS_CUDA(c->Zs.alloc(N));
+    CS_CUDA(c->np.alloc(kcap));
+    CS_CUDA(c->slot_label.alloc(kcap));
+    CS_CUDA(c->newslot.alloc(kcap));
+    CS_CUDA(c->scal.alloc(1));
+    CS_CUDA(c->mt.alloc(624));
+    CS_CUDA(c->L0.alloc(1));
+    CS_CUDA(c->psum.alloc(ph ? (size_t)nchunks * kcap * R : (size_t)nchunks + 16));
+    CS_CUDA(c->pcnt.alloc(ph ? (size_t)nchunks * kcap * R : 16));
+    if (ph) {
+        CS_CUDA(c->Q.alloc((size_t)N * kcap));
+        CS_CUDA(c->J.alloc(nx));
+        CS_CUDA(c->zspec.alloc(N));
+        CS_CUDA(c->qcols.alloc(N));
+        CS_CUDA(c->rej.alloc(N));
+    }
+    CS_CUDA(c->Zall.alloc((size_t)niter_cap * N));
+    CS_CUDA(c->sigma_all.alloc((size_t)niter_cap * R));
+    CS_CUDA(c->LL.alloc(niter_cap));
+    CS_CUDA(c->kt_all.alloc(niter_cap));
+    CS_CUDA(c->u_off.alloc((size_t)niter_cap + 1));
+    CS_CUDA(c->u_labels.alloc((size_t)urec_cap));
+    CS_CUDA(c->u_rows.alloc((size_t)urec_cap * R));
+    ChainDev &D = c->D;
+    D.N = N; D.R = R; D.kcap = kcap;
+    D.X = c->X.p; D.Zs = c->Zs.p; D.U = c->Ua.p; D.Unext = c->Ub.p; D.np = c->np.p;
+    D.slot_label = c->slot_label.p; D.sig = c->sig.p; D.isig = c->isig.p; D.Q = c->Q.p; D.J = c->J.p;
+    D.zspec = c->zspec.p; D.qcols = c->qcols.p; D.mean = c->mean.p; D.psum = c->psum.p; D.pcnt = c->pcnt.p;
+    D.newslot = c->newslot.p; D.mt = c->mt.p; D.scal = c->scal.p;
+    D.Zall = c->Zall.p; D.sigma_all = c->sigma_all.p; D.LL = c->LL.p; D.kt_all = c->kt_all.p;
+    D.u_off = c->u_off.p; D.u_labels = c->u_labels.p; D.u_rows = c->u_rows.p; D.urec_cap = urec_cap;
+    guard.c = nullptr;
+    *out = c;
+    return CS_OK;
+}
+
+extern "C" void cs_chain_destroy(cs_chain *c) { delete c; }
+
+static __global__ void isig_kernel(int R, const double *sig, double *isig)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) isig[r] = 1.0 / sig[r];
+}
+static __global__ void fill_kernel(size_t n, double *p, double v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" int cs_chain_init(cs_chain *c, const double *X, int K0, const double *U0, const int *Z0,
+                             const double *sigmas0, double alpha, double beta, uint32_t seed, int flags)
+{
+    CS_REQUIRE(c && X && U0 && Z0 && sigmas0, "cs_chain_init: NULL argument");
+    const int N = c->N, R = c->R;
+    CS_REQUIRE(K0 >= 1 && K0 <= c->kcap, "cs_chain_init: K0=%d outside [1, kcap=%d]", K0, c->kcap);
+    // the reference indexes U0[Z0,] (:133) and table(Zt)[1:nrow(U0)] (:150): labels outside
+    // 1..K0 give NA counts and an error further down
+    for (int i = 0; i < N; i++) {
+        if (Z0[i] < 1 || Z0[i] > K0) {
+            cs_set_error("Z0[%d]=%d is not a row of U0 (1..%d)", i + 1, Z0[i], K0);
+            return CS_ERR_STATE;
+        }
+    }
+    for (int r = 0; r < R; r++) CS_REQUIRE(sigmas0[r] > 0.0, "sigmas0[%d]=%g must be positive", r + 1, sigmas0[r]);
+    bool single = true;
+    for (int i = 1; i < N && single; i++) single = Z0[i] == Z0[0];
+    if (single && Z0[0] != 1) {
+        cs_set_error("all cells start in cluster %d != 1: the reference's npoints would be NA (R/BayesNonparCluster.R:141-151)", Z0[0]);
+        return CS_ERR_STATE;
+    }
+    cudaStream_t st = c->st;
+    ChainDev &D = c->D;
+    D.U = c->Ua.p;
+    D.Unext = c->Ub.p;
+    D.alpha = alpha;
+    D.beta = beta;
+    D.seed = seed;
+    D.single = single ? 1 : 0;
+    c->flags = flags;
+    c->sweeps_done = 0;
+    const bool ph = c->rng_mode == CS_RNG_PHILOX;
+    // X: column-major N x R (== row-major R x N) -> cell-major
+    CS_CUDA(cudaMemcpyAsync(c->Xc.p, X, sizeof(double) * (size_t)N * R, cudaMemcpyHostToDevice, st));
+    int rc = cs_transpose<double>(R, N, c->Xc.p, c->X.p, st);
+    if (rc) return rc;
+    // U0: column-major K0 x R -> rows
+    std::vector<double> Urows((size_t)K0 * R);
+    for (int k = 0; k < K0; k++)
+        for (int r = 0; r < R; r++) Urows[(size_t)k * R + r] = U0[(size_t)r * K0 + k];
+    CS_CUDA(cudaMemcpyAsync(D.U, Urows.data(), sizeof(double) * Urows.size(), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(D.sig, sigmas0, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    isig_kernel<<<(R + 127) / 128, 128, 0, st>>>(R, D.sig, D.isig);
+    // L0 at (U0, Z0, sigmas0)  (:133) — before the single-cluster replacement of U0
+    std::vector<int> zrows(N);
+    for (int i = 0; i < N; i++) zrows[i] = Z0[i] - 1;
+    CS_CUDA(cudaMemcpyAsync(D.Zs, zrows.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    rc = cs_total_loglik_async(D, D.U, D.Zs, D.sig, c->L0.p, st);
+    if (rc) return rc;
+    CS_CUDA(cudaStreamSynchronize(st)); // Urows / zrows are reused below
+    // state (:141-151)
+    std::vector<int> np(c->kcap, 0), lab(c->kcap, 0);
+    int kt;
+    if (single) {
+        kt = 1;
+        np[0] = N;
+        fill_kernel<<<(R + 127) / 128, 128, 0, st>>>((size_t)R, D.U, 1.0);
+    } else {
+        kt = K0;
+        for (int i = 0; i < N; i++) np[Z0[i] - 1]++;
+    }
+    for (int k = 0; k < c->kcap; k++) lab[k] = k + 1;
+    std::vector<int> zinit(N);
+    for (int i = 0; i < N; i++) zinit[i] = ph ? Z0[i] - 1 : Z0[i];
+    ChainScal h{};
+    h.nlive = kt;
+    h.kt = kt;
+    h.first_event = INT_MAX;
+    h.mt_pos = 624;
+    CS_CUDA(cudaMemcpyAsync(D.Zs, zinit.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(D.np, np.data(), sizeof(int) * c->kcap, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(D.slot_label, lab.data(), sizeof(int) * c->kcap, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(D.scal, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    uint32_t mt[624];
+    cs_r_set_seed(seed, mt);
+    CS_CUDA(cudaMemcpyAsync(D.mt, mt, sizeof(mt), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    CS_CUDA(cudaGetLastError());
+    c->inited = true;
+    return CS_OK;
+}
+
+extern "C" int cs_chain_run(cs_chain *c, int nsweeps, int is_last, int sync)
+{
+    CS_REQUIRE(c && c->inited, "cs_chain_run: chain not initialised");
+    CS_REQUIRE(nsweeps >= 0 && c->sweeps_done + nsweeps <= c->niter_cap,
+               "cs_chain_run: %d more sweeps exceed niter_cap=%d (done %d)", nsweeps, c->niter_cap, c->sweeps_done);
+    const int t0 = c->sweeps_done, t1 = t0 + nsweeps;
+    int rc = CS_OK;
+    if (c->rng_mode == CS_RNG_R) {
+        if (nsweeps > 0) rc = cs_rmode_run(c->D, c->kcap, t0, t1, is_last ? t1 - 1 : -1, c->mean.p, c->st);
+    } else {
+        for (int tt = t0; tt < t1 && rc == CS_OK; tt++) {
+            rc = cs_philox_sweep(c->D, tt, is_last && tt == t1 - 1, c->flags & 1, c->rej.p, c->st);
+            double *t = c->D.U;
+            c->D.U = c->D.Unext;
+            c->D.Unext = t;
+        }
+    }
+    if (rc) return rc;
+    c->sweeps_done = t1;
+    if (sync) return cs_chain_sync(c);
+    return CS_OK;
+}
+
+extern "C" int cs_chain_sync(cs_chain *c)
+{
+    CS_REQUIRE(c != nullptr, "cs_chain_sync: NULL chain");
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    ChainScal h;
+    CS_CUDA(cudaMemcpy(&h, c->D.scal, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h.err == CS_ERR_KCAP) {
+        cs_set_error("more clusters than capacity kcap=%d (raise cs_gibbs_opts.kcap)", c->kcap);
+        return CS_ERR_KCAP;
+    }
+    if (h.err == CS_ERR_UCAP) {
+        cs_set_error("internal Uall record capacity exceeded (%lld rows)", c->D.urec_cap);
+        return CS_ERR_UCAP;
+    }
+    if (h.err) {
+        cs_set_error("device-side error %d", h.err);
+        return h.err;
+    }
+    return CS_OK;
+}
+
+extern "C" int cs_chain_sweeps_done(cs_chain *c) { return c ? c->sweeps_done : -1; }
+
+extern "C" int cs_chain_stats(cs_chain *c, int64_t *cells_scanned, int64_t *n_events, int64_t *n_reject)
+{
+    CS_REQUIRE(c != nullptr, "cs_chain_stats: NULL chain");
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    ChainScal h;
+    CS_CUDA(cudaMemcpy(&h, c->D.scal, sizeof(h), cudaMemcpyDeviceToHost));
+    if (cells_scanned) *cells_scanned = h.cells_scanned;
+    if (n_events) *n_events = h.n_events;
+    if (n_reject) *n_reject = h.n_reject;
+    return CS_OK;
+}
+
+extern "C" int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double *LL, double *L0, int *kt_all,
+                              int64_t ucap_rows, int64_t *u_off, int *u_labels, double *u_rows)
+{
+    CS_REQUIRE(c && c->inited, "cs_chain_fetch: chain not initialised");
+    int rc = cs_chain_sync(c);
+    if (rc) return rc;
+    const int T = c->sweeps_done, N = c->N, R = c->R;
+    if (L0) CS_CUDA(cudaMemcpy(L0, c->L0.p, sizeof(double), cudaMemcpyDeviceToHost));
+    if (T == 0) return CS_OK;
+    if (Zall) { // device sweep-major T x N (row-major) -> R's column-major T x N (== row-major N x T)
+        DevBuf<int> tmp;
+        CS_CUDA(tmp.alloc((size_t)T * N));
+        rc = cs_transpose<int>(T, N, c->Zall.p, tmp.p, c->st);
+        if (rc) return rc;
+        CS_CUDA(cudaMemcpyAsync(Zall, tmp.p, sizeof(int) * (size_t)T * N, cudaMemcpyDeviceToHost, c->st));
+        CS_CUDA(cudaStreamSynchronize(c->st));
+    }
+    // sigma_all: device T x R row-major == column-major R x T: column t = sweep t
+    if (sigma_all) CS_CUDA(cudaMemcpy(sigma_all, c->sigma_all.p, sizeof(double) * (size_t)T * R, cudaMemcpyDeviceToHost));
+    if (LL) CS_CUDA(cudaMemcpy(LL, c->LL.p, sizeof(double) * T, cudaMemcpyDeviceToHost));
+    if (kt_all) CS_CUDA(cudaMemcpy(kt_all, c->kt_all.p, sizeof(int) * T, cudaMemcpyDeviceToHost));
+    if (u_off) {
+        std::vector<long long> off((size_t)T + 1);
+        CS_CUDA(cudaMemcpy(off.data(), c->u_off.p, sizeof(long long) * off.size(), cudaMemcpyDeviceToHost));
+        for (int t = 0; t <= T; t++) u_off[t] = off[t];
+        const long long need = off[T];
+        if (need > ucap_rows) {
+            cs_set_error("ucap_rows=%lld too small: %lld rows recorded", (long long)ucap_rows, need);
+            return CS_ERR_UCAP;
+        }
+        if (u_labels && need) CS_CUDA(cudaMemcpy(u_labels, c->u_labels.p, sizeof(int) * (size_t)need, cudaMemcpyDeviceToHost));
+        if (u_rows && need) CS_CUDA(cudaMemcpy(u_rows, c->u_rows.p, sizeof(double) * (size_t)need * R, cudaMemcpyDeviceToHost));
+    }
+    return CS_OK;
+}
+
+extern "C" int cs_ncrp_gibbs(int N, int R, const double *X, int K0, const double *U0, const int *Z0,
+                             const double *sigmas0, double alpha, double beta, int niter, uint32_t seed,
+                             const cs_gibbs_opts *opts, int *Zall, double *sigma_all, double *LL, double *L0,
+                             int *kt_all, int64_t ucap_rows, int64_t *u_off, int *u_labels, double *u_rows,
+                             int64_t *n_reject, int32_t *rng_state_out)
+{
+    cs_gibbs_opts o;
+    memset(&o, 0, sizeof(o));
+    o.rng_mode = CS_RNG_PHILOX;
+    o.device = -1;
+    if (opts) o = *opts;
+    CS_REQUIRE(niter >= 1, "niter=%d must be >= 1", niter);
+    if (o.device >= 0) CS_CUDA(cudaSetDevice(o.device));
+    cs_chain *c = nullptr;
+    int kcap = o.kcap;
+    if (kcap > 0 && kcap < K0) kcap = K0;
+    int rc = cs_chain_create(N, R, kcap, niter, o.rng_mode, &c);
+    if (rc) return rc;
+    struct Guard {
+        cs_chain *c;
+        ~Guard() { cs_chain_destroy(c); }
+    } guard{c};
+    if ((rc = cs_chain_init(c, X, K0, U0, Z0, sigmas0, alpha, beta, seed, o.flags))) return rc;
+    if ((rc = cs_chain_run(c, niter, 1, 1))) return rc;
+    if ((rc = cs_chain_fetch(c, Zall, sigma_all, LL, L0, kt_all, ucap_rows, u_off, u_labels, u_rows))) return rc;
+    if (n_reject) {
+        int64_t sc, ev;
+        if ((rc = cs_chain_stats(c, &sc, &ev, n_reject))) return rc;
+    }
+    if (rng_state_out && o.rng_mode == CS_RNG_R) { // .Random.seed[-1]: position, then the 624 state words
+        ChainScal h;
+        CS_CUDA(cudaMemcpy(&h, c->D.scal, sizeof(h), cudaMemcpyDeviceToHost));
+        rng_state_out[0] = h.mt_pos;
+        CS_CUDA(cudaMemcpy(rng_state_out + 1, c->D.mt, sizeof(uint32_t) * 624, cudaMemcpyDeviceToHost));
+    }
+    return CS_OK;
+}

@@ -1,0 +1,200 @@
+// cs_loglik.cu — fixed-state cell x cluster Gaussian log-likelihood matrix, layout
+// transposes, and the posterior majority-vote tally.
+//
+//   LL[i,k] = sum_r dnorm(X[i,r]; U[k,r], sigma[r], log=TRUE)   (NA segments skipped)
+// reference: R/BayesNonparCluster.R:91-96 (Z0 init), :193 (scoring), R/AssignCluster.R:58.
+// One warp per cell: lanes stride the segments (coalesced 256 B row reads), FP64
+// accumulation, butterfly reduction.  Not a tensor-core workload: the NaN mask and the
+// 1e-6 criterion rule out the expanded-square GEMM form.
+#include "cs_common.cuh"
+
+#include <vector>
+
+namespace {
+
+constexpr int LL_THREADS = 256;
+
+__global__ void __launch_bounds__(LL_THREADS)
+loglik_matrix_kernel(int N, int R, int K, const double *__restrict__ X, const double *__restrict__ U,
+                     const double *__restrict__ sigma, double *__restrict__ LL)
+{
+    extern __shared__ double s_ll[]; // isig[R], cterm[R] = log(sigma)+ln sqrt(2 pi)
+    double *s_isig = s_ll, *s_c = s_ll + R;
+    for (int r = threadIdx.x; r < R; r += LL_THREADS) {
+        const double s = sigma[r];
+        s_isig[r] = 1.0 / s;
+        s_c[r] = CS_LN_SQRT_2PI + log(s);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = LL_THREADS / 32;
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < N; i += gridDim.x * warps_per_block) {
+        const double *x = X + (size_t)i * R;
+        // constant part: -(sum over non-NA segments of log sigma + ln sqrt(2 pi))
+        double cpart = 0.0;
+        for (int r = lane; r < R; r += 32)
+            if (!cs_isna(x[r])) cpart += s_c[r];
+        cpart = cs_warp_sum_bfly(cpart);
+        for (int k = 0; k < K; k++) {
+            const double *u = U + (size_t)k * R;
+            double q = 0.0;
+            for (int r = lane; r < R; r += 32) {
+                const double xv = x[r];
+                if (!cs_isna(xv)) {
+                    const double d = (xv - __ldg(u + r)) * s_isig[r];
+                    q += d * d;
+                }
+            }
+            q = cs_warp_sum_bfly(q);
+            if (lane == 0) LL[(size_t)i * K + k] = -(cpart + 0.5 * q);
+        }
+    }
+}
+
+// out[c*rows + r] = in[r*cols + c] : generic tiled transpose (rows x cols row-major in)
+template <typename T>
+__global__ void transpose_kernel(int rows, int cols, const T *__restrict__ in, T *__restrict__ out)
+{
+    __shared__ T tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = by + j, c = bx + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = bx + j, r = by + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+// ---- majority vote --------------------------------------------------------
+// one thread per cell; element (t,i) at Z[t*st + i*si].  Fast path: the first label
+// holds a strict majority (the usual state of a converged chain).
+__global__ void majority_vote_kernel(int T, int N, const int *__restrict__ Z, int64_t st, int64_t si,
+                                     int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int *z = Z + (size_t)i * si;
+    int best = 0, bc = 0;
+    {
+        const int l0 = z[0];
+        int c0 = 0;
+        for (int t = 0; t < T; t++) c0 += (z[(size_t)t * st] == l0);
+        if (2 * c0 > T) {
+            out[i] = l0;
+            return;
+        }
+        best = l0;
+        bc = c0;
+    }
+    for (int a = 1; a < T; a++) {
+        const int la = z[(size_t)a * st];
+        if (la == best) continue;
+        int c = 0;
+        bool seen = false;
+        for (int t = 0; t < T; t++) {
+            const int lt = z[(size_t)t * st];
+            if (lt == la) {
+                if (t < a) { seen = true; break; }
+                c++;
+            }
+        }
+        if (seen) continue;
+        if (c > bc || (c == bc && la < best)) {
+            bc = c;
+            best = la;
+        }
+    }
+    out[i] = best;
+}
+
+} // namespace
+
+template <typename T>
+int cs_transpose(int rows, int cols, const T *d_in, T *d_out, cudaStream_t st)
+{
+    if (rows == 0 || cols == 0) return CS_OK;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    transpose_kernel<T><<<grid, block, 0, st>>>(rows, cols, d_in, d_out);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+template int cs_transpose<double>(int, int, const double *, double *, cudaStream_t);
+template int cs_transpose<int>(int, int, const int *, int *, cudaStream_t);
+
+extern "C" int cs_loglik_matrix_dev(int N, int R, int K, const double *d_X, const double *d_U,
+                                    const double *d_sigma, double *d_LL, void *stream)
+{
+    CS_REQUIRE(N >= 0 && R >= 1 && K >= 0, "cs_loglik_matrix: bad dimensions N=%d R=%d K=%d", N, R, K);
+    if (N == 0 || K == 0) return CS_OK;
+    const size_t smem = sizeof(double) * 2 * (size_t)R;
+    CS_REQUIRE(smem <= 200 * 1024, "cs_loglik_matrix: R=%d too large", R);
+    CS_CUDA(cudaFuncSetAttribute(loglik_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (N + LL_THREADS / 32 - 1) / (LL_THREADS / 32);
+    const int maxgrid = cs_num_sms() * 8;
+    if (grid > maxgrid) grid = maxgrid;
+    loglik_matrix_kernel<<<grid, LL_THREADS, smem, (cudaStream_t)stream>>>(N, R, K, d_X, d_U, d_sigma, d_LL);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+extern "C" int cs_loglik_matrix(int N, int R, int K, const double *X, const double *U, const double *sigma,
+                                double *LL)
+{
+    CS_REQUIRE(X && U && sigma && LL, "cs_loglik_matrix: NULL argument");
+    CS_REQUIRE(N >= 0 && R >= 1 && K >= 0, "cs_loglik_matrix: bad dimensions N=%d R=%d K=%d", N, R, K);
+    if (N == 0 || K == 0) return CS_OK;
+    DevBuf<double> dXc, dX, dUc, dU, dS, dL, dLc;
+    const size_t nx = (size_t)N * R, nu = (size_t)K * R, nl = (size_t)N * K;
+    CS_CUDA(dXc.alloc(nx));
+    CS_CUDA(dX.alloc(nx));
+    CS_CUDA(dUc.alloc(nu));
+    CS_CUDA(dU.alloc(nu));
+    CS_CUDA(dS.alloc(R));
+    CS_CUDA(dL.alloc(nl));
+    CS_CUDA(dLc.alloc(nl));
+    CS_CUDA(cudaMemcpy(dXc.p, X, sizeof(double) * nx, cudaMemcpyHostToDevice));
+    CS_CUDA(cudaMemcpy(dUc.p, U, sizeof(double) * nu, cudaMemcpyHostToDevice));
+    CS_CUDA(cudaMemcpy(dS.p, sigma, sizeof(double) * R, cudaMemcpyHostToDevice));
+    int rc;
+    // column-major N x R == row-major R x N -> transpose to row-major N x R
+    if ((rc = cs_transpose<double>(R, N, dXc.p, dX.p, 0))) return rc;
+    if ((rc = cs_transpose<double>(R, K, dUc.p, dU.p, 0))) return rc;
+    if ((rc = cs_loglik_matrix_dev(N, R, K, dX.p, dU.p, dS.p, dL.p, nullptr))) return rc;
+    // row-major N x K -> column-major N x K (== row-major K x N)
+    if ((rc = cs_transpose<double>(N, K, dL.p, dLc.p, 0))) return rc;
+    CS_CUDA(cudaMemcpy(LL, dLc.p, sizeof(double) * nl, cudaMemcpyDeviceToHost));
+    return CS_OK;
+}
+
+extern "C" int cs_majority_vote_dev(int T, int N, const int *d_Zall, int64_t stride_t, int64_t stride_i,
+                                    int *d_zmaj, void *stream)
+{
+    CS_REQUIRE(T >= 1 && N >= 0 && d_Zall && d_zmaj, "cs_majority_vote: bad arguments T=%d N=%d", T, N);
+    if (N == 0) return CS_OK;
+    majority_vote_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(T, N, d_Zall, stride_t, stride_i, d_zmaj);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+extern "C" int cs_majority_vote(int T, int N, const int *Zall, int *zmaj)
+{
+    CS_REQUIRE(T >= 1 && N >= 0 && Zall && zmaj, "cs_majority_vote: bad arguments T=%d N=%d", T, N);
+    if (N == 0) return CS_OK;
+    DevBuf<int> dZ, dZt, dO;
+    const size_t n = (size_t)T * N;
+    CS_CUDA(dZ.alloc(n));
+    CS_CUDA(dZt.alloc(n));
+    CS_CUDA(dO.alloc(N));
+    CS_CUDA(cudaMemcpy(dZ.p, Zall, sizeof(int) * n, cudaMemcpyHostToDevice));
+    // T x N column-major == row-major N x T; transpose to sweep-major (T x N row-major)
+    // so that consecutive threads (cells) read consecutive addresses
+    int rc = cs_transpose<int>(N, T, dZ.p, dZt.p, 0);
+    if (rc) return rc;
+    rc = cs_majority_vote_dev(T, N, dZt.p, (int64_t)N, 1, dO.p, nullptr);
+    if (rc) return rc;
+    CS_CUDA(cudaMemcpy(zmaj, dO.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    return CS_OK;
+}

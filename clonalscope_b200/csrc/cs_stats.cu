@@ -1,0 +1,108 @@
+// cs_stats.cu — cell-sharded sufficient statistics for the multi-GPU M-step.
+//
+// Each rank holds a contiguous shard of cells with fixed labels; the per-cluster sums,
+// non-NA counts and cluster sizes (R/BayesNonparCluster.R:221-224) and the per-segment
+// squared residuals (:234) of the shard are produced here, and the caller all-reduces
+// the (K*R*2 + K + 2R) doubles across ranks (NCCL over NVLink; latency-bound, ~100 KB).
+#include "cs_common.cuh"
+
+namespace {
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_CHUNK = 512;
+
+// grid: cell chunks.  Shared accumulators when K*R fits, global atomics otherwise.
+__global__ void __launch_bounds__(ST_THREADS)
+cluster_stats_kernel(int N, int R, int K, const double *__restrict__ X, const int *__restrict__ Z,
+                     double *__restrict__ sum_x, double *__restrict__ cnt_x, double *__restrict__ nk, int use_smem)
+{
+    extern __shared__ double s_acc[]; // K*R sums, K*R counts
+    const int i0 = blockIdx.x * ST_CHUNK, i1 = min(N, i0 + ST_CHUNK);
+    if (use_smem) {
+        for (int e = threadIdx.x; e < 2 * K * R; e += ST_THREADS) s_acc[e] = 0.0;
+        __syncthreads();
+    }
+    for (int i = i0; i < i1; i++) {
+        const int k = Z[i] - 1;
+        if (k < 0 || k >= K) continue;
+        const double *x = X + (size_t)i * R;
+        for (int r = threadIdx.x; r < R; r += ST_THREADS) {
+            const double v = x[r];
+            if (cs_isna(v)) continue;
+            if (use_smem) {
+                s_acc[k * R + r] += v; // thread owns column r: no race
+                s_acc[K * R + k * R + r] += 1.0;
+            } else {
+                atomicAdd(sum_x + (size_t)k * R + r, v);
+                atomicAdd(cnt_x + (size_t)k * R + r, 1.0);
+            }
+        }
+        if (threadIdx.x == 0) atomicAdd(nk + k, 1.0);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < K * R; e += ST_THREADS) {
+            if (s_acc[K * R + e] != 0.0) {
+                atomicAdd(sum_x + e, s_acc[e]);
+                atomicAdd(cnt_x + e, s_acc[K * R + e]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+sigma_stats_kernel(int N, int R, int K, const double *__restrict__ X, const int *__restrict__ Z,
+                   const double *__restrict__ U, double *__restrict__ sq, double *__restrict__ cnt)
+{
+    const int i0 = blockIdx.x * ST_CHUNK, i1 = min(N, i0 + ST_CHUNK);
+    for (int r = threadIdx.x; r < R; r += ST_THREADS) {
+        double s = 0.0, c = 0.0;
+        for (int i = i0; i < i1; i++) {
+            const double x = X[(size_t)i * R + r];
+            if (cs_isna(x)) continue;
+            c += 1.0;
+            const int k = Z[i] - 1;
+            if (k < 0 || k >= K) continue;
+            const double d = x - U[(size_t)k * R + r];
+            if (!cs_isna(d)) s += d * d;
+        }
+        atomicAdd(sq + r, s);
+        atomicAdd(cnt + r, c);
+    }
+}
+
+} // namespace
+
+extern "C" int cs_cluster_stats_dev(int N, int R, int K, const double *d_X, const int *d_Z, double *d_sum_x,
+                                    double *d_cnt_x, double *d_nk, void *stream)
+{
+    CS_REQUIRE(N >= 0 && R >= 1 && K >= 1 && d_sum_x && d_cnt_x && d_nk, "cs_cluster_stats_dev: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_CUDA(cudaMemsetAsync(d_sum_x, 0, sizeof(double) * (size_t)K * R, st));
+    CS_CUDA(cudaMemsetAsync(d_cnt_x, 0, sizeof(double) * (size_t)K * R, st));
+    CS_CUDA(cudaMemsetAsync(d_nk, 0, sizeof(double) * (size_t)K, st));
+    if (N == 0) return CS_OK;
+    const size_t smem = sizeof(double) * 2 * (size_t)K * R;
+    const int use_smem = smem <= 160 * 1024;
+    if (use_smem && smem > 48 * 1024)
+        CS_CUDA(cudaFuncSetAttribute(cluster_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cluster_stats_kernel<<<(N + ST_CHUNK - 1) / ST_CHUNK, ST_THREADS, use_smem ? smem : 0, st>>>(
+        N, R, K, d_X, d_Z, d_sum_x, d_cnt_x, d_nk, use_smem);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+extern "C" int cs_sigma_stats_dev(int N, int R, int K, const double *d_X, const int *d_Z, const double *d_U,
+                                  double *d_sq, double *d_cnt, void *stream)
+{
+    CS_REQUIRE(N >= 0 && R >= 1 && K >= 1 && d_sq && d_cnt, "cs_sigma_stats_dev: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_CUDA(cudaMemsetAsync(d_sq, 0, sizeof(double) * (size_t)R, st));
+    CS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(double) * (size_t)R, st));
+    if (N == 0) return CS_OK;
+    sigma_stats_kernel<<<(N + ST_CHUNK - 1) / ST_CHUNK, ST_THREADS, 0, st>>>(N, R, K, d_X, d_Z, d_U, d_sq, d_cnt);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+// allele variant lives in cs_allele.cu

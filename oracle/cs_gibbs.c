@@ -90,6 +90,27 @@ static void philox_draw(uint32_t seed, uint32_t c0, uint32_t c1, uint32_t c2, ui
     *ub = u53(o[2], o[3]);
 }
 
+/* Canonical evaluation order of the Philox mode (DESIGN.md "Philox mode"): the squared
+ * standardised distance of a cell to a row is accumulated as 32 strided partial sums
+ * (partial l takes segments l, l+32, ... with a fused multiply-add) that are then
+ * combined by a 5-level butterfly — the order one warp of the CUDA path uses, so the
+ * two agree bit for bit. */
+static double q_canon(int R, const double *x, const double *u, const double *isig)
+{
+    double s[32], t[32];
+    for (int l = 0; l < 32; l++) s[l] = 0.0;
+    for (int r = 0; r < R; r++) {
+        if (is_na(x[r])) continue;
+        double d = (x[r] - u[r]) * isig[r];
+        s[r & 31] = fma(d, d, s[r & 31]);
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        for (int l = 0; l < 32; l++) t[l] = s[l] + s[l ^ off];
+        for (int l = 0; l < 32; l++) s[l] = t[l];
+    }
+    return s[0];
+}
+
 typedef struct {
     int cap;      /* allocated rows */
     int kt;       /* rows in use == number of labels ever created */
@@ -163,6 +184,7 @@ int cso_gibbs(int N, int R, const double *X, int K0, const double *U0in, const i
     int *Zt = (int *)malloc(sizeof(int) * (size_t)N);
     double *sig = (double *)malloc(sizeof(double) * (size_t)R);
     double *mu_new = (double *)malloc(sizeof(double) * (size_t)R);
+    double *isig = (double *)malloc(sizeof(double) * (size_t)R);
     double *prob = NULL, *pk = NULL, *cumc = NULL;
     int *perm = NULL, *permc = NULL;
     int pcap = 0;
@@ -204,6 +226,7 @@ int cso_gibbs(int N, int R, const double *X, int K0, const double *U0in, const i
 
     for (int tt = 0; tt < niter; tt++) {
         int reject_live = single && tt == 0;
+        for (int r = 0; r < R; r++) isig[r] = 1.0 / sig[r];
         for (int ii = 0; ii < N; ii++) {
             const double *x = X + (size_t)ii * R;
             int kt = st.kt;
@@ -248,7 +271,7 @@ int cso_gibbs(int N, int R, const double *X, int K0, const double *U0in, const i
                         double ua, ub;
                         philox_draw(seed, (uint32_t)ii, (uint32_t)r, (uint32_t)tt, PH_PROPOSAL,
                                     attempt, &ua, &ub);
-                        tmpr = 0.3 + (2.5 - 0.3) * ua;
+                        tmpr = fma(2.5 - 0.3, ua, 0.3);
                         double v = ub * ((double)N + alpha);
                         if (v < (double)N) {
                             int j = (int)v;
@@ -301,12 +324,7 @@ int cso_gibbs(int N, int R, const double *X, int K0, const double *U0in, const i
                 for (int k = 0; k <= kt; k++) {
                     if (k < kt && st.np[k] == 0) continue;
                     const double *u = (k < kt) ? st.U + (size_t)k * R : mu_new;
-                    double q = 0.0;
-                    for (int r = 0; r < R; r++) {
-                        if (is_na(x[r])) continue;
-                        double d = (x[r] - u[r]) * (1.0 / sig[r]);
-                        q += d * d;
-                    }
+                    double q = q_canon(R, x, u, isig);
                     pk[k] = q;
                     if (q < qmin) qmin = q;
                 }
@@ -401,7 +419,7 @@ int cso_gibbs(int N, int R, const double *X, int K0, const double *U0in, const i
 
 done:
     if (n_reject) *n_reject = rejects;
-    free(st.U); free(st.np); free(Zt); free(sig); free(mu_new);
+    free(st.U); free(st.np); free(Zt); free(sig); free(mu_new); free(isig);
     free(prob); free(pk); free(cumc); free(perm); free(permc);
     free(acc); free(cnt); free(mean);
     return rc;

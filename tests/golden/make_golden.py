@@ -102,7 +102,28 @@ def deltas_fixture(name, path):
     print(name, len(deltas), "segments", len(universe), "barcodes", os.path.getsize(fn) // 1024, "KiB")
 
 
+def geometry_fixture():
+    """Real geometry for the binning tests: the 200-kb tiles and the GTF-like gene table the
+    reference ships (data-raw/hg38_200kb.windows.bed, data-raw/genes_filtered.rds)."""
+    chrom, start, end = [], [], []
+    with open(os.path.join(REF, "data-raw/hg38_200kb.windows.bed")) as fh:
+        for line in fh:
+            p = line.split()
+            if len(p) >= 3:
+                chrom.append(p[0]); start.append(int(p[1])); end.append(int(p[2]))
+    g = read_rds(os.path.join(REF, "data-raw/genes_filtered.rds"))
+    fn = os.path.join(HERE, "geometry_hg38.npz")
+    np.savez_compressed(
+        fn, bin_chr=np.array(chrom), bin_start=np.array(start, dtype=np.int64),
+        bin_end=np.array(end, dtype=np.int64),
+        gtf_V1=np.array([str(x) for x in g["V1"].data]), gtf_V3=np.array([str(x) for x in g["V3"].data]),
+        gtf_V4=g["V4"].data.astype(np.int64), gtf_V5=g["V5"].data.astype(np.int64),
+        gtf_V9=np.array([str(x).split(";")[0] + ";" for x in g["V9"].data]))
+    print("geometry", len(chrom), "bins", len(g["V1"].data), "genes", os.path.getsize(fn) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    geometry_fixture()
     for k, v in SAMPLER.items():
         sampler_fixture(k, v)
     for k, v in DELTAS.items():

@@ -1,0 +1,319 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, against the reference's golden fixtures, and through size-independent
+properties.  Integer / label work must match bit for bit; floating point to the stated
+tolerance (north star: log-likelihood matrix 1e-6 relative — we assert 1e-11)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SAMPLER_FIXTURES, load_golden
+
+pytestmark = pytest.mark.gpu
+FULL = os.environ.get("CS_FULL_FIXTURES", "0") == "1"
+
+
+# ------------------------------------------------------------------ log-likelihood matrix
+def test_loglik_matrix_vs_oracle(cs, oracle):
+    rng = np.random.default_rng(11)
+    for (N, R, K) in [(1, 1, 1), (37, 5, 3), (1000, 38, 47), (513, 300, 20), (200, 333, 2)]:
+        X = rng.uniform(0.05, 3.0, size=(N, R))
+        X[rng.random((N, R)) < 0.05] = np.nan
+        if N > 3:
+            X[2, :] = np.nan  # an all-NA cell scores 0 everywhere
+        U = rng.uniform(0.3, 2.5, size=(K, R))
+        sig = rng.uniform(0.05, 0.6, size=R)
+        got = cs.loglik_matrix(X, U, sig)
+        want = oracle.loglik_matrix(X, U, sig)
+        np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", SAMPLER_FIXTURES)
+def test_loglik_known_answers_from_fixtures(cs, name):
+    """Likelihood[t] = sum_i LL[i, Zall[t,i]] recomputed on the device from the reference's own
+    (data, Uall[[t]], sigma_all[[t]], Zall[t,]) — the 1e-6 criterion, asserted at 1e-10."""
+    g = load_golden(f"sampler_{name}.npz")
+    X = g["X"]
+    for j, t in enumerate(g["usel"]):
+        a, b = int(g["usel_off"][j]), int(g["usel_off"][j + 1])
+        labels = g["u_labels"][int(g["u_off"][t]):int(g["u_off"][t + 1])]
+        LLm = cs.loglik_matrix(X, g["usel_rows"][a:b], g["sigma_all"][t])
+        col = {int(l): i for i, l in enumerate(labels)}
+        Z = g["Zall"][t]
+        tot = LLm[np.arange(X.shape[0]), [col[int(z)] for z in Z]].sum()
+        assert abs(tot / g["Likelihood"][t] - 1) < 1e-10, (name, t)
+    L0m = cs.loglik_matrix(X, g["U0"], g["sigmas0"])
+    assert abs(L0m[np.arange(X.shape[0]), g["Z0"] - 1].sum() / float(g["L0"]) - 1) < 1e-10
+
+
+# ------------------------------------------------------------------ gene -> bin aggregation
+def _random_csc(rng, G, N, density, vmax=9):
+    cols = []
+    colptr = [0]
+    for c in range(N):
+        m = rng.binomial(G, density)
+        cols.append(np.sort(rng.choice(G, size=m, replace=False)).astype(np.int32))
+        colptr.append(colptr[-1] + m)
+    rowidx = np.concatenate(cols) if cols else np.zeros(0, np.int32)
+    x = rng.integers(1, vmax + 1, size=len(rowidx)).astype(np.float64)
+    return np.array(colptr, dtype=np.int32), rowidx.astype(np.int32), x
+
+
+def _check_bins(cs, oracle, G, N, B, colptr, rowidx, x, map_ptr, map_bin, exact=True):
+    from clonalscope_b200.api import bin_counts_csc
+    ocp, ori, ox = bin_counts_csc(G, N, B, colptr, rowidx, x, map_ptr, map_bin)
+    wcp, wri, wx = oracle.bin_counts(G, N, B, colptr, rowidx, x, map_ptr, map_bin)
+    assert np.array_equal(ocp, wcp)
+    assert np.array_equal(ori, wri)
+    if exact:
+        assert np.array_equal(ox, wx)
+    else:
+        np.testing.assert_allclose(ox, wx, rtol=1e-13)
+    return ocp, ori, ox
+
+
+def test_binning_synthetic_geometry_bit_exact(cs, oracle):
+    from clonalscope_b200 import synth
+    bins, genes = synth.geometry(G=3000, seed=7)
+    map_ptr, map_bin = synth.geometry_map(bins, genes)
+    B = len(bins["chr"])
+    colptr, rowidx, x = synth.counts_csc(400, G=3000, seed=8, mean_genes=300)
+    ocp, ori, ox = _check_bins(cs, oracle, 3000, 400, B, colptr, rowidx, x, map_ptr, map_bin)
+    # the reference's own dense algorithm (densify, loop over bins) agrees as well
+    dense = oracle.bin_counts_dense(3000, 400, B, colptr, rowidx, x, map_ptr, map_bin)
+    import scipy.sparse as sp
+    got = sp.csc_matrix((ox, ori, ocp), shape=(B, 400)).toarray()
+    assert np.array_equal(got, dense)
+    # property: total per cell = sum_g x[g,c] * #bins(g)   (many-to-many)
+    nh = np.diff(map_ptr).astype(np.float64)
+    for c in (0, 17, 399):
+        assert got[:, c].sum() == (x[colptr[c]:colptr[c + 1]] * nh[rowidx[colptr[c]:colptr[c + 1]]]).sum()
+
+
+def test_binning_real_geometry_api(cs, oracle):
+    """Gen_bin_cell_rna_filtered end to end on the reference's real tiles and gene table."""
+    import scipy.sparse as sp
+    from clonalscope_b200.api import gene_bin_map
+    g = load_golden("geometry_hg38.npz")
+    bed = np.stack([g["bin_chr"], g["bin_start"].astype(object), g["bin_end"].astype(object)], axis=1)
+    gtf = dict(V1=g["gtf_V1"], V3=g["gtf_V3"], V4=g["gtf_V4"], V5=g["gtf_V5"], V9=g["gtf_V9"])
+    ids = [s.split("gene_id ")[1].rstrip(";") for s in g["gtf_V9"]]
+    genes = np.array(ids, dtype=object).reshape(-1, 1)
+    G, N = len(ids), 150
+    rng = np.random.default_rng(3)
+    colptr, rowidx, x = _random_csc(rng, G, N, 0.05)
+    m = sp.csc_matrix((x, rowidx, colptr), shape=(G, N))
+    barcodes = np.array([f"cell{i}-1" for i in range(N)], dtype=object).reshape(-1, 1)
+    out = cs.Gen_bin_cell_rna_filtered(bin_bed=bed, barcodes=barcodes, gene_matrix=m, genes=genes, gtf=gtf)
+    assert out.shape == (15641, N) and out.colnames[3] == "cell3-1" and out.rownames[0] == "chr1-0-200000"
+    rn, map_ptr, map_bin = gene_bin_map(bed, genes, gtf)
+    wcp, wri, wx = oracle.bin_counts(G, N, 15641, colptr, rowidx, x, map_ptr, map_bin)
+    v = out.values
+    assert np.array_equal(v.indptr, wcp) and np.array_equal(v.indices, wri) and np.array_equal(v.data, wx)
+
+
+def test_binning_edge_cases(cs, oracle):
+    rng = np.random.default_rng(5)
+    G, B = 50, 40
+    # general (non-contiguous, unsorted-origin) map exercises the escape path
+    lists = [np.sort(rng.choice(B, size=rng.integers(0, 4), replace=False)) for _ in range(G)]
+    lists[3] = np.array([0, 5, 39])
+    map_ptr = np.zeros(G + 1, dtype=np.int32)
+    map_ptr[1:] = np.cumsum([len(l) for l in lists])
+    map_bin = np.concatenate(lists).astype(np.int32)
+    # ragged columns: empty, single entry, every alignment of the 128-bit body, full
+    cols = [np.zeros(0, np.int32), np.array([3], np.int32)]
+    for m in range(2, 14):
+        cols.append(np.sort(rng.choice(G, size=m, replace=False)).astype(np.int32))
+    cols.append(np.arange(G, dtype=np.int32))
+    cols.append(np.zeros(0, np.int32))
+    colptr = np.zeros(len(cols) + 1, dtype=np.int32)
+    colptr[1:] = np.cumsum([len(c) for c in cols])
+    rowidx = np.concatenate(cols)
+    x = rng.integers(1, 100, size=len(rowidx)).astype(np.float64)
+    N = len(cols)
+    _check_bins(cs, oracle, G, N, B, colptr, rowidx, x, map_ptr, map_bin)
+    # explicit zeros and cancelling negatives: touched bins with zero sum are dropped (shrink path)
+    x2 = x.copy()
+    x2[colptr[5]:colptr[6]] = 0.0
+    x2[colptr[8]] = 0.0
+    ocp, _, _ = _check_bins(cs, oracle, G, N, B, colptr, rowidx, x2, map_ptr, map_bin)
+    assert ocp[6] == ocp[5]
+    # counts beyond int32 and non-integer values go through the FP64 accumulators
+    x3 = x.copy()
+    x3[0] = 3.0e9
+    _check_bins(cs, oracle, G, N, B, colptr, rowidx, x3, map_ptr, map_bin)
+    x4 = x + 0.25
+    _check_bins(cs, oracle, G, N, B, colptr, rowidx, x4, map_ptr, map_bin, exact=False)
+    # no cells at all
+    from clonalscope_b200.api import bin_counts_csc
+    ocp, ori, ox = bin_counts_csc(G, 0, B, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0), map_ptr, map_bin)
+    assert list(ocp) == [0] and len(ori) == 0
+    with pytest.raises(cs.ClonalscopeError):
+        bin_counts_csc(G, 1, B, np.array([0, 1], np.int32), np.array([G], np.int32), np.ones(1), map_ptr, map_bin)
+
+
+def test_binning_permutation_invariance(cs):
+    """Relabelling the bins permutes the rows of the result and nothing else."""
+    from clonalscope_b200.api import bin_counts_csc
+    import scipy.sparse as sp
+    rng = np.random.default_rng(9)
+    G, N, B = 300, 64, 200
+    nh = rng.integers(0, 3, size=G)
+    first = rng.integers(0, B - 3, size=G)
+    map_ptr = np.zeros(G + 1, np.int32)
+    map_ptr[1:] = np.cumsum(nh)
+    map_bin = np.concatenate([np.arange(f, f + n) for f, n in zip(first, nh)]).astype(np.int32)
+    colptr, rowidx, x = _random_csc(rng, G, N, 0.2)
+    a = sp.csc_matrix(bin_counts_csc(G, N, B, colptr, rowidx, x, map_ptr, map_bin)[::-1], shape=(B, N)).toarray()
+    perm = rng.permutation(B)
+    pm = np.concatenate([np.sort(perm[np.arange(f, f + n)]) for f, n in zip(first, nh)]).astype(np.int32)
+    b = sp.csc_matrix(bin_counts_csc(G, N, B, colptr, rowidx, x, map_ptr, pm)[::-1], shape=(B, N)).toarray()
+    assert np.array_equal(b[perm], a)
+
+
+# ------------------------------------------------------------------ tally
+def test_majority_vote_vs_oracle(cs, oracle):
+    rng = np.random.default_rng(2)
+    for (T, N, L) in [(1, 5, 3), (100, 2000, 4), (100, 3000, 60), (7, 1000, 2), (33, 257, 500)]:
+        Z = rng.integers(1, L + 1, size=(T, N)).astype(np.int32)
+        Z[:, : N // 3] = Z[0, : N // 3]  # converged cells take the fast path
+        assert np.array_equal(cs.majority_vote(Z), oracle.majority_vote(Z))
+    Z = np.array([[5, 2], [2, 5], [5, 2], [2, 5]], dtype=np.int32)  # exact ties -> smallest label
+    assert list(cs.majority_vote(Z)) == [2, 2]
+
+
+@pytest.mark.parametrize("name", ["P5931", "BC_ductal2", "P5847_allcells"])
+def test_tally_on_fixture_chains(cs, oracle, name):
+    g = load_golden(f"sampler_{name}.npz")
+    obj = dict(results=dict(Zall=g["Zall"].astype(np.int32), Uall=[None] * 200, sigma_all=[None] * 200,
+                            Likelihood=np.zeros(200)), priors={}, data=None)
+    trimmed = cs.MCMCtrim(obj)  # burnin = 100
+    zm = cs.majority_vote(trimmed["results"]["Zall"])
+    assert np.array_equal(zm, oracle.majority_vote(g["Zall"][100:].astype(np.int32)))
+
+
+# ------------------------------------------------------------------ sampler, R-compatible RNG
+def _run_r(cs, g, niter):
+    return cs.BayesNonparCluster(g["X"], cna_states_WGS=g["cna_states_WGS"], alpha=float(g["alpha"]),
+                                 beta=float(g["beta"]), niter=niter, sigmas0=g["sigmas0"], U0=g["U0"],
+                                 Z0=g["Z0"], seed=int(g["seed"]), rng="R")
+
+
+def _ari(a, b):
+    from sklearn.metrics import adjusted_rand_score
+    return adjusted_rand_score(a, b)
+
+
+@pytest.mark.parametrize("name,niter", [("P5931", 200), ("P5931_updated1", 200), ("BC_ductal2", 200 if FULL else 30),
+                                        ("P5847_tumor", 200 if FULL else 25),
+                                        ("P5847_allcells", 200 if FULL else 12)])
+def test_sampler_r_mode_reproduces_reference_outputs(cs, name, niter):
+    """With base R's RNG stream consumed in the reference's order, the device reproduces the
+    Zall the reference itself shipped, label for label."""
+    g = load_golden(f"sampler_{name}.npz")
+    out = _run_r(cs, g, niter)
+    res = out["results"]
+    mism = int((res["Zall"] != g["Zall"][:niter]).sum())
+    assert mism == 0, f"{mism} label mismatches"
+    k = niter if niter == 200 else niter - 1  # a truncated run overwrites ITS last sweep noise-free
+    assert [u.shape[0] for u in res["Uall"]] == list(g["kt"][:niter])
+    np.testing.assert_allclose(np.array(res["sigma_all"][:k]), g["sigma_all"][:k], rtol=1e-9)
+    np.testing.assert_allclose(res["Likelihood"][:k], g["Likelihood"][:k], rtol=1e-9)
+    assert abs(out["priors"]["L0"] / float(g["L0"]) - 1) < 1e-12
+    for t in range(k):
+        live = np.nonzero(~np.isnan(res["Uall"][t][:, 0]))[0]
+        a, b = int(g["u_off"][t]), int(g["u_off"][t + 1])
+        assert np.array_equal(live + 1, g["u_labels"][a:b])
+        np.testing.assert_allclose(res["Uall"][t][live].sum(axis=1), g["u_rowsum"][a:b], rtol=1e-9, atol=1e-12)
+    if name == "BC_ductal2":
+        assert out["diagnostics"]["n_reject"] == 207384  # first-sweep identical() rejections
+    if niter == 200:  # north-star criterion: ARI >= 0.95 vs the reference's posterior clustering
+        zm = cs.majority_vote(cs.MCMCtrim(out)["results"]["Zall"])
+        zr = cs.majority_vote(g["Zall"][100:].astype(np.int32))
+        assert _ari(zm, zr) >= 0.95 and len(np.unique(zm)) == len(np.unique(zr))
+
+
+# ------------------------------------------------------------------ sampler, Philox
+def _philox_pair(cs, oracle, X, U0, Z0, sig0, niter, seed=200, alpha=2.0, beta=2.0, flags=0):
+    want = oracle.gibbs(X, U0, Z0, sig0, alpha, beta, niter, seed, rng_mode=oracle.RNG_PHILOX,
+                        ucap_rows=niter * 512)
+    got = cs.BayesNonparCluster(X, alpha=alpha, beta=beta, niter=niter, sigmas0=sig0, U0=U0, Z0=Z0, seed=seed,
+                                rng="philox", _flags=flags)
+    return got, want
+
+
+def _assert_same_chain(got, want, niter, tol=1e-9):
+    res = got["results"]
+    mism = int((res["Zall"] != want["Zall"]).sum())
+    assert mism == 0, f"{mism} label mismatches, first at sweep {np.argwhere(res['Zall'] != want['Zall'])[0]}"
+    assert [u.shape[0] for u in res["Uall"]] == list(want["kt"])
+    np.testing.assert_allclose(np.array(res["sigma_all"]), want["sigma_all"], rtol=tol)
+    np.testing.assert_allclose(res["Likelihood"], want["LL"], rtol=tol)
+    assert abs(got["priors"]["L0"] / want["L0"] - 1) < 1e-12
+    for t in range(niter):
+        live = np.nonzero(~np.isnan(res["Uall"][t][:, 0]))[0]
+        a, b = int(want["u_off"][t]), int(want["u_off"][t + 1])
+        assert np.array_equal(live + 1, want["u_labels"][a:b])
+        np.testing.assert_allclose(res["Uall"][t][live], want["u_rows"][a:b], rtol=tol, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,R,na,niter", [(1500, 40, 0.0, 12), (1200, 300, 0.0, 8), (900, 70, 0.02, 10),
+                                          (333, 4, 0.0, 25), (64, 1, 0.0, 10)])
+def test_sampler_philox_vs_oracle_synthetic(cs, oracle, N, R, na, niter):
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(N, R=R, seed=1003 + R, K_true=6, na_frac=na)
+    Z0 = oracle.loglik_matrix(s["X"], s["U0"], s["sigmas0"]).argmax(axis=1).astype(np.int32) + 1
+    got, want = _philox_pair(cs, oracle, s["X"], s["U0"], Z0, s["sigmas0"], niter)
+    _assert_same_chain(got, want, niter)
+    # the default Z0 of the shim (device log-likelihood argmax, :91-108) is the same vector
+    assert np.array_equal(cs.BayesNonparCluster(s["X"], U0=s["U0"], sigmas0=s["sigmas0"], niter=1)["priors"]["Z0"], Z0)
+
+
+@pytest.mark.parametrize("name,niter", [("P5931", 40), ("BC_ductal2", 6), ("P5847_tumor", 8)])
+def test_sampler_philox_vs_oracle_on_reference_data(cs, oracle, name, niter):
+    """Real fixtures are event-dense (8-25 % of the cells move per sweep, kt keeps growing) and
+    BC_ductal2 starts from a single cluster (first-sweep rejection loop)."""
+    g = load_golden(f"sampler_{name}.npz")
+    got, want = _philox_pair(cs, oracle, g["X"], g["U0"], g["Z0"], g["sigmas0"], niter, seed=int(g["seed"]),
+                             alpha=float(g["alpha"]), beta=float(g["beta"]))
+    _assert_same_chain(got, want, niter)
+    assert got["diagnostics"]["n_reject"] == want["n_reject"]
+
+
+def test_speculative_and_sequential_evaluation_agree(cs):
+    """flags bit 0 disables the speculative prepare pass (every cell goes through the scan
+    kernel): the chain must be identical, which is the 'sequential order preserved' claim."""
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(2500, R=120, seed=77, K_true=8)
+    kw = dict(alpha=2.0, beta=2.0, niter=10, sigmas0=s["sigmas0"], U0=s["U0"], seed=5, rng="philox")
+    a = cs.BayesNonparCluster(s["X"], **kw)
+    b = cs.BayesNonparCluster(s["X"], _flags=1, **kw)
+    assert np.array_equal(a["results"]["Zall"], b["results"]["Zall"])
+    for ua, ub in zip(a["results"]["Uall"], b["results"]["Uall"]):
+        assert np.array_equal(ua, ub, equal_nan=True)
+    assert np.array_equal(a["results"]["Likelihood"], b["results"]["Likelihood"])
+
+
+def test_philox_chain_is_in_the_reference_envelope(cs):
+    """Distributional criterion for the Philox stream: P5931, 200 sweeps,
+    burn-in 100, majority vote — ARI against the reference's posterior clustering inside the
+    reference's own seed-to-seed envelope (0.954-0.964) with a tolerance, 6-8 subclones."""
+    g = load_golden("sampler_P5931.npz")
+    out = cs.BayesNonparCluster(g["X"], cna_states_WGS=g["cna_states_WGS"], alpha=2, beta=2, niter=200,
+                                sigmas0=g["sigmas0"], U0=g["U0"], Z0=g["Z0"], seed=200, rng="philox")
+    zm = cs.majority_vote(cs.MCMCtrim(out)["results"]["Zall"])
+    zr = cs.majority_vote(g["Zall"][100:].astype(np.int32))
+    ari = _ari(zm, zr)
+    lab, cnt = np.unique(zm, return_counts=True)
+    nclu = int((cnt > 13).sum())
+    print("philox P5931 ARI", ari, "subclones", nclu)
+    assert ari >= 0.93 and 5 <= nclu <= 9
+
+
+def test_kcap_overflow_is_reported(cs):
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(400, R=8, seed=3, K_true=6)
+    with pytest.raises(cs.ClonalscopeError) as e:
+        cs.BayesNonparCluster(s["X"], U0=s["U0"], sigmas0=s["sigmas0"], niter=30, rng="philox", kcap=2)
+    assert e.value.status == 3

@@ -1,0 +1,177 @@
+"""CPU tests of the host-side logic and the C-ABI surface (no kernels are launched)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol(cs):
+    from clonalscope_b200 import _lib
+    L = cs.lib()
+    hdr = open(os.path.join(ROOT, "include", "clonalscope_b200.h")).read()
+    declared = set(re.findall(r"\b(cs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert L.cs_version() >= 100
+    assert isinstance(L.cs_last_error(), bytes)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "clonalscope_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                for pat in ("import oracle", "from oracle", "libcs_oracle", "cs_oracle.h", "cso_", "oracle/"):
+                    assert pat not in src, (pat, os.path.join(dirpath, f))
+
+
+def test_r_number_formatting():
+    from clonalscope_b200.intervals import r_as_character as f
+    assert f(600000.0) == "6e+05" and f(200000.0) == "2e+05" and f(100000.0) == "1e+05"
+    assert f(1200000.0) == "1200000" and f(123456.0) == "123456"
+    assert f(600000) == "600000" and f("17") == "17"
+    assert f(0.5) == "0.5" and f(1e-5) == "1e-05" and f(0.0001) == "1e-04" and f(0.1234) == "0.1234"
+    assert f(1e15) == "1e+15" and f(248956422.0) == "248956422"
+
+
+def test_sort_bins_matches_r_order():
+    from clonalscope_b200.intervals import sort_bins
+    chrom = ["chr2", "chr10", "chrX", "chr1", "chr1", "chrY", "chr2"]
+    start = [200, 0, 5, 400, 200, 1, 0]
+    end = [400, 200, 9, 600, 400, 2, 200]
+    c, s, e, order = sort_bins(chrom, start, end)
+    assert c == ["1", "1", "2", "2", "10", "Y", "X"]  # NA chromosomes last, ordered by start
+    assert s == [200, 400, 0, 200, 0, 1, 5]
+
+
+def test_overlap_map_any_overlap_semantics():
+    from clonalscope_b200.intervals import overlap_map
+    bins_chr = ["1", "1", "1", "2"]
+    bs, be = [0, 100, 200, 0], [100, 200, 300, 100]
+    gene_seq = ["chr1", "chr1", "chr1", "chr2", "chr0", "chr1"]
+    gs = np.array([50, 100, 101, 1, 0, 301])
+    ge = np.array([60, 100, 250, 100, 0, 400])
+    ptr, mb = overlap_map(bins_chr, bs, be, gene_seq, gs, ge)
+    hits = [list(mb[ptr[g]:ptr[g + 1]]) for g in range(6)]
+    # bin i covers [start+1, end]: gene [100,100] lies in bin 0 only; [101,250] spans bins 1 and 2
+    assert hits == [[0], [0], [1, 2], [3], [], []]
+
+
+def test_overlap_map_general_path_equals_tiles_path():
+    from clonalscope_b200.intervals import overlap_map
+    rng = np.random.default_rng(5)
+    bs = np.sort(rng.integers(0, 10000, size=60))
+    be = bs + rng.integers(1, 900, size=60)  # overlapping windows, ends not monotone
+    gs = rng.integers(0, 10000, size=200)
+    ge = gs + rng.integers(0, 1500, size=200)
+    ptr, mb = overlap_map(["1"] * 60, list(bs), list(be), ["chr1"] * 200, gs, ge)
+    for g in range(200):
+        want = [b for b in range(60) if bs[b] + 1 <= ge[g] and be[b] >= gs[g]]
+        assert list(mb[ptr[g]:ptr[g + 1]]) == want
+
+
+def test_real_geometry_map():
+    """14,385 autosomal + X/Y/... tiles x 36,601 genes of the reference's own data files."""
+    from clonalscope_b200.api import gene_bin_map
+    g = load_golden("geometry_hg38.npz")
+    bed = np.stack([g["bin_chr"], g["bin_start"].astype(object), g["bin_end"].astype(object)], axis=1)
+    gtf = dict(V1=g["gtf_V1"], V3=g["gtf_V3"], V4=g["gtf_V4"], V5=g["gtf_V5"], V9=g["gtf_V9"])
+    ids = [s.split("gene_id ")[1].rstrip(";") for s in g["gtf_V9"]]
+    genes = np.array(ids, dtype=object).reshape(-1, 1)
+    rownames, ptr, mb = gene_bin_map(bed, genes, gtf)
+    assert len(rownames) == 15641 and rownames[0] == "chr1-0-200000" and rownames[1] == "chr1-200000-400000"
+    nh = np.diff(ptr)
+    assert nh.min() >= 0 and nh.max() >= 10 and 1.0 < nh[nh > 0].mean() < 1.3
+    # every hit is a true overlap and bins are ascending per gene
+    from clonalscope_b200.intervals import sort_bins
+    c, s, e, _ = sort_bins(list(g["bin_chr"]), list(g["bin_start"]), list(g["bin_end"]))
+    for gi in np.random.default_rng(0).integers(0, len(ids), 300):
+        hb = mb[ptr[gi]:ptr[gi + 1]]
+        assert np.all(np.diff(hb) > 0)
+        for b in hb:
+            assert "chr" + c[b] == g["gtf_V1"][gi] and s[b] + 1 <= g["gtf_V5"][gi] and e[b] >= g["gtf_V4"][gi]
+
+
+@pytest.mark.parametrize("name,cap,sampler", [("P5931", 2.0, "P5931"), ("BC_ductal2", 3.0, "BC_ductal2")])
+def test_prepcovmatrix_reproduces_fixture_data(name, cap, sampler):
+    """deltas_allseg.rds -> PrepCovMatrix(ngene_filter=150, 'intersect') -> pmin(., est_cap) -> the
+    cells x segments the reference clustered == fixture `data`, difference 0.0."""
+    from clonalscope_b200 import PrepCovMatrix
+    d = load_golden(f"deltas_{name}.npz")
+    bar = d["barcodes"]
+    nseg = len(d["seg_names"])
+    deltas = [(list(bar[d[f"idx_{s}"]]), d[f"val_{s}"]) for s in range(nseg)]
+    seg = dict(chr=d["seg_chr"], start=d["seg_start"], end=d["seg_end"])
+    out = PrepCovMatrix(dict(deltas_all=deltas, ngenes=d["ngenes"], seg_table_filtered=seg), ngene_filter=150,
+                        prep_mode="intersect")
+    df = out["df"]
+    g = load_golden(f"sampler_{sampler}.npz")
+    rows = {b: i for i, b in enumerate(df.rownames)}
+    cols = {c: j for j, c in enumerate(df.colnames)}
+    ri = [rows[b] for b in g["cell_names"]]
+    ci = [cols[c] for c in g["seg_names"]]
+    sub = np.minimum(df.values[np.ix_(ri, ci)], cap)
+    assert sub.shape == g["X"].shape
+    assert np.array_equal(sub, g["X"])
+
+
+def test_prepcovmatrix_union_and_errors():
+    from clonalscope_b200 import PrepCovMatrix
+    deltas = [(["a", "b", "c"], np.array([1.0, 2.0, 3.0])), (["c", "a", "d"], np.array([4.0, 5.0, 6.0]))]
+    seg = dict(chr=np.array(["1", "2"]), start=np.array([0.0, 600000.0]), end=np.array([100.0, 1200000.0]))
+    obj = dict(deltas_all=deltas, ngenes=np.array([300, 300]), seg_table_filtered=seg)
+    u = PrepCovMatrix(obj, ngene_filter=200, ncell_filter=0, prep_mode="union")["df"]
+    assert u.rownames == ["a", "b", "c", "d"] and u.colnames == ["chr1-0-100", "chr2-6e+05-1200000"]
+    assert np.isnan(u.values[1, 1]) and np.isnan(u.values[3, 0]) and u.values[2, 1] == 4.0
+    i = PrepCovMatrix(obj, ngene_filter=200, ncell_filter=0, prep_mode="intersect")["df"]
+    assert i.rownames == ["a", "c"] and np.array_equal(i.values, [[1.0, 5.0], [3.0, 4.0]])
+    with pytest.raises(ValueError):
+        PrepCovMatrix(obj, prep_mode="both")
+
+
+def test_mcmctrim_slicing_and_quirk():
+    from clonalscope_b200 import MCMCtrim
+    niter, N = 200, 7
+    Z = np.arange(niter * N).reshape(niter, N)
+    obj = dict(results=dict(Zall=Z, Uall=list(range(niter)), sigma_all=list(range(niter)),
+                            Likelihood=np.arange(niter, dtype=float)), priors={}, data=None)
+    t = MCMCtrim(obj)
+    assert t["trim"] == dict(burnin=100, thinning=1)
+    assert np.array_equal(t["results"]["Zall"], Z[100:]) and t["results"]["Uall"] == list(range(100, 200))
+    t3 = MCMCtrim(obj, burnin=50, thinning=3)
+    assert np.array_equal(t3["results"]["Zall"], Z[50::3])  # 50 rows
+    # reference quirk (R/MCMCtrim.R:33-36): the lists are indexed with the thinned nrow -> 17 entries
+    assert t3["results"]["Uall"] == [50 + 3 * i for i in range(17)]
+    assert len(t3["results"]["Likelihood"]) == 17
+    with pytest.raises(ValueError):
+        MCMCtrim(obj, burnin=200)
+    short = dict(results=dict(Zall=Z[:30], Uall=list(range(30)), sigma_all=list(range(30)),
+                              Likelihood=np.arange(30.0)), priors={}, data=None)
+    assert MCMCtrim(short)["trim"]["burnin"] == 15
+
+
+def test_bayesnonparcluster_argument_errors(cs):
+    X = np.ones((5, 3))
+    with pytest.raises(ValueError):
+        cs.BayesNonparCluster(X, U0=np.ones((2, 4)))
+    with pytest.raises(ValueError):
+        cs.BayesNonparCluster(X, cna_states_WGS=[1, 1, 1], sigmas0=[0.1, 0.2])
+    with pytest.raises(ValueError):
+        cs.BayesNonparCluster(X, cna_states_WGS=[1, 1, 1], Z0=[1, 2])
+
+
+def test_no_gpu_means_loud_failure(cs):
+    """Without a CUDA device the product path must fail, never fall back to the CPU."""
+    L = cs.lib()
+    if L.cs_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(cs.ClonalscopeError):
+        cs.loglik_matrix(np.ones((4, 2)), np.ones((1, 2)), 0.25)
+    with pytest.raises(cs.ClonalscopeError):
+        cs.majority_vote(np.ones((3, 4), dtype=np.int32))
