@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the cell-clustering hot path (BASELINE.json).
+
+Workload (BASELINE.json configs[3]): synthetic 100k cells x 30k genes -> 15k 200-kb bins
+-> 300 segments, 1 GPU.  A "step" is one complete BayesNonparCluster chain (niter = 200
+sweeps over 100,000 cells x 300 segments, Philox mode, sequential within-sweep order kept);
+the metric is Gibbs cell-updates/s = N * niter / time.  The gene->bin aggregation of the
+100k x 30k count matrix (nnz ~ 2e8) is timed in the same run and reported under "binning"
+as GB/s against the measured HBM peak.
+
+  value     device-resident: inputs already in HBM, CUDA events on the chain's stream
+  e2e       through the C ABI with HOST buffers (cs_ncrp_gibbs): H2D of X, the chain,
+            D2H of Zall / Uall / sigma / Likelihood inside the timed region
+  roofline  dominant kernel of the step (prepare_kernel: scores every cell against every
+            live cluster + proposal + speculative draw), algorithmic bytes = N*S*8 per launch
+  cpu_baseline  the CPU oracle (validated restatement of the reference's R algorithm,
+            R-compatible RNG, 1 core) on a bounded sample of the same workload
+
+`--impl reference` times the reference's own algorithm on the host cores (oracle port in
+R-compatible mode, one independent chain per core) on the same workload/metric.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nCRP Gibbs cell-updates/sec at 100k cells x 300 segs; bin-count GB/s vs HBM"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------ CPU arms
+def _cpu_chain(args):
+    """one R-compatible chain of `niter` sweeps on the CPU oracle (a worker process)."""
+    N, R, niter, seed = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(N, R=R)
+    Z0 = O.loglik_matrix(s["X"], s["U0"], s["sigmas0"]).argmax(axis=1).astype(np.int32) + 1
+    t = time.perf_counter()
+    O.gibbs(s["X"], s["U0"], Z0, s["sigmas0"], 2.0, 2.0, niter, seed, rng_mode=O.RNG_R, ucap_rows=niter * 512)
+    return time.perf_counter() - t
+
+
+def cpu_gibbs_rate(N, R, niter, procs):
+    """cell-updates/s of the CPU port: `procs` independent chains, one per core."""
+    import multiprocessing as mp
+    if procs == 1:
+        dt = _cpu_chain((N, R, niter, 200))
+        return N * niter / dt, dt
+    with mp.get_context("spawn").Pool(procs) as pool:
+        t = time.perf_counter()
+        pool.map(_cpu_chain, [(N, R, niter, 200 + i) for i in range(procs)])
+        dt = time.perf_counter() - t
+    return procs * N * niter / dt, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's own (single-threaded R) algorithm, restated in C and
+    validated bit-for-bit against its shipped outputs, one independent chain per host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    O.build()
+    N, R, sweeps = a.cells, a.segs, 1
+    for _ in range(a.warmup):
+        cpu_gibbs_rate(max(1000, N // 50), R, 1, cores)
+    tot_t, tot_u = 0.0, 0.0
+    for _ in range(a.steps):
+        rate, dt = cpu_gibbs_rate(N, R, sweeps, cores)
+        tot_t += dt
+        tot_u += rate * dt
+    value = tot_u / tot_t
+    sample = (f"{cores} independent chains x {sweeps} sweep(s) of the {N} x {R} workload per step "
+              f"(R-compatible RNG, every sample.int heap-sorted as in base R)")
+    line = dict(metric=METRIC, value=value, unit="cell-updates/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=1e3 * tot_t / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=f"synthetic {N} cells x {R} segments, K_true=12, alpha=beta=2", niter=sweeps),
+                cpu_baseline=dict(value=value, unit="cell-updates/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ GPU arm
+def synth_counts_gpu(torch, dev, N, G, seed=1001, mean_genes=2000):
+    """gene x cell counts on the device (CSC slots), SURVEY §8d shape: per-gene weights
+    LogNormal(0,1.5), per-cell number of expressed genes ~ LogNormal(ln 2000, 0.4) clipped to
+    [200, 8000], Poisson-sampled inclusion proportional to the weights, values Geometric(0.6)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    w = torch.exp(1.5 * torch.randn(G, generator=g, device=dev, dtype=torch.float32))
+    m = torch.exp(np.log(mean_genes) + 0.4 * torch.randn(N, generator=g, device=dev)).round().clamp(200, 8000)
+    rows, counts = [], []
+    chunk = 4096
+    for c0 in range(0, N, chunk):
+        mc = m[c0:c0 + chunk]
+        s = mc / w.sum()
+        for _ in range(12):  # scale so that sum_g min(1, s*w_g) = m_c
+            p = (s[:, None] * w[None, :]).clamp(max=1.0)
+            s = s * mc / p.sum(dim=1)
+        p = (s[:, None] * w[None, :]).clamp(max=1.0)
+        hit = torch.rand(p.shape, generator=g, device=dev) < p
+        counts.append(hit.sum(dim=1))
+        rows.append(hit.nonzero()[:, 1].to(torch.int32))
+    counts = torch.cat(counts)
+    colptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    colptr[1:] = torch.cumsum(counts, 0)
+    rowidx = torch.cat(rows)
+    u = torch.rand(rowidx.numel(), generator=g, device=dev, dtype=torch.float32)
+    x = (torch.log(u) / np.log(0.4)).floor().clamp(0, 32766).to(torch.float64) + 1.0
+    return colptr, rowidx, x
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import clonalscope_b200 as cs
+    from clonalscope_b200 import _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = cs.lib()
+    assert L.cs_set_device(local) == 0
+    hbm_peak, peak_src = peaks()
+    N, R, niter = a.cells, a.segs, a.niter
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- sampler workload (each rank: an independent chain, seed + rank)
+    s = synth.sampler_input(N, R=R)
+    X = np.asfortranarray(s["X"])
+    U0 = np.asfortranarray(s["U0"])
+    sig0 = np.ascontiguousarray(s["sigmas0"])
+    Z0 = (cs.loglik_matrix(X, s["U0"], sig0).argmax(axis=1) + 1).astype(np.int32)
+    seed = 200 + rank
+    dp = lambda arr, t: arr.ctypes.data_as(C.POINTER(t))  # noqa: E731
+
+    chain = C.c_void_p()
+    rc = L.cs_chain_create(N, R, 0, niter, _lib.RNG_PHILOX, C.byref(chain))
+    assert rc == 0, L.cs_last_error()
+
+    def chain_step(flags):
+        rc = L.cs_chain_init(chain, dp(X, C.c_double), 2, dp(U0, C.c_double), dp(Z0, C.c_int), dp(sig0, C.c_double),
+                             C.c_double(2.0), C.c_double(2.0), C.c_uint32(seed), flags)
+        assert rc == 0, L.cs_last_error()
+        rc = L.cs_chain_run(chain, niter, 1, 1)
+        assert rc == 0, L.cs_last_error()
+        ms = [C.c_double() for _ in range(4)]
+        rc = L.cs_chain_timing(chain, *[C.byref(m) for m in ms])
+        assert rc == 0, L.cs_last_error()
+        return [m.value for m in ms]
+
+    for _ in range(a.warmup):
+        chain_step(0)
+    barrier()
+    run_ms = []
+    with ClockSampler(local) as clk:
+        for _ in range(a.steps):
+            barrier()
+            run_ms.append(chain_step(0)[0])
+        barrier()
+        # kernel-group split (events around every launch group; a separate, untimed-for-value pass)
+        prof = chain_step(2)
+    clocks = clk.summary()
+    sc, ev, rj = C.c_int64(), C.c_int64(), C.c_int64()
+    L.cs_chain_stats(chain, C.byref(sc), C.byref(ev), C.byref(rj))
+    step_ms = max_over_ranks(float(np.mean(run_ms)))
+    value = world * N * niter / (step_ms * 1e-3)
+
+    # ---------------- end to end through the C ABI with host buffers
+    Zall = np.zeros((niter, N), dtype=np.int32, order="F")
+    sigma_all = np.zeros((R, niter), order="F")
+    LLv, L0 = np.zeros(niter), C.c_double()
+    kt_all = np.zeros(niter, dtype=np.int32)
+    ucap = niter * 64
+    u_off = np.zeros(niter + 1, dtype=np.int64)
+    u_labels = np.zeros(ucap, dtype=np.int32)
+    u_rows = np.zeros((ucap, R))
+    opts = _lib.GibbsOpts()
+    opts.rng_mode, opts.device = _lib.RNG_PHILOX, local
+
+    def e2e_step():
+        rc = L.cs_ncrp_gibbs(N, R, dp(X, C.c_double), 2, dp(U0, C.c_double), dp(Z0, C.c_int), dp(sig0, C.c_double),
+                             C.c_double(2.0), C.c_double(2.0), niter, C.c_uint32(seed), C.byref(opts),
+                             dp(Zall, C.c_int), dp(sigma_all, C.c_double), dp(LLv, C.c_double), C.byref(L0),
+                             dp(kt_all, C.c_int), C.c_int64(ucap), dp(u_off, C.c_int64), dp(u_labels, C.c_int),
+                             dp(u_rows, C.c_double), None, None)
+        assert rc == 0, L.cs_last_error()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / a.steps)
+    h2d = X.nbytes + U0.nbytes + Z0.nbytes + sig0.nbytes
+    d2h = Zall.nbytes + sigma_all.nbytes + LLv.nbytes + kt_all.nbytes + int(u_off[-1]) * (R * 8 + 4) + u_off.nbytes
+    e2e = dict(value=world * N * niter / (e2e_ms * 1e-3), unit="cell-updates/s", ms_per_step=e2e_ms,
+               h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h))
+    L.cs_chain_destroy(chain)
+
+    # ---------------- gene -> bin aggregation (cells sharded across ranks, no collective)
+    G, NB = a.genes, a.bin_cells
+    bins, genes = synth.geometry(G=G)
+    map_ptr, map_bin = synth.geometry_map(bins, genes)
+    B = len(bins["chr"])
+    colptr, rowidx, x = synth_counts_gpu(torch, dev, NB, G, seed=1001 + rank)
+    nnz_in = int(colptr[-1].item())
+    plan = C.c_void_p()
+    rc = L.cs_bin_plan_create(G, B, dp(map_ptr, C.c_int32), dp(map_bin, C.c_int32), C.byref(plan))
+    assert rc == 0, L.cs_last_error()
+    out_colptr = torch.zeros(NB + 1, dtype=torch.int64, device=dev)
+    nnz_out = C.c_int64()
+    st = torch.cuda.current_stream().cuda_stream
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    rc = L.cs_bin_counts_dev(plan, NB, vp(colptr), vp(rowidx), vp(x), vp(out_colptr), None, None, 0,
+                             C.byref(nnz_out), C.c_void_p(st))
+    assert rc == 0, L.cs_last_error()
+    cap = nnz_out.value
+    out_rowidx = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_x = torch.empty(cap, dtype=torch.float64, device=dev)
+    bin_bytes = 12 * nnz_in + 12 * cap + 2 * 8 * (NB + 1) + 4 * (G + 1 + len(map_bin))
+
+    def bin_step():
+        rc = L.cs_bin_counts_dev(plan, NB, vp(colptr), vp(rowidx), vp(x), vp(out_colptr), vp(out_rowidx), vp(out_x),
+                                 cap, C.byref(nnz_out), C.c_void_p(st))
+        assert rc == 0, L.cs_last_error()
+
+    for _ in range(max(3, a.warmup)):
+        bin_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bin_ms, fill_ms, count_ms = [], [], []
+    for _ in range(max(5, a.steps)):
+        barrier()
+        e0.record()
+        bin_step()
+        e1.record()
+        torch.cuda.synchronize()
+        bin_ms.append(e0.elapsed_time(e1))
+        t = [C.c_double() for _ in range(3)]
+        L.cs_bin_plan_timing(plan, *[C.byref(v) for v in t])
+        count_ms.append(t[0].value)
+        fill_ms.append(t[2].value)
+    bms = max_over_ranks(float(np.mean(bin_ms)))
+    fms = float(np.mean(fill_ms))
+    binning = dict(value=world * bin_bytes / (bms * 1e-3) / 1e9, unit="GB/s (algorithmic bytes / device time, count+scan+fill)",
+                   ms=bms, cells=NB * world, genes=G, bins=B, nnz_in=nnz_in, nnz_out=cap,
+                   algorithmic_bytes=bin_bytes, count_kernel_ms=float(np.mean(count_ms)), fill_kernel_ms=fms,
+                   frac_of_hbm_peak=bin_bytes / (bms * 1e-3) / 1e9 / hbm_peak,
+                   fill_kernel_gbs=(12 * nnz_in + 12 * cap) / (fms * 1e-3) / 1e9,
+                   l2_note="inputs+outputs (~5 GB) exceed the 126 MB L2")
+    # binning end to end with host buffers (R layout), bounded to e2e_bin_cells
+    nb2 = min(NB, a.e2e_bin_cells)
+    cp_h = colptr[:nb2 + 1].cpu().numpy().astype(np.int32)
+    ri_h = rowidx[:int(cp_h[-1])].cpu().numpy()
+    x_h = x[:int(cp_h[-1])].cpu().numpy()
+    from clonalscope_b200.api import bin_counts_csc
+    bin_counts_csc(G, nb2, B, cp_h, ri_h, x_h, map_ptr, map_bin)
+    t0 = time.perf_counter()
+    ocp, ori, ox = bin_counts_csc(G, nb2, B, cp_h, ri_h, x_h, map_ptr, map_bin)
+    dt = time.perf_counter() - t0
+    binning["e2e"] = dict(cells=nb2, ms=dt * 1e3, gbs=(12 * int(cp_h[-1]) + 12 * len(ori)) / dt / 1e9,
+                          h2d_bytes=int(cp_h.nbytes + ri_h.nbytes + x_h.nbytes), d2h_bytes=int(ocp.nbytes + ori.nbytes + ox.nbytes))
+    L.cs_bin_plan_destroy(plan)
+
+    # ---------------- CPU baseline on the box's host cores (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        O.build()
+        cs_n = min(N, a.cpu_cells)
+        rate, dt = cpu_gibbs_rate(cs_n, R, a.cpu_sweeps, 1)
+        t0 = time.perf_counter()
+        nb3 = min(nb2, 5000)
+        O.bin_counts(G, nb3, B, cp_h[:nb3 + 1].astype(np.int64), ri_h, x_h, map_ptr, map_bin)
+        bdt = time.perf_counter() - t0
+        cpu = dict(value=rate, unit="cell-updates/s", cores=1, kind="port",
+                   sample=f"first {a.cpu_sweeps} sweeps of {cs_n} cells x {R} segments, R-compatible RNG "
+                          f"(the reference is single-threaded R; this is its C restatement, {dt:.1f} s)",
+                   host_cores_available=os.cpu_count(),
+                   binning_gbs=24.0 * int(cp_h[nb3]) / bdt / 1e9,
+                   binning_sample=f"sparse restatement, {nb3} cells, 1 core")
+
+    if rank == 0:
+        prep_ms = prof[1] / niter
+        alg_bytes = N * R * 8
+        ach = alg_bytes / (prep_ms * 1e-3) / 1e9
+        line = dict(
+            metric=METRIC, value=value, unit="cell-updates/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
+            ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+            data="synthetic",
+            config=dict(workload=f"synthetic {N} cells x {R} segments (K_true=12, alpha=beta=2, sigmas0=0.25), "
+                                 f"niter={niter}, Philox; one independent chain per GPU",
+                        step="one full chain of niter sweeps", l2="per-sweep working set (X 240 MB + Q + J) exceeds the 126 MB L2",
+                        binning=f"{NB} cells x {G} genes -> {B} bins per GPU"),
+            e2e=e2e, gpu_launches=int(a.steps * niter * 12),
+            roofline=dict(bound="hbm", kernel="prepare_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
+                          frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
+                          note="latency/FP64-issue bound sweep: algorithmic bytes are only N*S*8 per launch",
+                          ms_per_launch=prep_ms, share_of_step=prof[1] / max(prof[0], 1e-9)),
+            sweep_split_ms=dict(run=prof[0], prepare=prof[1], scan=prof[2], end_of_sweep=prof[3]),
+            scan=dict(cells_scanned=int(sc.value), events=int(ev.value)),
+            binning=binning, clocks=clocks)
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=100000)
+    ap.add_argument("--segs", type=int, default=300)
+    ap.add_argument("--niter", type=int, default=200)
+    ap.add_argument("--genes", type=int, default=30000)
+    ap.add_argument("--bin-cells", type=int, default=100000)
+    ap.add_argument("--e2e-bin-cells", type=int, default=20000)
+    ap.add_argument("--cpu-cells", type=int, default=100000)
+    ap.add_argument("--cpu-sweeps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

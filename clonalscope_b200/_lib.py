@@ -16,10 +16,10 @@ RNG_R, RNG_PHILOX = 0, 1
 SYMBOLS = [
     "cs_version", "cs_last_error", "cs_device_count", "cs_set_device",
     "cs_bin_counts_begin", "cs_bin_counts_fetch", "cs_bin_counts_free",
-    "cs_bin_plan_create", "cs_bin_plan_destroy", "cs_bin_counts_dev",
+    "cs_bin_plan_create", "cs_bin_plan_destroy", "cs_bin_plan_timing", "cs_bin_counts_dev",
     "cs_loglik_matrix", "cs_loglik_matrix_dev",
     "cs_ncrp_gibbs", "cs_chain_create", "cs_chain_init", "cs_chain_run", "cs_chain_sync",
-    "cs_chain_sweeps_done", "cs_chain_stats", "cs_chain_fetch", "cs_chain_destroy",
+    "cs_chain_sweeps_done", "cs_chain_timing", "cs_chain_stats", "cs_chain_fetch", "cs_chain_destroy",
     "cs_ncrp_gibbs_allele",
     "cs_majority_vote", "cs_majority_vote_dev",
     "cs_cluster_stats_dev", "cs_sigma_stats_dev",

@@ -21,6 +21,7 @@
 // as Matrix(sparse=TRUE) does; that rare case triggers a compaction pass.
 #include "cs_common.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -344,19 +345,335 @@ bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
     }
 }
 
-// moves column c from the padded offsets (old_colptr) to the compact ones
+// ---- streaming path (regular maps) -------------------------------------------
+// When every gene's bins are contiguous and their first bin is non-decreasing in gene
+// order (genes in genomic / GTF order over sorted tiles — what Cell Ranger matrices and
+// the reference's 200-kb tiles give), a CSC column is a stream of intervals [b0, b0+nh)
+// sorted by b0.  One WARP then aggregates one column with O(1) state: an interval "owns"
+// the bins no earlier interval covered (prefix max of the interval ends), owned bins get
+// consecutive output ranks (warp prefix sum) — ascending row order for free — and a bin
+// is final as soon as the stream's b0 passes it.  Values accumulate in a small per-warp
+// ring indexed by bin; finished ranks are flushed densely (coalesced stores).
+constexpr int STREAM_THREADS = 512;
+constexpr int STREAM_WARPS = STREAM_THREADS / 32;
+constexpr int RING = 512; // bins a warp keeps in flight; wider batches are split
+
+__device__ __forceinline__ int warp_incl_max(int v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(CS_FULL, v, off);
+        if (lane >= off) v = max(v, t);
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_sum(int v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(CS_FULL, v, off);
+        if (lane >= off) v += t;
+    }
+    return v;
+}
+
+constexpr int COUNT_UNROLL = 4;
+__global__ void __launch_bounds__(STREAM_THREADS)
+bin_count_stream_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                        const uint32_t *__restrict__ gmap, int *__restrict__ counts)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * STREAM_WARPS;
+    for (int c = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5); c < N; c += nwarps) {
+        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+        int cov = 0, cnt = 0;
+        for (int64_t e = e0; e < e1; e += 32 * COUNT_UNROLL) {
+            int g[COUNT_UNROLL];
+            uint32_t w[COUNT_UNROLL];
+#pragma unroll
+            for (int u = 0; u < COUNT_UNROLL; u++) {
+                const int64_t idx = e + 32 * u + lane;
+                g[u] = (idx < e1) ? __ldcs(rowidx + idx) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < COUNT_UNROLL; u++) w[u] = (g[u] >= 0) ? __ldg(gmap + g[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < COUNT_UNROLL; u++) {
+                const int nh = w[u] >> 20, b0 = w[u] & 0xFFFFF;
+                const int hi = nh ? b0 + nh : 0;
+                const int pm = warp_incl_max(hi, lane);
+                int prev = __shfl_up_sync(CS_FULL, pm, 1);
+                if (lane == 0) prev = 0;
+                prev = max(prev, cov);
+                if (nh) cnt += max(0, hi - max(b0, prev));
+                cov = max(cov, __shfl_sync(CS_FULL, pm, 31));
+            }
+        }
+        for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(CS_FULL, cnt, off);
+        if (lane == 0) counts[c] = cnt;
+    }
+}
+
+// EPL consecutive entries per lane and step (one 128-bit load of row indices, two of
+// values); all warp-wide scans are amortised over 32*EPL entries.  Index arithmetic is
+// 32-bit and column-relative; the common case (one bin per gene) is straight-line code.
+constexpr int EPL = 4;
+constexpr int FILL_RING = 1024;           // bins a warp keeps in flight; wider steps are split
+constexpr int FILL_STREAM_THREADS = 256;  // 8 warps x 6 KB of rings
+constexpr int FILL_STREAM_WARPS = FILL_STREAM_THREADS / 32;
+
+template <typename Acc>
+struct MagAcc; // exactness guard: sum of |value| * nbins per column
+template <>
+struct MagAcc<int> {
+    unsigned long long s = 0;
+    __device__ __forceinline__ void add(int iv, int nh) { s += (unsigned long long)(unsigned)abs(iv) * (unsigned)nh; }
+    __device__ __forceinline__ bool overflow(int lane)
+    {
+        unsigned long long t = s;
+        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(CS_FULL, t, off);
+        (void)lane;
+        return t >= 2147483647ull;
+    }
+};
+template <>
+struct MagAcc<double> {
+    __device__ __forceinline__ void add(double, int) {}
+    __device__ __forceinline__ bool overflow(int) { return false; }
+};
+
+template <typename Acc>
+__global__ void __launch_bounds__(FILL_STREAM_THREADS, 4)
+bin_fill_stream_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                       const double *__restrict__ x, const uint32_t *__restrict__ gmap,
+                       const int64_t *__restrict__ out_colptr, int32_t *__restrict__ out_rowidx,
+                       double *__restrict__ out_x, int64_t out_cap, int *__restrict__ counts_actual,
+                       int *__restrict__ flags)
+{
+    constexpr int M = FILL_RING - 1;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Acc *s_ring_all = reinterpret_cast<Acc *>(s_raw);
+    uint16_t *s_brk_all = reinterpret_cast<uint16_t *>(s_ring_all + FILL_STREAM_WARPS * FILL_RING);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Acc *ring = s_ring_all + wid * FILL_RING;    // value of bin b at ring[b & M]
+    uint16_t *brk = s_brk_all + wid * FILL_RING; // bin of output rank r at brk[r & M]
+    if (out_colptr[N] > out_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[FLAG_CAP] = 1;
+        return;
+    }
+    const int64_t nnz_total = colptr[N];
+    for (int i = lane; i < FILL_RING; i += 32) ring[i] = (Acc)0;
+    __syncwarp();
+    const int nwarps = gridDim.x * FILL_STREAM_WARPS;
+    for (int c = blockIdx.x * FILL_STREAM_WARPS + wid; c < N; c += nwarps) {
+        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+        const int64_t base4 = e0 & ~(int64_t)3;
+        const int head = (int)(e0 - base4);            // entries of the previous column in the first group
+        const int nent = (int)(e1 - base4);            // column-relative end
+        const int64_t o = out_colptr[c];
+        int32_t *__restrict__ orow = out_rowidx + o;
+        double *__restrict__ oval = out_x + o;
+        const int32_t *__restrict__ rsrc = rowidx + base4;
+        const double *__restrict__ xsrc = x + base4;
+        const bool tail_safe = base4 + (((int64_t)nent + 3) & ~(int64_t)3) <= nnz_total; // vector loads stay in bounds
+        int assigned = 0, emitted = 0, cov = 0, nzero = 0;
+        bool inexact = false;
+        MagAcc<Acc> mag;
+
+        // emit every pending rank whose bin is below `limit` (the stream has passed it)
+        auto flush = [&](int limit) {
+            while (emitted < assigned) {
+                const int r = emitted + lane;
+                const bool ok = r < assigned;
+                const int b = ok ? (int)brk[r & M] : 0x7fffffff;
+                const bool fin = b < limit;
+                const int k = __popc(__ballot_sync(CS_FULL, fin)); // bins ascend with rank: a prefix
+                if (fin) {
+                    const Acc v = ring[b & M];
+                    ring[b & M] = (Acc)0;
+                    __stcs(oval + r, (double)v);
+                    nzero += (v == (Acc)0);
+                }
+                emitted += k;
+                if (k < 32) break;
+            }
+            __syncwarp();
+        };
+
+        int nh[EPL], b0[EPL];
+        Acc iv[EPL];
+        // one step: the entries whose bit is set in `en` (per lane) join the stream
+        auto step = [&](unsigned en) {
+            int lanemax = 0;
+#pragma unroll
+            for (int k = 0; k < EPL; k++)
+                if ((en >> k) & 1u) lanemax = max(lanemax, b0[k] + nh[k]);
+            const int pm = warp_incl_max(lanemax, lane);
+            int prev = __shfl_up_sync(CS_FULL, pm, 1);
+            if (lane == 0) prev = 0;
+            prev = max(prev, cov);
+            int lo[EPL], own[EPL], lane_own = 0;
+#pragma unroll
+            for (int k = 0; k < EPL; k++) {
+                const bool on = (en >> k) & 1u;
+                const int hi = b0[k] + nh[k];
+                lo[k] = max(b0[k], prev);
+                own[k] = on ? max(0, hi - lo[k]) : 0;
+                prev = on ? max(prev, hi) : prev;
+                lane_own += own[k];
+            }
+            const int inc = warp_incl_sum(lane_own, lane);
+            int rk = assigned + inc - lane_own;
+#pragma unroll
+            for (int k = 0; k < EPL; k++) {
+                if (own[k] > 0) {
+                    brk[rk & M] = (uint16_t)lo[k];
+                    __stcs(orow + rk, lo[k]);
+                    if (own[k] > 1) {
+#pragma unroll 1
+                        for (int t = 1; t < own[k]; t++) {
+                            brk[(rk + t) & M] = (uint16_t)(lo[k] + t);
+                            __stcs(orow + rk + t, lo[k] + t);
+                        }
+                    }
+                    rk += own[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < EPL; k++) {
+                if ((en >> k) & 1u) {
+                    atomicAdd(&ring[b0[k] & M], iv[k]);
+                    if (nh[k] > 1) {
+#pragma unroll 1
+                        for (int t = 1; t < nh[k]; t++) atomicAdd(&ring[(b0[k] + t) & M], iv[k]);
+                    }
+                }
+            }
+            assigned += __shfl_sync(CS_FULL, inc, 31);
+            cov = max(cov, __shfl_sync(CS_FULL, pm, 31));
+            __syncwarp();
+        };
+
+        // raw loads of the next step are issued before the current one is processed
+        int4 g4n;
+        double2 v01n, v23n;
+        auto load = [&](int pos) { // pos: column-relative index of this lane's group (multiple of 4)
+            g4n = make_int4(-1, -1, -1, -1);
+            v01n = make_double2(0, 0);
+            v23n = make_double2(0, 0);
+            if (pos < nent) {
+                if (tail_safe) {
+                    g4n = *reinterpret_cast<const int4 *>(rsrc + pos);
+                    v01n = *reinterpret_cast<const double2 *>(xsrc + pos);
+                    v23n = *reinterpret_cast<const double2 *>(xsrc + pos + 2);
+                } else { // last column(s) of the matrix: stay inside the arrays
+                    int gg[4] = {-1, -1, -1, -1};
+                    double vv[4] = {0, 0, 0, 0};
+                    for (int k = 0; k < 4; k++)
+                        if (pos + k < nent) {
+                            gg[k] = rsrc[pos + k];
+                            vv[k] = xsrc[pos + k];
+                        }
+                    g4n = make_int4(gg[0], gg[1], gg[2], gg[3]);
+                    v01n = make_double2(vv[0], vv[1]);
+                    v23n = make_double2(vv[2], vv[3]);
+                }
+            }
+        };
+        load(lane * EPL);
+        for (int p0 = 0; p0 < nent; p0 += 32 * EPL) {
+            const int pos = p0 + lane * EPL;
+            const int g[EPL] = {g4n.x, g4n.y, g4n.z, g4n.w};
+            const double v[EPL] = {v01n.x, v01n.y, v23n.x, v23n.y};
+            uint32_t w[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; k++) {
+                const bool valid = pos + k >= head && pos + k < nent;
+                w[k] = valid ? __ldg(gmap + g[k]) : 0u;
+            }
+            load(pos + 32 * EPL);
+            unsigned en = 0;
+            int lane_b0 = 0x7fffffff, lane_hi = 0;
+#pragma unroll
+            for (int k = EPL - 1; k >= 0; k--) {
+                nh[k] = w[k] >> 20;
+                b0[k] = w[k] & 0xFFFFF;
+                iv[k] = (Acc)0;
+                if (nh[k]) {
+                    en |= 1u << k;
+                    if (!AccOps<Acc>::conv(v[k], iv[k])) inexact = true;
+                    mag.add(iv[k], nh[k]);
+                    lane_b0 = b0[k];
+                    lane_hi = max(lane_hi, b0[k] + nh[k]);
+                }
+            }
+            unsigned pending = __ballot_sync(CS_FULL, en != 0);
+            while (pending) {
+                const int first = __ffs(pending) - 1;
+                const int bmin = __shfl_sync(CS_FULL, lane_b0, first);
+                flush(bmin);
+                const bool mine = (pending >> lane) & 1u;
+                const unsigned nofit = __ballot_sync(CS_FULL, mine && lane_hi > bmin + FILL_RING);
+                if (nofit == 0) { // the usual case: the whole step fits the ring
+                    step(mine ? en : 0u);
+                    break;
+                }
+                if ((nofit >> first) & 1u) {
+                    // the first lane's own entries span more than a ring (very sparse cell):
+                    // feed them one at a time
+#pragma unroll 1
+                    for (int k = 0; k < EPL; k++) {
+                        const unsigned has = __shfl_sync(CS_FULL, en, first) & (1u << k);
+                        if (!has) continue;
+                        const int bk = (k == 0) ? b0[0] : (k == 1) ? b0[1] : (k == 2) ? b0[2] : b0[3];
+                        flush(__shfl_sync(CS_FULL, bk, first));
+                        step(lane == first ? (1u << k) : 0u);
+                    }
+                    pending &= ~(1u << first);
+                    continue;
+                }
+                const unsigned act = pending & ((1u << (__ffs(nofit) - 1)) - 1u);
+                step(((act >> lane) & 1u) ? en : 0u);
+                pending &= ~act;
+            }
+        }
+        flush(0x7fffffff);
+        for (int off = 16; off >= 1; off >>= 1) nzero += __shfl_xor_sync(CS_FULL, nzero, off);
+        const bool over = mag.overflow(lane);
+        if (inexact || over) flags[FLAG_INEXACT] = 1;
+        if (lane == 0) {
+            counts_actual[c] = assigned - nzero;
+            if (nzero) flags[FLAG_SHRUNK] = 1;
+        }
+    }
+}
+
+// closes the gaps left by dropped zero sums: column c's first nwritten entries (all of its
+// padded range when nwritten == NULL) are copied, zeros skipped, to the compact offsets
 __global__ void compact_columns_kernel(int N, const int64_t *__restrict__ old_colptr,
+                                       const int *__restrict__ nwritten,
                                        const int64_t *__restrict__ new_colptr,
                                        const int32_t *__restrict__ src_i,
                                        const double *__restrict__ src_x,
                                        int32_t *__restrict__ dst_i, double *__restrict__ dst_x)
 {
-    for (int c = blockIdx.x; c < N; c += gridDim.x) {
-        const int64_t so = old_colptr[c], d0 = new_colptr[c];
-        const int n = (int)(new_colptr[c + 1] - d0);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            dst_i[d0 + i] = src_i[so + i];
-            dst_x[d0 + i] = src_x[so + i];
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < N; c += nwarps) {
+        const int64_t so = old_colptr[c];
+        int64_t d = new_colptr[c];
+        const int n = nwritten ? nwritten[c] : (int)(old_colptr[c + 1] - so);
+        for (int i = 0; i < n; i += 32) {
+            const bool ok = i + lane < n;
+            const double v = ok ? src_x[so + i + lane] : 0.0;
+            const bool keep = ok && v != 0.0;
+            const unsigned m = __ballot_sync(CS_FULL, keep);
+            if (keep) {
+                const int64_t pos = d + __popc(m & ((1u << lane) - 1u));
+                dst_i[pos] = src_i[so + i + lane];
+                dst_x[pos] = v;
+            }
+            d += __popc(m);
         }
     }
 }
@@ -366,6 +683,7 @@ __global__ void compact_columns_kernel(int N, const int64_t *__restrict__ old_co
 // ----------------------------------------------------------------- plan / API
 struct cs_bin_plan {
     int G = 0, B = 0;
+    bool regular = false; // contiguous hits with non-decreasing first bin: streaming kernels apply
     DevBuf<uint32_t> gmap;
     DevBuf<int32_t> map_ptr, map_bin;
     DevBuf<int> counts, counts2, flags;
@@ -373,9 +691,13 @@ struct cs_bin_plan {
     DevBuf<int32_t> tmp_i;
     DevBuf<double> tmp_x;
     int *h_pinned = nullptr; // NFLAGS ints + 1 int64 (nnz)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // count | scan | fill boundaries
+    bool timed = false;
     ~cs_bin_plan()
     {
         if (h_pinned) cudaFreeHost(h_pinned);
+        for (auto e : ev)
+            if (e) cudaEventDestroy(e);
     }
 };
 
@@ -410,6 +732,19 @@ extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const in
     cs_bin_plan *p = new cs_bin_plan();
     p->G = G;
     p->B = B;
+    {
+        bool reg = true;
+        int last_b0 = 0;
+        for (int g = 0; g < G && reg; g++) {
+            if (gm[g] == 0u) continue; // no hits
+            if (gm[g] == GMAP_ESC || (int)(gm[g] >> 20) >= RING) { reg = false; break; } // RING <= FILL_RING
+            const int b0 = gm[g] & 0xFFFFF;
+            if (b0 < last_b0) reg = false;
+            last_b0 = b0;
+        }
+        if (getenv("CS_BIN_FORCE_GENERAL")) reg = false; // profiling / test hook
+        p->regular = reg;
+    }
     int rc = CS_OK;
     do {
 #define TRY(call) if ((call) != cudaSuccess) { cs_set_error("cs_bin_plan_create: %s", cudaGetErrorString(cudaGetLastError())); rc = CS_ERR_CUDA; break; }
@@ -419,6 +754,7 @@ extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const in
         TRY(p->flags.alloc(NFLAGS));
         TRY(p->grand.alloc(1));
         TRY(cudaMallocHost((void **)&p->h_pinned, 64));
+        for (int i = 0; i < 4; i++) TRY(cudaEventCreate(&p->ev[i]));
         TRY(cudaMemcpy(p->gmap.p, gm.data(), sizeof(uint32_t) * G, cudaMemcpyHostToDevice));
         TRY(cudaMemcpy(p->map_ptr.p, map_ptr, sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice));
         if (nhits) TRY(cudaMemcpy(p->map_bin.p, map_bin, sizeof(int32_t) * nhits, cudaMemcpyHostToDevice));
@@ -434,11 +770,38 @@ extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const in
 
 extern "C" void cs_bin_plan_destroy(cs_bin_plan *plan) { delete plan; }
 
+extern "C" int cs_bin_plan_timing(cs_bin_plan *p, double *count_ms, double *scan_ms, double *fill_ms)
+{
+    CS_REQUIRE(p && p->timed, "cs_bin_plan_timing: no completed count+fill call to report");
+    float ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]));
+    if (count_ms) *count_ms = ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]));
+    if (scan_ms) *scan_ms = ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]));
+    if (fill_ms) *fill_ms = ms;
+    return CS_OK;
+}
+
 template <typename Acc>
 static int launch_fill(cs_bin_plan *p, int N, const int64_t *d_colptr, const int32_t *d_rowidx,
                        const double *d_x, const int64_t *d_out_colptr, int32_t *d_out_rowidx,
                        double *d_out_x, int64_t out_cap, cudaStream_t st)
 {
+    if (p->regular) {
+        const size_t smem = (size_t)FILL_STREAM_WARPS * FILL_RING * (sizeof(Acc) + sizeof(uint16_t));
+        CS_CUDA(cudaFuncSetAttribute(bin_fill_stream_kernel<Acc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_fill_stream_kernel<Acc>, FILL_STREAM_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        int grid = cs_num_sms() * per_sm;
+        if (grid > (N + FILL_STREAM_WARPS - 1) / FILL_STREAM_WARPS) grid = (N + FILL_STREAM_WARPS - 1) / FILL_STREAM_WARPS;
+        bin_fill_stream_kernel<Acc><<<grid, FILL_STREAM_THREADS, smem, st>>>(
+            N, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr, d_out_rowidx, d_out_x, out_cap, p->counts2.p,
+            p->flags.p);
+        CS_CUDA(cudaGetLastError());
+        return CS_OK;
+    }
     const size_t smem = fill_smem_bytes(p->B, sizeof(Acc));
     if (smem > 227 * 1024) {
         cs_set_error("cs_bin_counts: B=%d bins with FP64 accumulators need %zu B of shared memory", p->B, smem);
@@ -487,11 +850,21 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
     const int words = (p->B + 31) / 32;
     int grid1 = cs_num_sms() * 16;
     if (grid1 > N) grid1 = N;
-    bin_count_kernel<<<grid1, COUNT_THREADS, words * 4, st>>>(
-        N, p->B, d_colptr, d_rowidx, p->gmap.p, p->map_ptr.p, p->map_bin.p, p->counts.p);
+    p->timed = false;
+    CS_CUDA(cudaEventRecord(p->ev[0], st));
+    if (p->regular) {
+        int grid = cs_num_sms() * 4;
+        if (grid > (N + STREAM_WARPS - 1) / STREAM_WARPS) grid = (N + STREAM_WARPS - 1) / STREAM_WARPS;
+        bin_count_stream_kernel<<<grid, STREAM_THREADS, 0, st>>>(N, d_colptr, d_rowidx, p->gmap.p, p->counts.p);
+    } else {
+        bin_count_kernel<<<grid1, COUNT_THREADS, words * 4, st>>>(
+            N, p->B, d_colptr, d_rowidx, p->gmap.p, p->map_ptr.p, p->map_bin.p, p->counts.p);
+    }
     CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaEventRecord(p->ev[1], st));
     int rc = run_scan(p, N, p->counts.p, d_out_colptr, st);
     if (rc) return rc;
+    CS_CUDA(cudaEventRecord(p->ev[2], st));
     int64_t *h_nnz = reinterpret_cast<int64_t *>(p->h_pinned + NFLAGS);
     if (!d_out_rowidx) {
         CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -502,6 +875,8 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
     CS_REQUIRE(d_out_x != nullptr, "cs_bin_counts_dev: d_out_x is NULL");
     rc = launch_fill<int>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
     if (rc) return rc;
+    CS_CUDA(cudaEventRecord(p->ev[3], st));
+    p->timed = true;
     CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaMemcpyAsync(p->h_pinned, p->flags.p, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
@@ -525,8 +900,9 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         CS_CUDA(p->tmp_x.reserve((size_t)padded));
         rc = run_scan(p, N, p->counts2.p, p->colptr2.p, st);
         if (rc) return rc;
-        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, p->colptr2.p, d_out_rowidx,
-                                                                 d_out_x, p->tmp_i.p, p->tmp_x.p);
+        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, p->regular ? nullptr : p->counts2.p,
+                                                                 p->colptr2.p, d_out_rowidx, d_out_x, p->tmp_i.p,
+                                                                 p->tmp_x.p);
         CS_CUDA(cudaGetLastError());
         CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CS_CUDA(cudaStreamSynchronize(st));

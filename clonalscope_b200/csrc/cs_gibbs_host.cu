@@ -9,7 +9,8 @@
 
 template <typename T>
 int cs_transpose(int rows, int cols, const T *d_in, T *d_out, cudaStream_t st);
-int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, cudaStream_t st);
+int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, cudaStream_t st,
+                    cudaEvent_t *ev);
 int cs_total_loglik_async(const ChainDev &D, const double *U, const int *Zrows, const double *sig, double *d_out,
                           cudaStream_t st);
 int cs_rmode_run(const ChainDev &D, int lcap, int t0, int t1, int last_sweep, double *scratch, cudaStream_t st);
@@ -26,8 +27,15 @@ struct cs_chain {
     DevBuf<long long> u_off;
     DevBuf<uint32_t> mt;
     DevBuf<ChainScal> scal;
+    // timing of the last cs_chain_run: whole run, and (flags bit 1) per-sweep kernel groups
+    cudaEvent_t run_ev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> sweep_ev;
+    int prof_sweeps = 0;
     ~cs_chain()
     {
+        for (auto e : sweep_ev) cudaEventDestroy(e);
+        for (auto e : run_ev)
+            if (e) cudaEventDestroy(e);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -56,6 +64,8 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     c->niter_cap = niter_cap;
     c->rng_mode = rng_mode;
     CS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CS_CUDA(cudaEventCreate(&c->run_ev[0]));
+    CS_CUDA(cudaEventCreate(&c->run_ev[1]));
     const size_t nx = (size_t)N * R;
     const int nchunks = (N + CS_STAT_CHUNK - 1) / CS_STAT_CHUNK;
     const bool ph = rng_mode == CS_RNG_PHILOX;
@@ -205,17 +215,29 @@ extern "C" int cs_chain_run(cs_chain *c, int nsweeps, int is_last, int sync)
                "cs_chain_run: %d more sweeps exceed niter_cap=%d (done %d)", nsweeps, c->niter_cap, c->sweeps_done);
     const int t0 = c->sweeps_done, t1 = t0 + nsweeps;
     int rc = CS_OK;
+    const bool prof = (c->flags & 2) != 0 && c->rng_mode == CS_RNG_PHILOX;
+    if (prof) {
+        while ((int)c->sweep_ev.size() < 4 * nsweeps) {
+            cudaEvent_t e;
+            CS_CUDA(cudaEventCreate(&e));
+            c->sweep_ev.push_back(e);
+        }
+    }
+    c->prof_sweeps = prof ? nsweeps : 0;
+    CS_CUDA(cudaEventRecord(c->run_ev[0], c->st));
     if (c->rng_mode == CS_RNG_R) {
         if (nsweeps > 0) rc = cs_rmode_run(c->D, c->kcap, t0, t1, is_last ? t1 - 1 : -1, c->mean.p, c->st);
     } else {
         for (int tt = t0; tt < t1 && rc == CS_OK; tt++) {
-            rc = cs_philox_sweep(c->D, tt, is_last && tt == t1 - 1, c->flags & 1, c->rej.p, c->st);
+            rc = cs_philox_sweep(c->D, tt, is_last && tt == t1 - 1, c->flags & 1, c->rej.p, c->st,
+                                 prof ? &c->sweep_ev[4 * (size_t)(tt - t0)] : nullptr);
             double *t = c->D.U;
             c->D.U = c->D.Unext;
             c->D.Unext = t;
         }
     }
     if (rc) return rc;
+    CS_CUDA(cudaEventRecord(c->run_ev[1], c->st));
     c->sweeps_done = t1;
     if (sync) return cs_chain_sync(c);
     return CS_OK;
@@ -243,6 +265,31 @@ extern "C" int cs_chain_sync(cs_chain *c)
 }
 
 extern "C" int cs_chain_sweeps_done(cs_chain *c) { return c ? c->sweeps_done : -1; }
+
+extern "C" int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *scan_ms, double *eos_ms)
+{
+    CS_REQUIRE(c != nullptr, "cs_chain_timing: NULL chain");
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    float ms = 0.f;
+    if (run_ms) {
+        CS_CUDA(cudaEventElapsedTime(&ms, c->run_ev[0], c->run_ev[1]));
+        *run_ms = ms;
+    }
+    double a = 0, b = 0, d = 0;
+    for (int s = 0; s < c->prof_sweeps; s++) {
+        cudaEvent_t *e = &c->sweep_ev[4 * (size_t)s];
+        CS_CUDA(cudaEventElapsedTime(&ms, e[0], e[1]));
+        a += ms;
+        CS_CUDA(cudaEventElapsedTime(&ms, e[1], e[2]));
+        b += ms;
+        CS_CUDA(cudaEventElapsedTime(&ms, e[2], e[3]));
+        d += ms;
+    }
+    if (prepare_ms) *prepare_ms = a;
+    if (scan_ms) *scan_ms = b;
+    if (eos_ms) *eos_ms = d;
+    return CS_OK;
+}
 
 extern "C" int cs_chain_stats(cs_chain *c, int64_t *cells_scanned, int64_t *n_events, int64_t *n_reject)
 {

@@ -625,7 +625,8 @@ __global__ void compact_kernel(ChainDev D, int *__restrict__ rej, int reject_liv
 }
 
 template <int NCH>
-int launch_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, int nsm, cudaStream_t st)
+int launch_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, int nsm, cudaStream_t st,
+                 cudaEvent_t *ev)
 {
     const size_t smem_prep = sizeof(double) * D.R + sizeof(int) * D.kcap;
     const size_t smem_scan = sizeof(double) * D.R + sizeof(int) * 2 * D.kcap;
@@ -633,14 +634,17 @@ int launch_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, i
         CS_CUDA(cudaFuncSetAttribute(prepare_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
         CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     }
+    if (ev) CS_CUDA(cudaEventRecord(ev[0], st));
     if (!force_all) {
         int grid = (D.N + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
         if (grid > nsm * 8) grid = nsm * 8;
         prepare_kernel<NCH><<<grid, PREP_THREADS, smem_prep, st>>>(D, tt, rej);
-    }
-    else
+    } else {
         CS_CUDA(cudaMemsetAsync(D.qcols, 0, sizeof(int) * (size_t)D.N, st));
+    }
+    if (ev) CS_CUDA(cudaEventRecord(ev[1], st));
     scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, force_all, rej);
+    if (ev) CS_CUDA(cudaEventRecord(ev[2], st));
     (void)last;
     CS_CUDA(cudaGetLastError());
     return CS_OK;
@@ -651,15 +655,16 @@ int launch_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, i
 int cs_philox_max_R() { return 1024; }
 
 // one full sweep (asynchronous).  D.U / D.Unext are swapped by the caller afterwards.
-int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, cudaStream_t st)
+int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, cudaStream_t st,
+                    cudaEvent_t *ev)
 {
     const int nsm = cs_num_sms();
     int rc;
-    if (D.R <= 32) rc = launch_sweep<1>(D, tt, last, force_all, rej, nsm, st);
-    else if (D.R <= 64) rc = launch_sweep<2>(D, tt, last, force_all, rej, nsm, st);
-    else if (D.R <= 128) rc = launch_sweep<4>(D, tt, last, force_all, rej, nsm, st);
-    else if (D.R <= 320) rc = launch_sweep<10>(D, tt, last, force_all, rej, nsm, st);
-    else if (D.R <= 1024) rc = launch_sweep<32>(D, tt, last, force_all, rej, nsm, st);
+    if (D.R <= 32) rc = launch_sweep<1>(D, tt, last, force_all, rej, nsm, st, ev);
+    else if (D.R <= 64) rc = launch_sweep<2>(D, tt, last, force_all, rej, nsm, st, ev);
+    else if (D.R <= 128) rc = launch_sweep<4>(D, tt, last, force_all, rej, nsm, st, ev);
+    else if (D.R <= 320) rc = launch_sweep<10>(D, tt, last, force_all, rej, nsm, st, ev);
+    else if (D.R <= 1024) rc = launch_sweep<32>(D, tt, last, force_all, rej, nsm, st, ev);
     else {
         cs_set_error("Philox sampler supports up to 1024 segments (R=%d)", D.R);
         return CS_ERR_UNSUPPORTED;
@@ -678,6 +683,7 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
     record_kernel<<<1, 256, 0, st>>>(D, tt);
     relabel_kernel<<<(D.N + 255) / 256, 256, 0, st>>>(D, tt);
     compact_kernel<<<1, 256, 0, st>>>(D, rej, D.single && tt == 0);
+    if (ev) CS_CUDA(cudaEventRecord(ev[3], st));
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

@@ -71,6 +71,9 @@ typedef struct cs_bin_plan cs_bin_plan;
 int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const int32_t *map_bin,
                        cs_bin_plan **plan);
 void cs_bin_plan_destroy(cs_bin_plan *plan);
+/* device time (CUDA events on the call's stream) of the count, scan and fill kernels of the
+ * last completed cs_bin_counts_dev call that produced output */
+int cs_bin_plan_timing(cs_bin_plan *plan, double *count_ms, double *scan_ms, double *fill_ms);
 /* d_colptr/d_out_colptr: int64[N+1]; d_rowidx/d_out_rowidx: int32; d_x/d_out_x: double.
  * Pass d_out_rowidx == NULL to count only (fills d_out_colptr, *nnz_out).
  * With outputs given, out_cap is their capacity in entries; CS_ERR_UCAP if too small
@@ -110,7 +113,8 @@ typedef struct {
     int device;     /* CUDA ordinal, -1 = current */
     int kcap;       /* Philox: max live clusters within a sweep (0 = 256);
                        R mode: max labels ever created (0 = 4096) */
-    int flags;      /* bit 0: disable speculative evaluation (scan every cell) */
+    int flags;      /* bit 0: disable speculative evaluation (scan every cell);
+                       bit 1: record per-kernel-group CUDA events (cs_chain_timing) */
     int reserved[4];
 } cs_gibbs_opts;
 
@@ -142,6 +146,10 @@ int cs_chain_init(cs_chain *c, const double *X, int K0, const double *U0, const 
 int cs_chain_run(cs_chain *c, int nsweeps, int is_last, int sync);
 int cs_chain_sync(cs_chain *c);
 int cs_chain_sweeps_done(cs_chain *c);
+/* device time of the last cs_chain_run (CUDA events on the chain's stream); with init flag
+ * bit 1 set also the per-sweep totals of the prepare kernel, the scan kernel and the
+ * end-of-sweep kernels.  Synchronises the chain. */
+int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *scan_ms, double *eos_ms);
 /* number of cells the sequential scan kernel had to process (diagnostics) */
 int cs_chain_stats(cs_chain *c, int64_t *cells_scanned, int64_t *n_events, int64_t *n_reject);
 int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double *LL, double *L0,

@@ -153,6 +153,39 @@ def test_binning_edge_cases(cs, oracle):
         bin_counts_csc(G, 1, B, np.array([0, 1], np.int32), np.array([G], np.int32), np.ones(1), map_ptr, map_bin)
 
 
+def test_binning_streaming_path_edge_cases(cs, oracle):
+    """Regular map (contiguous bins, non-decreasing first bin in gene order) -> the warp-per-column
+    streaming kernels: ragged / empty / very sparse columns whose batches span more bins than a
+    warp's ring (forces batch splitting), long genes, zero sums, non-integer and huge values."""
+    rng = np.random.default_rng(21)
+    G, B = 6000, 20000
+    b0 = np.sort(rng.integers(0, B - 400, size=G))
+    nh = rng.choice([0, 1, 1, 1, 1, 2, 3, 12, 300], size=G, p=[.05, .3, .2, .2, .1, .08, .05, .015, .005])
+    map_ptr = np.zeros(G + 1, np.int32)
+    map_ptr[1:] = np.cumsum(nh)
+    map_bin = np.concatenate([np.arange(f, f + n) for f, n in zip(b0, nh)]).astype(np.int32)
+    cols = [np.zeros(0, np.int32), np.array([G - 1], np.int32), np.arange(G, dtype=np.int32)]
+    for m in (1, 2, 3, 5, 31, 32, 33, 64, 65, 100, 1000, 3000):
+        cols.append(np.sort(rng.choice(G, size=m, replace=False)).astype(np.int32))
+    cols += [np.zeros(0, np.int32)] * 3
+    colptr = np.zeros(len(cols) + 1, np.int32)
+    colptr[1:] = np.cumsum([len(c) for c in cols])
+    rowidx = np.concatenate(cols)
+    x = rng.integers(1, 50, size=len(rowidx)).astype(np.float64)
+    N = len(cols)
+    _check_bins(cs, oracle, G, N, B, colptr, rowidx, x, map_ptr, map_bin)
+    x2 = x.copy()
+    x2[colptr[6]:colptr[7]] = 0.0          # a whole column of explicit zeros
+    x2[colptr[12] + 3] = 0.0
+    k = colptr[13]
+    x2[k], x2[k + 1] = 7.0, -7.0           # may or may not share a bin; the oracle decides
+    _check_bins(cs, oracle, G, N, B, colptr, rowidx, x2, map_ptr, map_bin)
+    x3 = x.copy()
+    x3[5] = 2.5e9
+    _check_bins(cs, oracle, G, N, B, colptr, rowidx, x3, map_ptr, map_bin)
+    _check_bins(cs, oracle, G, N, B, colptr, rowidx, x + 0.5, map_ptr, map_bin, exact=False)
+
+
 def test_binning_permutation_invariance(cs):
     """Relabelling the bins permutes the rows of the result and nothing else."""
     from clonalscope_b200.api import bin_counts_csc
