@@ -7,7 +7,11 @@
 // aggregated independently on one CTA:
 //
 //   pass 1  bin_count_kernel   rowidx only (4 B/nz): marks touched bins in a shared
-//                              bitmap, popcounts -> upper bound of nnz per column
+//                              bitmap, popcounts -> upper bound of nnz per column.
+//           bin_count_stream_kernel: when genes are in genomic order over sorted tiles
+//                              (first bins non-decreasing, hits contiguous) a column is a
+//                              stream of sorted intervals and one warp counts it with a
+//                              prefix-max scan — no shared memory, 64 warps per SM
 //   scan    exclusive scan of the per-column counts -> out_colptr
 //   pass 2  bin_fill_kernel    128-bit loads of rowidx/x, gene->bin lookup through a
 //                              packed per-gene word (first_bin | nhits<<20), shared
@@ -21,7 +25,6 @@
 // as Matrix(sparse=TRUE) does; that rare case triggers a compaction pass.
 #include "cs_common.cuh"
 
-#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -345,18 +348,17 @@ bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
     }
 }
 
-// ---- streaming path (regular maps) -------------------------------------------
+// ---- streaming count (regular maps) ------------------------------------------
 // When every gene's bins are contiguous and their first bin is non-decreasing in gene
 // order (genes in genomic / GTF order over sorted tiles — what Cell Ranger matrices and
 // the reference's 200-kb tiles give), a CSC column is a stream of intervals [b0, b0+nh)
-// sorted by b0.  One WARP then aggregates one column with O(1) state: an interval "owns"
-// the bins no earlier interval covered (prefix max of the interval ends), owned bins get
-// consecutive output ranks (warp prefix sum) — ascending row order for free — and a bin
-// is final as soon as the stream's b0 passes it.  Values accumulate in a small per-warp
-// ring indexed by bin; finished ranks are flushed densely (coalesced stores).
+// sorted by b0, and the number of distinct bins it touches is the length of their union:
+// an interval adds the bins no earlier interval covered (prefix max of the interval ends).
+// One warp counts one column with shuffles only.  (Warp-cooperative and lane-per-column
+// streaming FILL kernels built on the same idea were measured at 2.7-11 ms per 100k cells
+// against 3.2 ms for bin_fill_kernel and dropped; see DESIGN.md "Binning: what was tried".)
 constexpr int STREAM_THREADS = 512;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
-constexpr int RING = 512; // bins a warp keeps in flight; wider batches are split
 
 __device__ __forceinline__ int warp_incl_max(int v, int lane)
 {
@@ -367,16 +369,6 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane)
     }
     return v;
 }
-__device__ __forceinline__ int warp_incl_sum(int v, int lane)
-{
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(CS_FULL, v, off);
-        if (lane >= off) v += t;
-    }
-    return v;
-}
-
 constexpr int COUNT_UNROLL = 4;
 __global__ void __launch_bounds__(STREAM_THREADS)
 bin_count_stream_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
@@ -411,240 +403,6 @@ bin_count_stream_kernel(int N, const int64_t *__restrict__ colptr, const int32_t
         }
         for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(CS_FULL, cnt, off);
         if (lane == 0) counts[c] = cnt;
-    }
-}
-
-// EPL consecutive entries per lane and step (one 128-bit load of row indices, two of
-// values); all warp-wide scans are amortised over 32*EPL entries.  Index arithmetic is
-// 32-bit and column-relative; the common case (one bin per gene) is straight-line code.
-constexpr int EPL = 4;
-constexpr int FILL_RING = 1024;           // bins a warp keeps in flight; wider steps are split
-constexpr int FILL_STREAM_THREADS = 256;  // 8 warps x 6 KB of rings
-constexpr int FILL_STREAM_WARPS = FILL_STREAM_THREADS / 32;
-
-template <typename Acc>
-struct MagAcc; // exactness guard: sum of |value| * nbins per column
-template <>
-struct MagAcc<int> {
-    unsigned long long s = 0;
-    __device__ __forceinline__ void add(int iv, int nh) { s += (unsigned long long)(unsigned)abs(iv) * (unsigned)nh; }
-    __device__ __forceinline__ bool overflow(int lane)
-    {
-        unsigned long long t = s;
-        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(CS_FULL, t, off);
-        (void)lane;
-        return t >= 2147483647ull;
-    }
-};
-template <>
-struct MagAcc<double> {
-    __device__ __forceinline__ void add(double, int) {}
-    __device__ __forceinline__ bool overflow(int) { return false; }
-};
-
-template <typename Acc>
-__global__ void __launch_bounds__(FILL_STREAM_THREADS, 4)
-bin_fill_stream_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
-                       const double *__restrict__ x, const uint32_t *__restrict__ gmap,
-                       const int64_t *__restrict__ out_colptr, int32_t *__restrict__ out_rowidx,
-                       double *__restrict__ out_x, int64_t out_cap, int *__restrict__ counts_actual,
-                       int *__restrict__ flags)
-{
-    constexpr int M = FILL_RING - 1;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    Acc *s_ring_all = reinterpret_cast<Acc *>(s_raw);
-    uint16_t *s_brk_all = reinterpret_cast<uint16_t *>(s_ring_all + FILL_STREAM_WARPS * FILL_RING);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    Acc *ring = s_ring_all + wid * FILL_RING;    // value of bin b at ring[b & M]
-    uint16_t *brk = s_brk_all + wid * FILL_RING; // bin of output rank r at brk[r & M]
-    if (out_colptr[N] > out_cap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) flags[FLAG_CAP] = 1;
-        return;
-    }
-    const int64_t nnz_total = colptr[N];
-    for (int i = lane; i < FILL_RING; i += 32) ring[i] = (Acc)0;
-    __syncwarp();
-    const int nwarps = gridDim.x * FILL_STREAM_WARPS;
-    for (int c = blockIdx.x * FILL_STREAM_WARPS + wid; c < N; c += nwarps) {
-        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
-        const int64_t base4 = e0 & ~(int64_t)3;
-        const int head = (int)(e0 - base4);            // entries of the previous column in the first group
-        const int nent = (int)(e1 - base4);            // column-relative end
-        const int64_t o = out_colptr[c];
-        int32_t *__restrict__ orow = out_rowidx + o;
-        double *__restrict__ oval = out_x + o;
-        const int32_t *__restrict__ rsrc = rowidx + base4;
-        const double *__restrict__ xsrc = x + base4;
-        const bool tail_safe = base4 + (((int64_t)nent + 3) & ~(int64_t)3) <= nnz_total; // vector loads stay in bounds
-        int assigned = 0, emitted = 0, cov = 0, nzero = 0;
-        bool inexact = false;
-        MagAcc<Acc> mag;
-
-        // emit every pending rank whose bin is below `limit` (the stream has passed it)
-        auto flush = [&](int limit) {
-            while (emitted < assigned) {
-                const int r = emitted + lane;
-                const bool ok = r < assigned;
-                const int b = ok ? (int)brk[r & M] : 0x7fffffff;
-                const bool fin = b < limit;
-                const int k = __popc(__ballot_sync(CS_FULL, fin)); // bins ascend with rank: a prefix
-                if (fin) {
-                    const Acc v = ring[b & M];
-                    ring[b & M] = (Acc)0;
-                    __stcs(oval + r, (double)v);
-                    nzero += (v == (Acc)0);
-                }
-                emitted += k;
-                if (k < 32) break;
-            }
-            __syncwarp();
-        };
-
-        int nh[EPL], b0[EPL];
-        Acc iv[EPL];
-        // one step: the entries whose bit is set in `en` (per lane) join the stream
-        auto step = [&](unsigned en) {
-            int lanemax = 0;
-#pragma unroll
-            for (int k = 0; k < EPL; k++)
-                if ((en >> k) & 1u) lanemax = max(lanemax, b0[k] + nh[k]);
-            const int pm = warp_incl_max(lanemax, lane);
-            int prev = __shfl_up_sync(CS_FULL, pm, 1);
-            if (lane == 0) prev = 0;
-            prev = max(prev, cov);
-            int lo[EPL], own[EPL], lane_own = 0;
-#pragma unroll
-            for (int k = 0; k < EPL; k++) {
-                const bool on = (en >> k) & 1u;
-                const int hi = b0[k] + nh[k];
-                lo[k] = max(b0[k], prev);
-                own[k] = on ? max(0, hi - lo[k]) : 0;
-                prev = on ? max(prev, hi) : prev;
-                lane_own += own[k];
-            }
-            const int inc = warp_incl_sum(lane_own, lane);
-            int rk = assigned + inc - lane_own;
-#pragma unroll
-            for (int k = 0; k < EPL; k++) {
-                if (own[k] > 0) {
-                    brk[rk & M] = (uint16_t)lo[k];
-                    __stcs(orow + rk, lo[k]);
-                    if (own[k] > 1) {
-#pragma unroll 1
-                        for (int t = 1; t < own[k]; t++) {
-                            brk[(rk + t) & M] = (uint16_t)(lo[k] + t);
-                            __stcs(orow + rk + t, lo[k] + t);
-                        }
-                    }
-                    rk += own[k];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < EPL; k++) {
-                if ((en >> k) & 1u) {
-                    atomicAdd(&ring[b0[k] & M], iv[k]);
-                    if (nh[k] > 1) {
-#pragma unroll 1
-                        for (int t = 1; t < nh[k]; t++) atomicAdd(&ring[(b0[k] + t) & M], iv[k]);
-                    }
-                }
-            }
-            assigned += __shfl_sync(CS_FULL, inc, 31);
-            cov = max(cov, __shfl_sync(CS_FULL, pm, 31));
-            __syncwarp();
-        };
-
-        // raw loads of the next step are issued before the current one is processed
-        int4 g4n;
-        double2 v01n, v23n;
-        auto load = [&](int pos) { // pos: column-relative index of this lane's group (multiple of 4)
-            g4n = make_int4(-1, -1, -1, -1);
-            v01n = make_double2(0, 0);
-            v23n = make_double2(0, 0);
-            if (pos < nent) {
-                if (tail_safe) {
-                    g4n = *reinterpret_cast<const int4 *>(rsrc + pos);
-                    v01n = *reinterpret_cast<const double2 *>(xsrc + pos);
-                    v23n = *reinterpret_cast<const double2 *>(xsrc + pos + 2);
-                } else { // last column(s) of the matrix: stay inside the arrays
-                    int gg[4] = {-1, -1, -1, -1};
-                    double vv[4] = {0, 0, 0, 0};
-                    for (int k = 0; k < 4; k++)
-                        if (pos + k < nent) {
-                            gg[k] = rsrc[pos + k];
-                            vv[k] = xsrc[pos + k];
-                        }
-                    g4n = make_int4(gg[0], gg[1], gg[2], gg[3]);
-                    v01n = make_double2(vv[0], vv[1]);
-                    v23n = make_double2(vv[2], vv[3]);
-                }
-            }
-        };
-        load(lane * EPL);
-        for (int p0 = 0; p0 < nent; p0 += 32 * EPL) {
-            const int pos = p0 + lane * EPL;
-            const int g[EPL] = {g4n.x, g4n.y, g4n.z, g4n.w};
-            const double v[EPL] = {v01n.x, v01n.y, v23n.x, v23n.y};
-            uint32_t w[EPL];
-#pragma unroll
-            for (int k = 0; k < EPL; k++) {
-                const bool valid = pos + k >= head && pos + k < nent;
-                w[k] = valid ? __ldg(gmap + g[k]) : 0u;
-            }
-            load(pos + 32 * EPL);
-            unsigned en = 0;
-            int lane_b0 = 0x7fffffff, lane_hi = 0;
-#pragma unroll
-            for (int k = EPL - 1; k >= 0; k--) {
-                nh[k] = w[k] >> 20;
-                b0[k] = w[k] & 0xFFFFF;
-                iv[k] = (Acc)0;
-                if (nh[k]) {
-                    en |= 1u << k;
-                    if (!AccOps<Acc>::conv(v[k], iv[k])) inexact = true;
-                    mag.add(iv[k], nh[k]);
-                    lane_b0 = b0[k];
-                    lane_hi = max(lane_hi, b0[k] + nh[k]);
-                }
-            }
-            unsigned pending = __ballot_sync(CS_FULL, en != 0);
-            while (pending) {
-                const int first = __ffs(pending) - 1;
-                const int bmin = __shfl_sync(CS_FULL, lane_b0, first);
-                flush(bmin);
-                const bool mine = (pending >> lane) & 1u;
-                const unsigned nofit = __ballot_sync(CS_FULL, mine && lane_hi > bmin + FILL_RING);
-                if (nofit == 0) { // the usual case: the whole step fits the ring
-                    step(mine ? en : 0u);
-                    break;
-                }
-                if ((nofit >> first) & 1u) {
-                    // the first lane's own entries span more than a ring (very sparse cell):
-                    // feed them one at a time
-#pragma unroll 1
-                    for (int k = 0; k < EPL; k++) {
-                        const unsigned has = __shfl_sync(CS_FULL, en, first) & (1u << k);
-                        if (!has) continue;
-                        const int bk = (k == 0) ? b0[0] : (k == 1) ? b0[1] : (k == 2) ? b0[2] : b0[3];
-                        flush(__shfl_sync(CS_FULL, bk, first));
-                        step(lane == first ? (1u << k) : 0u);
-                    }
-                    pending &= ~(1u << first);
-                    continue;
-                }
-                const unsigned act = pending & ((1u << (__ffs(nofit) - 1)) - 1u);
-                step(((act >> lane) & 1u) ? en : 0u);
-                pending &= ~act;
-            }
-        }
-        flush(0x7fffffff);
-        for (int off = 16; off >= 1; off >>= 1) nzero += __shfl_xor_sync(CS_FULL, nzero, off);
-        const bool over = mag.overflow(lane);
-        if (inexact || over) flags[FLAG_INEXACT] = 1;
-        if (lane == 0) {
-            counts_actual[c] = assigned - nzero;
-            if (nzero) flags[FLAG_SHRUNK] = 1;
-        }
     }
 }
 
@@ -737,12 +495,11 @@ extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const in
         int last_b0 = 0;
         for (int g = 0; g < G && reg; g++) {
             if (gm[g] == 0u) continue; // no hits
-            if (gm[g] == GMAP_ESC || (int)(gm[g] >> 20) >= RING) { reg = false; break; } // RING <= FILL_RING
+            if (gm[g] == GMAP_ESC) { reg = false; break; }
             const int b0 = gm[g] & 0xFFFFF;
             if (b0 < last_b0) reg = false;
             last_b0 = b0;
         }
-        if (getenv("CS_BIN_FORCE_GENERAL")) reg = false; // profiling / test hook
         p->regular = reg;
     }
     int rc = CS_OK;
@@ -788,20 +545,6 @@ static int launch_fill(cs_bin_plan *p, int N, const int64_t *d_colptr, const int
                        const double *d_x, const int64_t *d_out_colptr, int32_t *d_out_rowidx,
                        double *d_out_x, int64_t out_cap, cudaStream_t st)
 {
-    if (p->regular) {
-        const size_t smem = (size_t)FILL_STREAM_WARPS * FILL_RING * (sizeof(Acc) + sizeof(uint16_t));
-        CS_CUDA(cudaFuncSetAttribute(bin_fill_stream_kernel<Acc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_fill_stream_kernel<Acc>, FILL_STREAM_THREADS, smem));
-        if (per_sm < 1) per_sm = 1;
-        int grid = cs_num_sms() * per_sm;
-        if (grid > (N + FILL_STREAM_WARPS - 1) / FILL_STREAM_WARPS) grid = (N + FILL_STREAM_WARPS - 1) / FILL_STREAM_WARPS;
-        bin_fill_stream_kernel<Acc><<<grid, FILL_STREAM_THREADS, smem, st>>>(
-            N, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr, d_out_rowidx, d_out_x, out_cap, p->counts2.p,
-            p->flags.p);
-        CS_CUDA(cudaGetLastError());
-        return CS_OK;
-    }
     const size_t smem = fill_smem_bytes(p->B, sizeof(Acc));
     if (smem > 227 * 1024) {
         cs_set_error("cs_bin_counts: B=%d bins with FP64 accumulators need %zu B of shared memory", p->B, smem);
@@ -900,7 +643,7 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         CS_CUDA(p->tmp_x.reserve((size_t)padded));
         rc = run_scan(p, N, p->counts2.p, p->colptr2.p, st);
         if (rc) return rc;
-        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, p->regular ? nullptr : p->counts2.p,
+        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, p->counts2.p,
                                                                  p->colptr2.p, d_out_rowidx, d_out_x, p->tmp_i.p,
                                                                  p->tmp_x.p);
         CS_CUDA(cudaGetLastError());

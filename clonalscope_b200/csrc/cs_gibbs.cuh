@@ -17,6 +17,7 @@ struct ChainScal {
 
 struct ChainDev {
     int N, R, kcap;
+    int chunk;        // cells per end-of-sweep reduction chunk
     double alpha, beta;
     uint32_t seed;
     int single;       // initial assignment had one distinct label (rejection live in sweep 0)
@@ -28,10 +29,23 @@ struct ChainDev {
     int *slot_label;  // kcap (Philox)
     double *sig;      // R
     double *isig;     // R : 1/sig
-    double *Q;        // N x kcap (Philox)
-    int *J;           // N x R proposal sources (Philox)
-    int *zspec;       // N speculative draws (Philox)
-    int *qcols;       // N valid columns of Q (Philox)
+    // Philox path (all "columns" are slot-major: element (slot s, cell c) at [s*N + c])
+    double *Q;        // kcap x N   squared standardised distance of cell c to cluster s (2^-32 fixed point)
+    double *E;        // kcap x N   exp(-0.5 (Q - qmin[c])) cached by the prepare kernel
+    long long *qnew_i; // N         fixed-point distance of cell c to ITS proposed new cluster
+    double *qmin;     // N          the reference value the cached exponentials were taken against
+    double *ua;       // N          uniform of the categorical draw of this sweep
+    long long *wn_q;  // N          proposal distance the cached new-table weight was computed at
+    double *wn_w;     // N          beta * exp(-0.5 (q_new - qmin)) at wn_q
+    unsigned char *kmin; // N       a live cluster attaining qmin (255: only the proposal does)
+    int *J;           // N x R      proposal sources (cell index, -1 = fresh Uniform state)
+    int *zspec;       // N          speculative draws
+    int *qcols;       // N          (sequential kernel) valid columns of Q
+    int *icnt;        // N+1        inverse source index: offsets (after the scan)
+    int *icur;        // N          fill cursors
+    unsigned *inv;    // N x R      (cell << 10 | segment) entries grouped by source cell
+    double *inv_x;    // N x R      X[cell][segment] of the same entries
+    long long *tile_sums; // scan scratch
     double *mean;     // kcap x R cluster means
     double *psum;     // partial sums workspace
     int *pcnt;        // partial counts workspace
@@ -49,4 +63,5 @@ struct ChainDev {
     long long urec_cap;
 };
 
-constexpr int CS_STAT_CHUNK = 1024; // cells per deterministic reduction chunk
+// cells per deterministic reduction chunk: at most 512 chunks, at least 256 cells each
+inline int cs_stat_chunk(int N) { const int c = (N + 511) / 512; return c < 256 ? 256 : ((c + 31) / 32) * 32; }

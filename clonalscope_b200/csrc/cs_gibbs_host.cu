@@ -22,7 +22,12 @@ struct cs_chain {
     bool inited = false;
     cudaStream_t st = nullptr;
     ChainDev D{};
-    DevBuf<double> X, Xc, Ua, Ub, sig, isig, Q, mean, psum, sigma_all, LL, u_rows, L0;
+    DevBuf<double> X, Xc, Ua, Ub, sig, isig, Q, E, qmin, ua, inv_x, mean, psum, sigma_all, LL, u_rows, L0;
+    DevBuf<long long> qnew_i, tile_sums, wn_q;
+    DevBuf<double> wn_w;
+    DevBuf<unsigned char> kmin;
+    DevBuf<int> icnt, icur;
+    DevBuf<unsigned> inv;
     DevBuf<int> Zs, np, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
     DevBuf<long long> u_off;
     DevBuf<uint32_t> mt;
@@ -47,6 +52,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_REQUIRE(out != nullptr, "cs_chain_create: NULL output");
     *out = nullptr;
     CS_REQUIRE(N >= 1 && R >= 1 && niter_cap >= 1, "cs_chain_create: bad dimensions N=%d R=%d niter=%d", N, R, niter_cap);
+    CS_REQUIRE(rng_mode != CS_RNG_PHILOX || N < (1 << 22), "cs_chain_create: the Philox sampler takes up to 4,194,303 cells per chain (N=%d)", N);
     CS_REQUIRE(rng_mode == CS_RNG_R || rng_mode == CS_RNG_PHILOX, "cs_chain_create: unknown rng_mode %d", rng_mode);
     if (kcap <= 0) kcap = rng_mode == CS_RNG_PHILOX ? kDefaultKcapPhilox : kDefaultLcapR;
     if (rng_mode == CS_RNG_PHILOX && R > 1024) {
@@ -67,7 +73,8 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_CUDA(cudaEventCreate(&c->run_ev[0]));
     CS_CUDA(cudaEventCreate(&c->run_ev[1]));
     const size_t nx = (size_t)N * R;
-    const int nchunks = (N + CS_STAT_CHUNK - 1) / CS_STAT_CHUNK;
+    const int chunk = cs_stat_chunk(N);
+    const int nchunks = (N + chunk - 1) / chunk;
     const bool ph = rng_mode == CS_RNG_PHILOX;
     const long long urec_cap = (long long)niter_cap * (ph ? (kcap < 128 ? kcap : 128) : 128) + kcap;
     CS_CUDA(c->X.alloc(nx));
@@ -88,6 +95,18 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_CUDA(c->pcnt.alloc(ph ? (size_t)nchunks * kcap * R : 16));
     if (ph) {
         CS_CUDA(c->Q.alloc((size_t)N * kcap));
+        CS_CUDA(c->E.alloc((size_t)N * kcap));
+        CS_CUDA(c->qmin.alloc(N));
+        CS_CUDA(c->ua.alloc(N));
+        CS_CUDA(c->qnew_i.alloc(N));
+        CS_CUDA(c->wn_q.alloc(N));
+        CS_CUDA(c->wn_w.alloc(N));
+        CS_CUDA(c->kmin.alloc(N));
+        CS_CUDA(c->icnt.alloc((size_t)N + 1));
+        CS_CUDA(c->icur.alloc(N));
+        CS_CUDA(c->inv.alloc(nx));
+        CS_CUDA(c->inv_x.alloc(nx));
+        CS_CUDA(c->tile_sums.alloc((size_t)N / 1024 + 8));
         CS_CUDA(c->J.alloc(nx));
         CS_CUDA(c->zspec.alloc(N));
         CS_CUDA(c->qcols.alloc(N));
@@ -101,9 +120,12 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_CUDA(c->u_labels.alloc((size_t)urec_cap));
     CS_CUDA(c->u_rows.alloc((size_t)urec_cap * R));
     ChainDev &D = c->D;
-    D.N = N; D.R = R; D.kcap = kcap;
+    D.N = N; D.R = R; D.kcap = kcap; D.chunk = chunk;
     D.X = c->X.p; D.Zs = c->Zs.p; D.U = c->Ua.p; D.Unext = c->Ub.p; D.np = c->np.p;
     D.slot_label = c->slot_label.p; D.sig = c->sig.p; D.isig = c->isig.p; D.Q = c->Q.p; D.J = c->J.p;
+    D.E = c->E.p; D.qmin = c->qmin.p; D.ua = c->ua.p; D.qnew_i = c->qnew_i.p; D.icnt = c->icnt.p;
+    D.wn_q = c->wn_q.p; D.wn_w = c->wn_w.p; D.kmin = c->kmin.p;
+    D.icur = c->icur.p; D.inv = c->inv.p; D.inv_x = c->inv_x.p; D.tile_sums = c->tile_sums.p;
     D.zspec = c->zspec.p; D.qcols = c->qcols.p; D.mean = c->mean.p; D.psum = c->psum.p; D.pcnt = c->pcnt.p;
     D.newslot = c->newslot.p; D.mt = c->mt.p; D.scal = c->scal.p;
     D.Zall = c->Zall.p; D.sigma_all = c->sigma_all.p; D.LL = c->LL.p; D.kt_all = c->kt_all.p;

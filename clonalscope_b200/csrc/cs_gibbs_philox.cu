@@ -5,26 +5,36 @@
 // cell.  That order is kept EXACTLY, but evaluated speculatively:
 //
 //   prepare_kernel (all SMs, one warp per cell)
-//       scores every cell against all live clusters (Q matrix), draws its nested-CRP
-//       proposal (:165-175) and its categorical draw (:193-207) against the state at
-//       the START of the sweep.  As long as no earlier cell changed its label that state
-//       is the state the sequential sampler would have seen (a cell that re-draws its
-//       own label leaves counts and rows untouched), so all draws up to and including
-//       the first label change ("event") are already the sequential result.
-//   scan_kernel (one CTA, 32 warps)
-//       resumes at the first event and walks the rest of the sweep in windows of 32
-//       cells, one warp per cell, re-drawing against the committed state; a window is
-//       cut at its first event, that event is committed, and the walk continues behind
-//       it.  Q columns of clusters opened during the sweep are filled on demand.
+//       scores every cell against all live clusters (Q), draws its nested-CRP proposal
+//       (:165-175) and its categorical draw (:193-207) against the state at the START of
+//       the sweep, and caches what a later re-draw needs (the exponentials E, their
+//       reference value qmin, the draw's uniform, the proposal sources J).  As long as no
+//       earlier cell changed its label that state is the state the sequential sampler would
+//       have seen (a cell that re-draws its own label leaves counts and rows untouched), so
+//       every draw up to and including the first label change ("event") is already the
+//       sequential result.
+//   index kernels (all SMs; skipped when the sweep has no event)
+//       inverse source index: for every cell f the (cell, segment) pairs whose proposal
+//       copies f's cluster state — what an event at f invalidates.
+//   scan_kernel (one CTA, thread per cell)
+//       resumes at the first event and walks the rest of the sweep in windows of 1024 cells:
+//       each thread re-draws its cell against the committed state from the cached
+//       exponentials (no exp, no gathers: counts are the only thing an event changes for
+//       almost every cell), the window is cut at its first event, that event is committed,
+//       its dependents' proposal distances are corrected in place (fixed-point, so the
+//       correction is exact), and the walk continues behind it.
+//   seq_scan_kernel (one CTA, warp per cell): the plain sequential evaluation, used for the
+//       first sweep of a single-cluster start (rejection loop live, :174) and as the
+//       test hook that proves the speculative path draws the same chain.
 //   end of sweep (:221-245): deterministic chunked reductions for cluster means and
 //       sigmas, Philox/AS241 redraw of the means, total log-likelihood, compaction of
 //       emptied clusters (labels keep growing, rows are never renumbered).
 //
 // Random numbers are counter-based (Philox4x32-10 keyed by seed; counter = cell, segment,
-// sweep, purpose|attempt), so a draw does not depend on how many draws preceded it —
-// that is what makes the speculation exact.  All sums that decide a draw are evaluated
-// in one canonical order (lane-strided fma + butterfly), identical in every kernel and
-// in the CPU oracle's Philox mode.
+// sweep, purpose|attempt), so a draw does not depend on how many draws preceded it — that
+// is what makes the speculation exact.  Squared distances are accumulated in 64-bit fixed
+// point (2^-32), so they do not depend on summation order and can be corrected term by term;
+// the CPU oracle's Philox mode uses the same definition.
 #include "cs_gibbs.cuh"
 
 #include <limits.h>
@@ -32,8 +42,11 @@
 namespace {
 
 constexpr int PREP_THREADS = 256;
-constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_THREADS = 1024;  // sequential kernel: one warp per cell
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int WIN_THREADS = 256;    // windowed kernel: one thread per cell of the window ...
+constexpr int WIN_CELLS = 128;      // ... one warp per scheduler draws, all threads correct dependents
+constexpr double Q_SCALE = 1.0 / 4294967296.0;
 
 template <int NCH>
 __device__ __forceinline__ void load_row(const double *__restrict__ xrow, int R, int lane, double (&x)[NCH])
@@ -45,43 +58,60 @@ __device__ __forceinline__ void load_row(const double *__restrict__ xrow, int R,
     }
 }
 
-// canonical squared standardised distance of one cell to one row
-template <int NCH>
-__device__ __forceinline__ double q_row(const double (&x)[NCH], const double *u, const double *s_isig, int R,
-                                        int lane)
+// one segment's contribution, 2^-32 fixed point: llrint(((x - u) * 65536 / sigma)^2)
+__device__ __forceinline__ long long tint(double x, double u, double isig16)
 {
-    double s = 0.0;
+    const double d = __dmul_rn(__dsub_rn(x, u), isig16);
+    double t = __dmul_rn(d, d);
+    if (!(t < 4611686018427387904.0)) t = 4611686018427387904.0;
+    return __double2ll_rn(t);
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(CS_FULL, v, off);
+    return v;
+}
+
+// fixed-point squared standardised distance of one cell (registers) to one row
+template <int NCH>
+__device__ __forceinline__ long long q_row(const double (&x)[NCH], const double *u, const double *s_isig16, int R,
+                                           int lane)
+{
+    long long s = 0;
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
         const int r = lane + 32 * i;
         if (r < R) {
             const double xv = x[i];
-            if (!cs_isna(xv)) {
-                const double d = __dmul_rn(__dsub_rn(xv, u[r]), s_isig[r]);
-                s = __fma_rn(d, d, s);
-            }
+            if (!cs_isna(xv)) s += tint(xv, u[r], s_isig16[r]);
         }
     }
-    return cs_warp_sum_bfly(s);
+    return warp_sum_ll(s);
 }
 
 template <int NCH>
-__device__ __forceinline__ double q_regs(const double (&x)[NCH], const double (&mu)[NCH], const double *s_isig,
-                                         int R, int lane)
+__device__ __forceinline__ long long q_regs(const double (&x)[NCH], const double (&mu)[NCH], const double *s_isig16,
+                                            int R, int lane)
 {
-    double s = 0.0;
+    long long s = 0;
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
         const int r = lane + 32 * i;
         if (r < R) {
             const double xv = x[i];
-            if (!cs_isna(xv)) {
-                const double d = __dmul_rn(__dsub_rn(xv, mu[i]), s_isig[r]);
-                s = __fma_rn(d, d, s);
-            }
+            if (!cs_isna(xv)) s += tint(xv, mu[i], s_isig16[r]);
         }
     }
-    return cs_warp_sum_bfly(s);
+    return warp_sum_ll(s);
+}
+
+__device__ __forceinline__ double fresh_state(const ChainDev &D, int c, int r, int tt, uint32_t attempt)
+{
+    double ua, ub;
+    cs_philox_draw(D.seed, (uint32_t)c, (uint32_t)r, (uint32_t)tt, CS_PH_PROPOSAL, attempt, ua, ub);
+    return __fma_rn(2.5 - 0.3, ua, 0.3);
 }
 
 // nested-CRP proposal for one cell (R/BayesNonparCluster.R:166-173): per segment either a
@@ -101,11 +131,7 @@ __device__ __forceinline__ void propose(const ChainDev &D, int c, int tt, uint32
             double tm = 0.0;
             if (Jrow) {
                 j = Jrow[r];
-                if (j < 0) {
-                    double ua, ub;
-                    cs_philox_draw(D.seed, (uint32_t)c, (uint32_t)r, (uint32_t)tt, CS_PH_PROPOSAL, attempt, ua, ub);
-                    tm = __fma_rn(2.5 - 0.3, ua, 0.3);
-                }
+                if (j < 0) tm = fresh_state(D, c, r, tt, attempt);
             } else {
                 double ua, ub;
                 cs_philox_draw(D.seed, (uint32_t)c, (uint32_t)r, (uint32_t)tt, CS_PH_PROPOSAL, attempt, ua, ub);
@@ -148,30 +174,34 @@ __device__ __forceinline__ bool is_duplicate(const ChainDev &D, int nlive, const
 }
 
 // categorical draw over the live clusters (slot order == label order) and the new table
-// (R/BayesNonparCluster.R:193-207).  Returns the slot, or nlive for "open a new cluster".
-__device__ __forceinline__ int draw_cell(const double *Qrow, int nlive, const int *s_np, int zold, double q_new,
-                                         double beta, double ua, int lane)
+// (R/BayesNonparCluster.R:193-207), one warp.  Qc / Ec point at this cell's element of slot
+// 0 (slot stride = N).  Returns the slot, or nlive for "open a new cluster".  When Ec is
+// given the exponentials are stored for later re-draws; *qmin_out receives their reference.
+__device__ __forceinline__ int draw_cell_warp(const double *Qc, double *Ec, size_t stride, int nlive,
+                                              const int *s_np, int zold, double q_new, double beta, double ua,
+                                              int lane, double *qmin_out)
 {
     double qmin = q_new;
     for (int s0 = 0; s0 < nlive; s0 += 32) {
         const int s = s0 + lane;
         if (s < nlive) {
             const int n = s_np[s] - (s == zold ? 1 : 0);
-            if (n > 0) qmin = fmin(qmin, Qrow[s]);
+            if (n > 0) qmin = fmin(qmin, Qc[(size_t)s * stride]);
         }
     }
     qmin = cs_warp_min(qmin);
+    if (qmin_out) *qmin_out = qmin;
     const double w_new = __dmul_rn(beta, exp(-0.5 * (q_new - qmin)));
-    double w0 = 0.0; // weight of this lane's slot in the first group (kept for pass 2)
     double run = 0.0;
     for (int s0 = 0; s0 < nlive; s0 += 32) {
         const int s = s0 + lane;
         double w = 0.0;
         if (s < nlive) {
+            const double e = exp(-0.5 * (Qc[(size_t)s * stride] - qmin));
+            if (Ec) Ec[(size_t)s * stride] = e;
             const int n = s_np[s] - (s == zold ? 1 : 0);
-            if (n > 0) w = __dmul_rn((double)n, exp(-0.5 * (Qrow[s] - qmin)));
+            if (n > 0) w = __dmul_rn((double)n, e);
         }
-        if (s0 == 0) w0 = w;
         const int cnt = min(32, nlive - s0);
         for (int j = 0; j < cnt; j++) run = __dadd_rn(run, __shfl_sync(CS_FULL, w, j));
     }
@@ -181,13 +211,10 @@ __device__ __forceinline__ int draw_cell(const double *Qrow, int nlive, const in
     int z = -1, lastpos = -1;
     for (int s0 = 0; s0 < nlive && z < 0; s0 += 32) {
         const int s = s0 + lane;
-        double w = w0;
-        if (s0 != 0) {
-            w = 0.0;
-            if (s < nlive) {
-                const int n = s_np[s] - (s == zold ? 1 : 0);
-                if (n > 0) w = __dmul_rn((double)n, exp(-0.5 * (Qrow[s] - qmin)));
-            }
+        double w = 0.0;
+        if (s < nlive) {
+            const int n = s_np[s] - (s == zold ? 1 : 0);
+            if (n > 0) w = __dmul_rn((double)n, exp(-0.5 * (Qc[(size_t)s * stride] - qmin)));
         }
         const int cnt = min(32, nlive - s0);
         for (int j = 0; j < cnt; j++) {
@@ -213,36 +240,141 @@ __device__ __forceinline__ int draw_cell(const double *Qrow, int nlive, const in
     return z;
 }
 
+// the same draw by ONE thread from cached exponentials: slots below ncached use Ec when the
+// cached reference value still is the minimum over today's candidates, everything else is
+// re-exponentiated.  Same operations in the same order as draw_cell_warp.
+__device__ __forceinline__ int draw_cell_thread(const double *Qc, const double *Ec, size_t stride, int ncached,
+                                                int nlive, const int *s_np, int zold, double q_new,
+                                                double qmin_cached, double beta, double ua)
+{
+    constexpr int CH = 8; // loads are issued CH at a time, unconditionally, so they overlap
+    double qmin = q_new;
+    for (int s0 = 0; s0 < nlive; s0 += CH) {
+        double q[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) q[i] = (s0 + i < nlive) ? Qc[(size_t)(s0 + i) * stride] : 0.0;
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int s = s0 + i;
+            if (s < nlive && s_np[s] - (s == zold ? 1 : 0) > 0) qmin = fmin(qmin, q[i]);
+        }
+    }
+    const int nfast = (qmin == qmin_cached) ? ncached : 0;
+    const double w_new = __dmul_rn(beta, exp(-0.5 * (q_new - qmin)));
+    double run = 0.0;
+    for (int s0 = 0; s0 < nlive; s0 += CH) {
+        double e[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int s = s0 + i;
+            e[i] = (s < nfast) ? Ec[(size_t)s * stride] : ((s < nlive) ? Qc[(size_t)s * stride] : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int s = s0 + i;
+            if (s < nlive) {
+                const int n = s_np[s] - (s == zold ? 1 : 0);
+                if (n > 0) {
+                    const double ee = (s < nfast) ? e[i] : exp(-0.5 * (e[i] - qmin));
+                    run = __dadd_rn(run, __dmul_rn((double)n, ee));
+                }
+            }
+        }
+    }
+    run = __dadd_rn(run, w_new);
+    const double t = __dmul_rn(ua, run);
+    run = 0.0;
+    int lastpos = -1;
+    for (int s0 = 0; s0 < nlive; s0 += CH) {
+        double e[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int s = s0 + i;
+            e[i] = (s < nfast) ? Ec[(size_t)s * stride] : ((s < nlive) ? Qc[(size_t)s * stride] : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int s = s0 + i;
+            if (s < nlive) {
+                const int n = s_np[s] - (s == zold ? 1 : 0);
+                if (n > 0) {
+                    const double ee = (s < nfast) ? e[i] : exp(-0.5 * (e[i] - qmin));
+                    const double w = __dmul_rn((double)n, ee);
+                    if (w > 0.0) {
+                        run = __dadd_rn(run, w);
+                        lastpos = s;
+                        if (run > t) return s;
+                    }
+                }
+            }
+        }
+    }
+    if (w_new > 0.0) lastpos = nlive;
+    return lastpos;
+}
+
+// the common case of the windowed scan: at most 32 live clusters, all exponentials cached,
+// candidate set as at the start of the sweep.  One pass, cumulative sums kept in registers.
+// s_npd[s] / s_npd1[s] = (double) np[s] / (double)(np[s] - 1), 0 when not positive.
+__device__ __forceinline__ int draw_cell_fast32(const double *Ec, size_t stride, int nlive, const double *s_npd,
+                                                const double *s_npd1, int zold, double w_new, double ua)
+{
+    double cum[32];
+    unsigned pos = 0;
+    double run = 0.0;
+#pragma unroll
+    for (int s = 0; s < 32; s++) {
+        cum[s] = 0.0;
+        if (s < nlive) {
+            const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
+            const double w = __dmul_rn(nd, Ec[(size_t)s * stride]);
+            run = __dadd_rn(run, w);
+            cum[s] = run;
+            if (w > 0.0) pos |= 1u << s;
+        }
+    }
+    const double t = __dmul_rn(ua, __dadd_rn(run, w_new));
+    unsigned hit = 0;
+#pragma unroll
+    for (int s = 0; s < 32; s++)
+        if (cum[s] > t) hit |= 1u << s;
+    hit &= pos;
+    if (hit) return __ffs(hit) - 1;
+    if (w_new > 0.0) return nlive;
+    return pos ? 31 - __clz(pos) : -1;
+}
+
 // ---------------------------------------------------------------- prepare (all SMs)
 template <int NCH>
 __global__ void __launch_bounds__(PREP_THREADS)
 prepare_kernel(ChainDev D, int tt, int *__restrict__ rej)
 {
     extern __shared__ double s_dyn[];
-    double *s_isig = s_dyn;
+    double *s_isig16 = s_dyn;
     int *s_np = reinterpret_cast<int *>(s_dyn + D.R);
     const int nlive = D.scal->nlive;
-    for (int r = threadIdx.x; r < D.R; r += PREP_THREADS) s_isig[r] = D.isig[r];
+    for (int r = threadIdx.x; r < D.R; r += PREP_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
     for (int s = threadIdx.x; s < nlive; s += PREP_THREADS) s_np[s] = D.np[s];
     __syncthreads();
     const bool reject_live = D.single && tt == 0;
     const int lane = threadIdx.x & 31;
     const int wpb = PREP_THREADS / 32;
+    const size_t N = (size_t)D.N;
     int first = INT_MAX;
     for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < D.N; c += gridDim.x * wpb) {
         double x[NCH], mu[NCH];
         int jj[NCH];
         load_row<NCH>(D.X + (size_t)c * D.R, D.R, lane, x);
         const int zold = D.Zs[c];
-        double *Qrow = D.Q + (size_t)c * D.kcap;
+        double *Qc = D.Q + c, *Ec = D.E + c;
         for (int s0 = 0; s0 < nlive; s0 += 32) {
             double myq = 0.0;
             const int cnt = min(32, nlive - s0);
             for (int j = 0; j < cnt; j++) {
-                const double q = q_row<NCH>(x, D.U + (size_t)(s0 + j) * D.R, s_isig, D.R, lane);
-                if (lane == j) myq = q;
+                const long long q = q_row<NCH>(x, D.U + (size_t)(s0 + j) * D.R, s_isig16, D.R, lane);
+                if (lane == j) myq = (double)q * Q_SCALE;
             }
-            if (lane < cnt) Qrow[s0 + lane] = myq;
+            if (lane < cnt) Qc[(size_t)(s0 + lane) * N] = myq;
         }
         uint32_t attempt = 0;
         for (;;) {
@@ -256,27 +388,310 @@ prepare_kernel(ChainDev D, int tt, int *__restrict__ rej)
             const int r = lane + 32 * i;
             if (r < D.R) D.J[(size_t)c * D.R + r] = jj[i];
         }
-        const double q_new = q_regs<NCH>(x, mu, s_isig, D.R, lane);
+        const long long qn = q_regs<NCH>(x, mu, s_isig16, D.R, lane);
         double ua, ub;
         cs_philox_draw(D.seed, (uint32_t)c, 0u, (uint32_t)tt, CS_PH_ASSIGN, 0u, ua, ub);
         __syncwarp();
-        const int z = draw_cell(Qrow, nlive, s_np, zold, q_new, D.beta, ua, lane);
+        double qmin;
+        const double q_new = (double)qn * Q_SCALE;
+        const int z = draw_cell_warp(Qc, Ec, N, nlive, s_np, zold, q_new, D.beta, ua, lane, &qmin);
+        // a live candidate that attains qmin (255: only the proposal does).  While it stays a
+        // candidate, and nothing smaller joins, the cached exponentials stay exact.
+        int km = 255;
+        for (int s = lane; s < nlive && s < 255; s += 32)
+            if (km == 255 && s_np[s] - (s == zold ? 1 : 0) > 0 && Qc[(size_t)s * N] == qmin) km = s;
+        km = cs_warp_min_i(km);
         if (lane == 0) {
             D.zspec[c] = z;
             D.qcols[c] = nlive;
+            D.qnew_i[c] = qn;
+            D.qmin[c] = qmin;
+            D.ua[c] = ua;
+            D.kmin[c] = (unsigned char)km;
+            D.wn_q[c] = qn;
+            D.wn_w[c] = __dmul_rn(D.beta, exp(-0.5 * (q_new - qmin)));
             if (z != zold && c < first) first = c;
         }
     }
     if (lane == 0 && first != INT_MAX) atomicMin(&D.scal->first_event, first);
 }
 
-// ---------------------------------------------------------------- scan (one CTA)
+// ---------------------------------------------------------------- inverse source index
+// icnt[j] = number of (cell, segment) proposals that copy cell j's cluster state
+__global__ void index_count_kernel(ChainDev D)
+{
+    if (D.scal->first_event >= D.N) return;
+    const size_t n = (size_t)D.N * D.R;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = D.J[e];
+        if (j >= 0) atomicAdd(&D.icnt[j], 1);
+    }
+}
+
+// exclusive scan of icnt[0..N) in place (icnt[N] = total); one CTA, N is at most a few 10^6
+__global__ void __launch_bounds__(1024) index_scan_kernel(ChainDev D)
+{
+    if (D.scal->first_event >= D.N) return;
+    __shared__ int s_w[33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int carry = 0;
+    for (int base = 0; base < D.N; base += 1024 * 4) {
+        int v[4], sum = 0;
+        const int i0 = base + threadIdx.x * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[k] = (i0 + k < D.N) ? D.icnt[i0 + k] : 0;
+            sum += v[k];
+        }
+        int inc = sum;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(CS_FULL, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int w = s_w[lane];
+            int winc = w;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(CS_FULL, winc, off);
+                if (lane >= off) winc += t;
+            }
+            s_w[lane] = winc - w;
+            if (lane == 31) s_w[32] = winc;
+        }
+        __syncthreads();
+        int ex = carry + s_w[wid] + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < D.N) {
+                D.icnt[i0 + k] = ex;
+                D.icur[i0 + k] = ex;
+            }
+            ex += v[k];
+        }
+        carry += s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) D.icnt[D.N] = carry;
+}
+
+__global__ void index_fill_kernel(ChainDev D)
+{
+    if (D.scal->first_event >= D.N) return;
+    const size_t n = (size_t)D.N * D.R;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = D.J[e];
+        if (j >= 0) {
+            const int p = atomicAdd(&D.icur[j], 1);
+            D.inv[p] = ((unsigned)(e / (size_t)D.R) << 10) | (unsigned)(e % (size_t)D.R);
+            D.inv_x[p] = D.X[e]; // the value the correction needs rides along: one dependent load less
+        }
+    }
+}
+
+// ---------------------------------------------------------------- scan (one CTA, thread per cell)
 template <int NCH>
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
+__global__ void __launch_bounds__(WIN_THREADS)
+scan_kernel(ChainDev D, int tt)
 {
     extern __shared__ double s_dyn[];
-    double *s_isig = s_dyn;
+    double *s_isig16 = s_dyn;                 // R
+    double *s_npd = s_dyn + D.R;              // kcap : (double) np[s]      (0 when np <= 0)
+    double *s_npd1 = s_npd + D.kcap;          // kcap : (double)(np[s] - 1) (0 when np <= 1)
+    int *s_np = reinterpret_cast<int *>(s_npd1 + D.kcap);
+    int *s_label = s_np + D.kcap;
+    int *s_np0 = s_label + D.kcap;            // counts at the start of the sweep
+    // s_fmin[k % 3] collects window k's first event; slot (k+2) % 3 is reset right after window
+    // k's barrier: its last readers (window k-1) are behind that barrier and its next writers
+    // (window k+2) are beyond the next one, so one barrier per event-free window suffices
+    __shared__ int s_nlive, s_kt, s_fmin[3], s_err, s_z, s_zold, s_e0, s_e1;
+    __shared__ long long s_scanned, s_events;
+
+    const int f0 = D.scal->first_event;
+    if (f0 >= D.N) return;
+    for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
+    for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
+        const int n = D.np[s];
+        s_np[s] = n;
+        s_npd[s] = n > 0 ? (double)n : 0.0;
+        s_npd1[s] = n > 1 ? (double)(n - 1) : 0.0;
+        s_np0[s] = n;
+        s_label[s] = D.slot_label[s];
+    }
+    if (threadIdx.x == 0) {
+        s_nlive = D.scal->nlive;
+        s_kt = D.scal->kt;
+        s_fmin[0] = s_fmin[1] = s_fmin[2] = INT_MAX;
+        s_err = 0;
+        s_scanned = 0;
+        s_events = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t N = (size_t)D.N;
+    int pos = f0, round = 0;
+    while (pos < D.N) {
+        const int c = pos + threadIdx.x;
+        const int nlive = s_nlive;
+        int z = -1, zold = -1, ev = INT_MAX, e0 = 0, e1 = 0;
+        if (threadIdx.x < WIN_CELLS && c < D.N) {
+            zold = D.Zs[c];
+            const long long qi = __ldcg(D.qnew_i + c);
+            const double q_new = (double)qi * Q_SCALE;
+            const double qmin = D.qmin[c];
+            const double ua = D.ua[c];
+            // the cached exponentials are exactly today's when the cached minimum still is the
+            // minimum over today's candidates: the cluster that attained it still is a candidate,
+            // the proposal is not below it, and no cluster below it became a candidate (clusters
+            // opened this sweep clear kmin themselves; the cell's own cluster joins the candidates
+            // when it stops being a singleton)
+            const int km = D.kmin[c];
+            bool fast = nlive <= 32 && km != 255 && q_new >= qmin && s_np[km] - (km == zold ? 1 : 0) > 0;
+            if (fast && s_np0[zold] < 2 && s_np[zold] >= 2 && D.Q[(size_t)zold * N + c] < qmin) fast = false;
+            if (fast) {
+                double w_new = D.wn_w[c];
+                if (D.wn_q[c] != qi) { // the proposal was corrected since the weight was cached
+                    w_new = __dmul_rn(D.beta, exp(-0.5 * (q_new - qmin)));
+                    D.wn_q[c] = qi;
+                    D.wn_w[c] = w_new;
+                }
+                z = draw_cell_fast32(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua);
+            } else {
+                z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, s_np, zold, q_new, qmin, D.beta, ua);
+            }
+            if (z != zold) {
+                ev = c;
+                e0 = D.icnt[c]; // dependents' range, fetched while the window is being reduced
+                e1 = D.icnt[c + 1];
+                // candidates that lose this round usually still are events in a later one:
+                // pull their dependents towards the SM now
+                for (int e = e0; e < e1; e += 16) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(D.inv_x + e));
+                    if (((e - e0) & 16) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(D.inv + e));
+                }
+            }
+        }
+        const int wev = __reduce_min_sync(CS_FULL, ev);
+        if (lane == 0 && wev != INT_MAX) atomicMin(&s_fmin[round % 3], wev);
+        __syncthreads();
+        const int f = s_fmin[round % 3];
+        if (threadIdx.x == 0) {
+            s_scanned += (f != INT_MAX ? (f - pos + 1) : min(WIN_CELLS, D.N - pos));
+            s_fmin[(round + 2) % 3] = INT_MAX;
+        }
+        round++;
+        if (f == INT_MAX) { // no event in the window: everything in it keeps its label
+            pos += WIN_CELLS;
+            continue;
+        }
+        if (c == f) {
+            s_z = z;
+            s_zold = zold;
+            s_e0 = e0;
+            s_e1 = e1;
+        }
+        __syncthreads();
+        // ---- commit the event at cell f: it moves from slot a to slot b
+        const int a = s_zold;
+        const int b = s_z;
+        const bool opens = (b == nlive);
+        if (opens) { // :209-212 open a new cluster with the proposed per-segment states
+            if (nlive >= D.kcap) {
+                if (threadIdx.x == 0) s_err = CS_ERR_KCAP;
+            } else {
+                double *urow = D.U + (size_t)nlive * D.R;
+                const int *Jrow = D.J + (size_t)f * D.R;
+                for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) {
+                    const int j = Jrow[r];
+                    urow[r] = (j >= 0) ? D.U[(size_t)D.Zs[j] * D.R + r] : fresh_state(D, f, r, tt, 0u);
+                }
+            }
+            __syncthreads();
+            if (s_err) break;
+        }
+        if (threadIdx.x == 0) {
+            const int na = s_np[a] - 1, nb = opens ? 1 : s_np[b] + 1;
+            s_np[a] = na;
+            s_npd[a] = na > 0 ? (double)na : 0.0;
+            s_npd1[a] = na > 1 ? (double)(na - 1) : 0.0;
+            s_np[b] = nb;
+            s_npd[b] = (double)nb;
+            s_npd1[b] = nb > 1 ? (double)(nb - 1) : 0.0;
+            if (opens) {
+                s_label[b] = ++s_kt;
+                s_nlive = nlive + 1;
+            }
+            D.Zs[f] = b;
+            s_events += 1;
+        }
+        // ---- proposals that copied cell f's cluster state: correct their distance exactly
+        {
+            const int e1s = s_e1;
+            const double *ua_row = D.U + (size_t)a * D.R, *ub_row = D.U + (size_t)b * D.R;
+            for (int e = s_e0 + threadIdx.x; e < e1s; e += WIN_THREADS) {
+                const unsigned cr = D.inv[e];
+                const double xv = D.inv_x[e];
+                const int cc = (int)(cr >> 10), r = (int)(cr & 1023u);
+                if (cc > f && !cs_isna(xv)) {
+                    const long long d = tint(xv, ub_row[r], s_isig16[r]) - tint(xv, ua_row[r], s_isig16[r]);
+                    if (d) atomicAdd(reinterpret_cast<unsigned long long *>(D.qnew_i + cc), (unsigned long long)d);
+                }
+            }
+        }
+        // ---- a new cluster is a new candidate for every later cell: score them now
+        if (opens) {
+            double x[NCH];
+            const double *urow = D.U + (size_t)b * D.R;
+            for (int cc = f + 1 + warp; cc < D.N; cc += WIN_THREADS / 32) {
+                load_row<NCH>(D.X + (size_t)cc * D.R, D.R, lane, x);
+                const long long q = q_row<NCH>(x, urow, s_isig16, D.R, lane);
+                const double qd = (double)q * Q_SCALE, qm = D.qmin[cc];
+                if (qd < qm) {
+                    // the new cluster is this cell's best candidate: it becomes the reference of the
+                    // cached exponentials (slots 0..b re-exponentiated, one lane each)
+                    for (int s = lane; s <= b; s += 32) {
+                        const double qs = (s == b) ? qd : D.Q[(size_t)s * N + cc];
+                        D.E[(size_t)s * N + cc] = exp(-0.5 * (qs - qd));
+                    }
+                    if (lane == 0) {
+                        D.Q[(size_t)b * N + cc] = qd;
+                        D.qmin[cc] = qd;
+                        D.kmin[cc] = (unsigned char)(b < 255 ? b : 255);
+                        D.wn_q[cc] = LLONG_MIN; // the cached new-table weight used the old reference
+                    }
+                } else if (lane == 0) {
+                    D.Q[(size_t)b * N + cc] = qd;
+                    D.E[(size_t)b * N + cc] = exp(-0.5 * (qd - qm)); // cached like the other slots'
+                }
+            }
+        }
+        __syncthreads(); // orders the corrections (L2 atomics) before the next window's .cg loads
+        pos = f + 1;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
+        D.np[s] = s_np[s];
+        D.slot_label[s] = s_label[s];
+    }
+    if (threadIdx.x == 0) {
+        D.scal->nlive = s_nlive;
+        D.scal->kt = s_kt;
+        D.scal->cells_scanned += s_scanned;
+        D.scal->n_events += s_events;
+        if (s_err) D.scal->err = s_err;
+    }
+}
+
+// ---------------------------------------------------------------- sequential scan (one CTA, warp per cell)
+// every cell from `start` on is re-proposed, re-scored and re-drawn against the committed
+// state, 32 cells at a time (a window is cut at its first event).
+template <int NCH>
+__global__ void __launch_bounds__(SCAN_THREADS)
+seq_scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
+{
+    extern __shared__ double s_dyn[];
+    double *s_isig16 = s_dyn;
     int *s_np = reinterpret_cast<int *>(s_dyn + D.R);
     int *s_label = s_np + D.kcap;
     __shared__ int s_nlive, s_kt, s_fmin[2], s_err;
@@ -284,7 +699,7 @@ scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
 
     const int f0 = force_all ? 0 : D.scal->first_event;
     if (f0 >= D.N) return;
-    for (int r = threadIdx.x; r < D.R; r += SCAN_THREADS) s_isig[r] = D.isig[r];
+    for (int r = threadIdx.x; r < D.R; r += SCAN_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
     for (int s = threadIdx.x; s < D.kcap; s += SCAN_THREADS) {
         s_np[s] = D.np[s];
         s_label[s] = D.slot_label[s];
@@ -300,8 +715,9 @@ scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
     }
     __syncthreads();
     const bool reject_live = D.single && tt == 0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool use_J = !reject_live && !force_all;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t N = (size_t)D.N;
     int a = f0, round = 0;
     while (a < D.N) {
         const int c = a + warp;
@@ -312,7 +728,7 @@ scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
         if (c < D.N) {
             load_row<NCH>(D.X + (size_t)c * D.R, D.R, lane, x);
             zold = D.Zs[c];
-            double *Qrow = D.Q + (size_t)c * D.kcap;
+            double *Qc = D.Q + c;
             uint32_t attempt = 0;
             for (;;) {
                 propose<NCH>(D, c, tt, attempt, use_J ? D.J + (size_t)c * D.R : nullptr, lane, mu, jj);
@@ -320,17 +736,17 @@ scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
                 attempt++;
             }
             if (reject_live && lane == 0) rej[c] = (int)attempt;
-            // Q columns of the clusters opened since this row was last scored
+            // Q entries of the clusters opened since this cell was last scored
             for (int s = D.qcols[c]; s < nlive; s++) {
-                const double q = q_row<NCH>(x, D.U + (size_t)s * D.R, s_isig, D.R, lane);
-                if (lane == 0) Qrow[s] = q;
+                const long long q = q_row<NCH>(x, D.U + (size_t)s * D.R, s_isig16, D.R, lane);
+                if (lane == 0) Qc[(size_t)s * N] = (double)q * Q_SCALE;
             }
             if (lane == 0) D.qcols[c] = nlive;
-            const double q_new = q_regs<NCH>(x, mu, s_isig, D.R, lane);
+            const long long qn = q_regs<NCH>(x, mu, s_isig16, D.R, lane);
             double ua, ub;
             cs_philox_draw(D.seed, (uint32_t)c, 0u, (uint32_t)tt, CS_PH_ASSIGN, 0u, ua, ub);
             __syncwarp();
-            z = draw_cell(Qrow, nlive, s_np, zold, q_new, D.beta, ua, lane);
+            z = draw_cell_warp(Qc, nullptr, N, nlive, s_np, zold, (double)qn * Q_SCALE, D.beta, ua, lane, nullptr);
             if (z != zold && lane == 0) atomicMin(&s_fmin[round & 1], c);
         }
         __syncthreads();
@@ -394,7 +810,7 @@ stats_partial_kernel(ChainDev D, int smem_doubles)
     const int ST = max(1, smem_doubles / (R + (R + 1) / 2)); // slots per pass (double acc + int cnt)
     double *acc = s_dyn;
     int *cnt = reinterpret_cast<int *>(s_dyn + (size_t)ST * R);
-    const int i0 = blockIdx.x * CS_STAT_CHUNK, i1 = min(D.N, i0 + CS_STAT_CHUNK);
+    const int i0 = blockIdx.x * D.chunk, i1 = min(D.N, i0 + D.chunk);
     for (int t0 = 0; t0 < nlive; t0 += ST) {
         const int ns = min(ST, nlive - t0);
         for (int e = threadIdx.x; e < ns * R; e += blockDim.x) {
@@ -479,7 +895,7 @@ redraw_kernel(ChainDev D, int tt, int last)
 __global__ void __launch_bounds__(256)
 sigma_partial_kernel(ChainDev D)
 {
-    const int i0 = blockIdx.x * CS_STAT_CHUNK, i1 = min(D.N, i0 + CS_STAT_CHUNK);
+    const int i0 = blockIdx.x * D.chunk, i1 = min(D.N, i0 + D.chunk);
     for (int r = threadIdx.x; r < D.R; r += blockDim.x) {
         double s = 0.0;
         int c = 0;
@@ -517,7 +933,7 @@ ll_partial_kernel(ChainDev D, const double *__restrict__ U, const int *__restric
 {
     __shared__ double s_w[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i0 = blockIdx.x * CS_STAT_CHUNK, i1 = min(D.N, i0 + CS_STAT_CHUNK);
+    const int i0 = blockIdx.x * D.chunk, i1 = min(D.N, i0 + D.chunk);
     double acc = 0.0;
     for (int i = i0 + warp; i < i1; i += 8) {
         const double *x = D.X + (size_t)i * D.R;
@@ -625,27 +1041,37 @@ __global__ void compact_kernel(ChainDev D, int *__restrict__ rej, int reject_liv
 }
 
 template <int NCH>
-int launch_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, int nsm, cudaStream_t st,
-                 cudaEvent_t *ev)
+int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cudaStream_t st, cudaEvent_t *ev)
 {
     const size_t smem_prep = sizeof(double) * D.R + sizeof(int) * D.kcap;
-    const size_t smem_scan = sizeof(double) * D.R + sizeof(int) * 2 * D.kcap;
+    const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap) + sizeof(int) * 3 * D.kcap + 16;
     if (smem_scan > 48 * 1024) {
         CS_CUDA(cudaFuncSetAttribute(prepare_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
         CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+        CS_CUDA(cudaFuncSetAttribute(seq_scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     }
+    const bool reject_live = D.single && tt == 0;
     if (ev) CS_CUDA(cudaEventRecord(ev[0], st));
-    if (!force_all) {
+    if (force_all) {
+        CS_CUDA(cudaMemsetAsync(D.qcols, 0, sizeof(int) * (size_t)D.N, st));
+        if (ev) CS_CUDA(cudaEventRecord(ev[1], st));
+        seq_scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, 1, rej);
+    } else {
         int grid = (D.N + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
         if (grid > nsm * 8) grid = nsm * 8;
         prepare_kernel<NCH><<<grid, PREP_THREADS, smem_prep, st>>>(D, tt, rej);
-    } else {
-        CS_CUDA(cudaMemsetAsync(D.qcols, 0, sizeof(int) * (size_t)D.N, st));
+        if (ev) CS_CUDA(cudaEventRecord(ev[1], st));
+        if (reject_live) {
+            seq_scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, 0, rej);
+        } else {
+            CS_CUDA(cudaMemsetAsync(D.icnt, 0, sizeof(int) * ((size_t)D.N + 1), st));
+            index_count_kernel<<<nsm * 8, 256, 0, st>>>(D);
+            index_scan_kernel<<<1, 1024, 0, st>>>(D);
+            index_fill_kernel<<<nsm * 8, 256, 0, st>>>(D);
+            scan_kernel<NCH><<<1, WIN_THREADS, smem_scan, st>>>(D, tt);
+        }
     }
-    if (ev) CS_CUDA(cudaEventRecord(ev[1], st));
-    scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, force_all, rej);
     if (ev) CS_CUDA(cudaEventRecord(ev[2], st));
-    (void)last;
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
@@ -660,17 +1086,17 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
 {
     const int nsm = cs_num_sms();
     int rc;
-    if (D.R <= 32) rc = launch_sweep<1>(D, tt, last, force_all, rej, nsm, st, ev);
-    else if (D.R <= 64) rc = launch_sweep<2>(D, tt, last, force_all, rej, nsm, st, ev);
-    else if (D.R <= 128) rc = launch_sweep<4>(D, tt, last, force_all, rej, nsm, st, ev);
-    else if (D.R <= 320) rc = launch_sweep<10>(D, tt, last, force_all, rej, nsm, st, ev);
-    else if (D.R <= 1024) rc = launch_sweep<32>(D, tt, last, force_all, rej, nsm, st, ev);
+    if (D.R <= 32) rc = launch_sweep<1>(D, tt, force_all, rej, nsm, st, ev);
+    else if (D.R <= 64) rc = launch_sweep<2>(D, tt, force_all, rej, nsm, st, ev);
+    else if (D.R <= 128) rc = launch_sweep<4>(D, tt, force_all, rej, nsm, st, ev);
+    else if (D.R <= 320) rc = launch_sweep<10>(D, tt, force_all, rej, nsm, st, ev);
+    else if (D.R <= 1024) rc = launch_sweep<32>(D, tt, force_all, rej, nsm, st, ev);
     else {
         cs_set_error("Philox sampler supports up to 1024 segments (R=%d)", D.R);
         return CS_ERR_UNSUPPORTED;
     }
     if (rc) return rc;
-    const int nchunks = (D.N + CS_STAT_CHUNK - 1) / CS_STAT_CHUNK;
+    const int nchunks = (D.N + D.chunk - 1) / D.chunk;
     const int stat_smem = 160 * 1024;
     CS_CUDA(cudaFuncSetAttribute(stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stat_smem));
     stats_partial_kernel<<<nchunks, 256, stat_smem, st>>>(D, stat_smem / 8);
@@ -692,7 +1118,7 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
 int cs_total_loglik_async(const ChainDev &D, const double *U, const int *Zrows, const double *sig, double *d_out,
                           cudaStream_t st)
 {
-    const int nchunks = (D.N + CS_STAT_CHUNK - 1) / CS_STAT_CHUNK;
+    const int nchunks = (D.N + D.chunk - 1) / D.chunk;
     ll_partial_kernel<<<nchunks, 256, 0, st>>>(D, U, Zrows, sig);
     ll_final_kernel<<<1, 32, 0, st>>>(D, nchunks, d_out);
     CS_CUDA(cudaGetLastError());

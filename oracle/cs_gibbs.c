@@ -90,25 +90,23 @@ static void philox_draw(uint32_t seed, uint32_t c0, uint32_t c1, uint32_t c2, ui
     *ub = u53(o[2], o[3]);
 }
 
-/* Canonical evaluation order of the Philox mode (DESIGN.md "Philox mode"): the squared
- * standardised distance of a cell to a row is accumulated as 32 strided partial sums
- * (partial l takes segments l, l+32, ... with a fused multiply-add) that are then
- * combined by a 5-level butterfly — the order one warp of the CUDA path uses, so the
- * two agree bit for bit. */
-static double q_canon(int R, const double *x, const double *u, const double *isig)
+/* Philox mode (DESIGN.md "Philox mode"): the squared standardised distance of a cell to a
+ * row is accumulated in FIXED POINT — every segment contributes
+ *     llrint( ((x - u) * (65536 / sigma))^2 )          (2^-32 resolution)
+ * to a 64-bit integer sum, and q = sum * 2^-32.  Integer addition is associative, so the
+ * value does not depend on the order in which a parallel machine adds the segments and can
+ * be updated exactly when a single term changes; the CUDA path relies on both. */
+static double q_fixed(int R, const double *x, const double *u, const double *isig16)
 {
-    double s[32], t[32];
-    for (int l = 0; l < 32; l++) s[l] = 0.0;
+    long long s = 0;
     for (int r = 0; r < R; r++) {
         if (is_na(x[r])) continue;
-        double d = (x[r] - u[r]) * isig[r];
-        s[r & 31] = fma(d, d, s[r & 31]);
+        double d = (x[r] - u[r]) * isig16[r];
+        double t = d * d;
+        if (!(t < 4611686018427387904.0)) t = 4611686018427387904.0; /* 2^62 clamp (also NaN) */
+        s += llrint(t);
     }
-    for (int off = 16; off >= 1; off >>= 1) {
-        for (int l = 0; l < 32; l++) t[l] = s[l] + s[l ^ off];
-        for (int l = 0; l < 32; l++) s[l] = t[l];
-    }
-    return s[0];
+    return (double)s * (1.0 / 4294967296.0);
 }
 
 typedef struct {
@@ -226,7 +224,7 @@ int cso_gibbs(int N, int R, const double *X, int K0, const double *U0in, const i
 
     for (int tt = 0; tt < niter; tt++) {
         int reject_live = single && tt == 0;
-        for (int r = 0; r < R; r++) isig[r] = 1.0 / sig[r];
+        for (int r = 0; r < R; r++) isig[r] = (1.0 / sig[r]) * 65536.0;
         for (int ii = 0; ii < N; ii++) {
             const double *x = X + (size_t)ii * R;
             int kt = st.kt;
@@ -324,7 +322,7 @@ int cso_gibbs(int N, int R, const double *X, int K0, const double *U0in, const i
                 for (int k = 0; k <= kt; k++) {
                     if (k < kt && st.np[k] == 0) continue;
                     const double *u = (k < kt) ? st.U + (size_t)k * R : mu_new;
-                    double q = q_canon(R, x, u, isig);
+                    double q = q_fixed(R, x, u, isig);
                     pk[k] = q;
                     if (q < qmin) qmin = q;
                 }
