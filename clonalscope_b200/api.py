@@ -337,38 +337,45 @@ def BayesNonparAlleleCluster(Xir_cov=None, Xir_allele=None, cna_states_WGS=None,
     if Xc.shape != Xa.shape:
         raise ValueError("Xir_cov and Xir_allele must have the same shape")
     N, R = Xc.shape
-    ngrid = sum(c + 1 for c in range(maxcp + 1))  # (copies, major copies) states, :26-30
+    grid = np.array([(0.5 * ii, 0.0 if j == 0 else j / ii) for ii in range(1, maxcp + 1) for j in range(ii + 1)])
+    ngrid = grid.shape[0]  # (copies, major-allele fraction) states, :26-30
     if U0 is None:
         if cna_states_WGS is not None:
             U0m = np.vstack([np.full(R, 4), np.asarray(cna_states_WGS).ravel()]).astype(np.int32)
         else:
             U0m = np.full((1, R), 4, dtype=np.int32)
     else:
-        U0m = np.atleast_2d(np.asarray(U0)).astype(np.int32)
+        U0m = np.atleast_2d(np.asarray(_values(U0)[0] if not isinstance(U0, np.ndarray) else U0)).astype(np.int32)
+        if U0m.shape[1] != R:
+            raise ValueError("Please specify a U0 matrix with ncol the same as that of Xir!")
+        if U0m.shape[0] != 1:
+            # the reference dereferences an undefined `result$Uest` here (:51,:62)
+            raise NameError("object 'result' not found")
     if U0m.shape[1] != R:
         raise ValueError("Please specify a U0 matrix with ncol the same as that of Xir!")
     if U0m.min() < 1 or U0m.max() > ngrid:
         raise ValueError(f"U0 state ids must lie in 1..{ngrid}")
 
-    def _sig(s, default):
+    def _sig(s, default, what):
         if s is None:
             return np.full(R, default)
         s = np.asarray(s, dtype=np.float64).ravel()
         if s.size == 1:
             return np.repeat(s, R)
         if s.size != R:
-            raise ValueError("Please specify sigmas0 with length R or length 1.")
+            raise ValueError(f"Please specify {what} with length R or length 1.")
         return s
 
-    sc, sa = _sig(sigmas0_cov, 0.3), _sig(sigmas0_allele, 0.15)
+    sc, sa = _sig(sigmas0_cov, 0.3, "sigmas0_cov"), _sig(sigmas0_allele, 0.15, "sigmas0_allele")
     if Z0 is None:
-        Z0v = np.ones(N, dtype=np.int32)
-        Z0_given = 0
+        # :99-105 argmax over the rows of U0 of the coverage + allele log-likelihood (device)
+        PP = loglik_matrix(np.minimum(Xc, 3.0), grid[U0m - 1, 0], sc) + loglik_matrix(Xa, grid[U0m - 1, 1], sa)
+        Z0v = (np.argmax(PP, axis=1) + 1).astype(np.int32)
     else:
-        Z0v = np.asarray(Z0).astype(np.int32).ravel()
+        Z0v = np.asarray(Z0).ravel()
         if Z0v.size != N:
             raise ValueError("Please specify a vector with length the same as the number of cells!")
-        Z0_given = 1
+        Z0v = np.where(np.isnan(Z0v.astype(np.float64)), 0, Z0v).astype(np.int32)
     K0 = U0m.shape[0]
     Zall = np.zeros((niter, N), dtype=np.int32, order="F")
     sig_cov_all = np.zeros((R, niter), order="F")
@@ -386,7 +393,6 @@ def BayesNonparAlleleCluster(Xir_cov=None, Xir_allele=None, cna_states_WGS=None,
     opts.rng_mode = {"r": _lib.RNG_R, "philox": _lib.RNG_PHILOX}[str(rng).lower()]
     opts.device = -1 if device is None else int(device)
     opts.kcap = 0 if kcap is None else int(kcap)
-    opts.flags = Z0_given << 8
     Xcf, Xaf, U0f = np.asfortranarray(Xc), np.asfortranarray(Xa), np.asfortranarray(U0m)
     _check(_lib.lib().cs_ncrp_gibbs_allele(
         N, R, _ptr(Xcf, C.c_double), _ptr(Xaf, C.c_double), K0, _ptr(U0f, C.c_int), _ptr(Z0v, C.c_int),
@@ -399,10 +405,12 @@ def BayesNonparAlleleCluster(Xir_cov=None, Xir_allele=None, cna_states_WGS=None,
     for t in range(niter):
         a, b = int(u_off[t]), int(u_off[t + 1])
         kt = int(kt_all[t])
-        Uall.append(_expand_U(kt, R, u_labels[a:b], u_state[a:b].astype(np.float64)))
-        Ucov.append(_expand_U(kt, R, u_labels[a:b], u_cov[a:b]))
-        Uallele.append(_expand_U(kt, R, u_labels[a:b], u_allele[a:b]))
+        # emptied clusters keep all-zero rows here (the reference fills with 0, not NA, :203-205)
+        Uall.append(np.nan_to_num(_expand_U(kt, R, u_labels[a:b], u_state[a:b].astype(np.float64))))
+        Ucov.append(np.nan_to_num(_expand_U(kt, R, u_labels[a:b], u_cov[a:b])))
+        Uallele.append(np.nan_to_num(_expand_U(kt, R, u_labels[a:b], u_allele[a:b])))
         print(f"Iteration:{t + 1}")
+        print(f"nclusters={kt}")
     results = dict(Zall=np.ascontiguousarray(Zall), Uall=Uall, Ucov=Ucov, Uallele=Uallele,
                    sigma_cov_all=[sig_cov_all[:, t].copy() for t in range(niter)],
                    sigma_allele_all=[sig_all_all[:, t].copy() for t in range(niter)], Likelihood=LL)

@@ -340,6 +340,7 @@ bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
         if (total == (int)(out_colptr[c + 1] - o)) {
             for (int i = threadIdx.x; i < total; i += FILL_THREADS) s_acc[s_list[i]] = 0;
         } else {
+            __syncthreads(); // the stores above read accumulators this sweep clears
             for (int b = threadIdx.x; b < B; b += FILL_THREADS) s_acc[b] = 0;
             if (threadIdx.x == 0) flags[FLAG_SHRUNK] = 1;
         }

@@ -155,6 +155,53 @@ def expand_U(res, t):
     return U
 
 
+def genotype_grid(maxcp=6):
+    G = maxcp * (maxcp + 3) // 2
+    mu = np.zeros((G, 2))
+    assert lib().cso_genotype_grid(maxcp, _p(mu, C.c_double)) == G
+    return mu
+
+
+def genotype_neighbor(cov, allele, maxcp=6):
+    f = lib().cso_genotype_neighbor
+    f.argtypes = [C.c_double, C.c_double, C.c_int]
+    return f(float(cov), float(allele), maxcp)
+
+
+def gibbs_allele(Xcov, Xall, U0, Z0, sig0_cov, sig0_all, alpha=1.0, beta=1.0, niter=200, seed=200, maxcp=6,
+                 rng_mode=RNG_R, ucap_rows=None):
+    """Returns dict(Zall, sig_cov_all, sig_allele_all, LL, L0, kt, u_off, u_labels, u_state, u_cov, u_allele)."""
+    Xcov = np.ascontiguousarray(Xcov, dtype=np.float64)
+    Xall = np.ascontiguousarray(Xall, dtype=np.float64)
+    U0 = np.ascontiguousarray(np.atleast_2d(U0), dtype=np.int32)
+    Z0 = np.ascontiguousarray(Z0, dtype=np.int32)
+    N, R = Xcov.shape
+    K0 = U0.shape[0]
+    sc = np.ascontiguousarray(np.broadcast_to(np.asarray(sig0_cov, dtype=np.float64), (R,)))
+    sa = np.ascontiguousarray(np.broadcast_to(np.asarray(sig0_all, dtype=np.float64), (R,)))
+    if ucap_rows is None:
+        ucap_rows = niter * 256
+    Zall = np.zeros((niter, N), dtype=np.int32)
+    sca, saa = np.zeros((niter, R)), np.zeros((niter, R))
+    LL, L0 = np.zeros(niter), np.zeros(1)
+    kt = np.zeros(niter, dtype=np.int32)
+    u_off = np.zeros(niter + 1, dtype=np.int64)
+    u_labels = np.zeros(ucap_rows, dtype=np.int32)
+    u_state = np.zeros((ucap_rows, R), dtype=np.int32)
+    u_cov, u_all = np.zeros((ucap_rows, R)), np.zeros((ucap_rows, R))
+    rc = lib().cso_gibbs_allele(
+        N, R, _p(Xcov, C.c_double), _p(Xall, C.c_double), K0, _p(U0, C.c_int), _p(Z0, C.c_int), _p(sc, C.c_double),
+        _p(sa, C.c_double), C.c_double(alpha), C.c_double(beta), niter, C.c_uint32(int(seed)), maxcp, rng_mode,
+        _p(Zall, C.c_int), _p(sca, C.c_double), _p(saa, C.c_double), _p(LL, C.c_double), _p(L0, C.c_double),
+        _p(kt, C.c_int), C.c_int64(ucap_rows), _p(u_off, C.c_int64), _p(u_labels, C.c_int), _p(u_state, C.c_int),
+        _p(u_cov, C.c_double), _p(u_all, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"cso_gibbs_allele failed with code {rc}")
+    n = int(u_off[-1])
+    return dict(Zall=Zall, sig_cov_all=sca, sig_allele_all=saa, LL=LL, L0=float(L0[0]), kt=kt, u_off=u_off,
+                u_labels=u_labels[:n], u_state=u_state[:n], u_cov=u_cov[:n], u_allele=u_all[:n])
+
+
 def majority_vote(Zall):
     Zall = np.ascontiguousarray(Zall, dtype=np.int32)
     T, N = Zall.shape

@@ -350,3 +350,62 @@ def test_kcap_overflow_is_reported(cs):
     with pytest.raises(cs.ClonalscopeError) as e:
         cs.BayesNonparCluster(s["X"], U0=s["U0"], sigmas0=s["sigmas0"], niter=30, rng="philox", kcap=2)
     assert e.value.status == 3
+
+
+# ------------------------------------------------------------------ allele variant (parity UNPINNED by the reference)
+def _allele_data(oracle, N=260, R=7, seed=0, na=0.0):
+    rng = np.random.default_rng(seed)
+    G = oracle.genotype_grid(6)
+    true = np.array([[4] * R, [4, 4, 7, 7, 12, 4, 4][:R], [4, 2, 4, 9, 4, 4, 14][:R]])
+    z = rng.integers(0, 3, N)
+    Xc = G[true[z] - 1, 0] + 0.15 * rng.standard_normal((N, R))
+    Xc[0, 0] = 3.7  # capped at 3 inside the sampler (:37)
+    Xa = np.clip(G[true[z] - 1, 1] + 0.08 * rng.standard_normal((N, R)), 0, 1)
+    if na > 0:
+        Xc[rng.random((N, R)) < na] = np.nan
+        Xa[rng.random((N, R)) < na] = np.nan
+    return Xc, Xa, true, z
+
+
+@pytest.mark.parametrize("rng_name", ["R", "philox"])
+@pytest.mark.parametrize("na", [0.0, 0.03])
+def test_allele_sampler_vs_oracle(cs, oracle, rng_name, na):
+    """No reference output exists for BayesNonparAlleleCluster; the device chain is compared
+    with the CPU restatement of R/BayesNonparAlleleCluster.R draw for draw."""
+    Xc, Xa, true, z = _allele_data(oracle, na=na)
+    niter = 25
+    mode = oracle.RNG_R if rng_name == "R" else oracle.RNG_PHILOX
+    got = cs.BayesNonparAlleleCluster(Xc, Xa, cna_states_WGS=true[1], niter=niter, seed=200, rng=rng_name)
+    Z0 = got["priors"]["Z0"]
+    U0 = np.vstack([np.full(Xc.shape[1], 4), true[1]])
+    want = oracle.gibbs_allele(Xc, Xa, U0, Z0, 0.3, 0.15, niter=niter, seed=200, rng_mode=mode)
+    res = got["results"]
+    mism = int((res["Zall"] != want["Zall"]).sum())
+    assert mism == 0, f"{mism} label mismatches"
+    assert [u.shape[0] for u in res["Uall"]] == list(want["kt"])
+    np.testing.assert_allclose(np.array(res["sigma_cov_all"]), want["sig_cov_all"], rtol=1e-9)
+    np.testing.assert_allclose(np.array(res["sigma_allele_all"]), want["sig_allele_all"], rtol=1e-9)
+    np.testing.assert_allclose(res["Likelihood"], want["LL"], rtol=1e-9)
+    assert abs(got["priors"]["L0"] / want["L0"] - 1) < 1e-12
+    for t in range(niter):
+        a, b = int(want["u_off"][t]), int(want["u_off"][t + 1])
+        lab = want["u_labels"][a:b] - 1
+        assert np.array_equal(res["Uall"][t][lab], want["u_state"][a:b])
+        np.testing.assert_allclose(res["Ucov"][t][lab], want["u_cov"][a:b], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(res["Uallele"][t][lab], want["u_allele"][a:b], rtol=1e-9, atol=1e-12)
+        dead = np.setdiff1d(np.arange(res["Uall"][t].shape[0]), lab)
+        assert not res["Uall"][t][dead].any()  # emptied clusters keep all-zero rows, not NA (:203-205)
+    # invariants: states live on the maxcp = 6 grid, trimmed object has the allele fields
+    assert res["Uall"][-1].max() <= 27
+    tr = cs.MCMCtrim(got, burnin=10, allele=True)
+    assert len(tr["results"]["Ucov"]) == niter - 10 and tr["results"]["Zall"].shape[0] == niter - 10
+
+
+def test_allele_shim_reference_quirks(cs, oracle):
+    Xc, Xa, true, z = _allele_data(oracle)
+    with pytest.raises(NameError):  # a user U0 with more than one row hits the undefined `result$Uest`
+        cs.BayesNonparAlleleCluster(Xc, Xa, U0=np.vstack([np.full(7, 4), true[1]]), niter=2)
+    with pytest.raises(cs.ClonalscopeError) as e:  # a cluster of U0 without cells: sample.int would fail
+        cs.BayesNonparAlleleCluster(Xc, Xa, cna_states_WGS=true[1], Z0=np.ones(len(z), dtype=int), niter=2)
+    assert e.value.status == 6
+    assert oracle.genotype_neighbor(1.02, 0.48) == 4 and oracle.genotype_neighbor(1.6, 0.7) == 8
