@@ -409,3 +409,25 @@ def test_allele_shim_reference_quirks(cs, oracle):
         cs.BayesNonparAlleleCluster(Xc, Xa, cna_states_WGS=true[1], Z0=np.ones(len(z), dtype=int), niter=2)
     assert e.value.status == 6
     assert oracle.genotype_neighbor(1.02, 0.48) == 4 and oracle.genotype_neighbor(1.6, 0.7) == 8
+
+
+# ------------------------------------------------------------------ cell-sharded sufficient statistics
+def test_device_stats_match_numpy(cs):
+    import torch
+    from clonalscope_b200 import distributed as D
+    rng = np.random.default_rng(4)
+    for (N, R, K) in [(1000, 13, 5), (5000, 300, 20), (300, 40, 80)]:
+        X = rng.normal(1.0, 0.3, size=(N, R))
+        X[rng.random((N, R)) < 0.03] = np.nan
+        Z = rng.integers(1, K + 1, size=N).astype(np.int32)
+        U = rng.uniform(0.5, 2.0, size=(K, R))
+        out = D.allreduce_stats(torch.from_numpy(X).cuda(), torch.from_numpy(Z).cuda(), torch.from_numpy(U).cuda(), K)
+        for k in range(K):
+            rows = X[Z == k + 1]
+            assert int(out["n_k"][k].item()) == len(rows)
+            cnt = (~np.isnan(rows)).sum(axis=0)
+            want = np.where(cnt > 0, np.nansum(rows, axis=0) / np.maximum(cnt, 1), 0.0)
+            np.testing.assert_allclose(out["mean"][k].cpu().numpy(), want, rtol=1e-11, atol=1e-12)
+        d = X - U[Z - 1]
+        sig = np.sqrt(np.nansum(d * d, axis=0) / (~np.isnan(X)).sum(axis=0))
+        np.testing.assert_allclose(out["sigma"].cpu().numpy(), sig, rtol=1e-11)
