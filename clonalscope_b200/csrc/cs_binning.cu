@@ -31,6 +31,7 @@ namespace {
 
 constexpr uint32_t GMAP_ESC = 0xFFFFFFFFu;
 constexpr int FILL_THREADS = 512;
+constexpr int LIST_CAP = 6144; // ranks staged per output round (u16 each)
 constexpr int COUNT_THREADS = 128;
 
 enum { FLAG_INEXACT = 0, FLAG_SHRUNK = 1, FLAG_CAP = 2, NFLAGS = 4 };
@@ -173,11 +174,10 @@ struct AccOps<int> {
     // returns false when v cannot be accumulated exactly as an int32
     static __device__ __forceinline__ bool conv(double v, int &iv)
     {
-        iv = (int)v; // saturating cvt.rzi
-        return (double)iv == v && v < 1073741824.0 && v > -1073741824.0;
+        iv = __double2int_rz(v); // saturating
+        return __int2double_rn(iv) == v && (unsigned)(iv + (1 << 30)) < (1u << 31);
     }
-    static __device__ __forceinline__ bool add(int *a, int iv) { return atomicAdd(a, iv) == 0; }
-    static __device__ __forceinline__ double mag(int iv) { return fabs((double)iv); }
+    static __device__ __forceinline__ unsigned mag(int iv) { return (unsigned)abs(iv); }
 };
 template <>
 struct AccOps<double> {
@@ -186,45 +186,61 @@ struct AccOps<double> {
         iv = v;
         return true;
     }
-    // the "first toucher" test cannot rely on the old value for doubles (a partial sum
-    // may pass through zero), so the bitmap bit is set unconditionally
-    static __device__ __forceinline__ bool add(double *a, double v)
-    {
-        atomicAdd(a, v);
-        return true;
-    }
-    static __device__ __forceinline__ double mag(double) { return 0.0; }
+    static __device__ __forceinline__ unsigned mag(double) { return 0u; }
 };
 
+// Shared-memory atomics retire about one lane every two cycles on this part, which makes them
+// the budget of this kernel (~2,500 per column): one ATOMS.ADD per hit and nothing else — the
+// touched bins are recovered afterwards from the accumulators themselves.
 template <typename Acc>
-__device__ __forceinline__ void scatter_entry(int g, double v, Acc *s_acc, uint32_t *s_bits,
-                                              const uint32_t *__restrict__ gmap,
-                                              const int32_t *__restrict__ map_ptr,
-                                              const int32_t *__restrict__ map_bin, bool &inexact,
-                                              double &magsum)
+__device__ __forceinline__ void hit(int b, Acc iv, Acc *s_acc)
 {
-    Acc iv;
-    if (!AccOps<Acc>::conv(v, iv)) inexact = true;
-    const uint32_t w = __ldg(gmap + g);
+    atomicAdd(&s_acc[b], iv);
+}
+
+// genes spanning three or more bins, or with non-contiguous bins (rare): rolled loops so that
+// the common path stays a handful of instructions
+template <typename Acc>
+__device__ __forceinline__ void scatter_wide(int g, uint32_t w, Acc iv, Acc *s_acc,
+                                          const int32_t *__restrict__ map_ptr,
+                                          const int32_t *__restrict__ map_bin, unsigned long long &magsum)
+{
     if (w != GMAP_ESC) {
         const int b0 = w & 0xFFFFF, nh = w >> 20;
-        for (int t = 0; t < nh; t++) {
-            const int b = b0 + t;
-            if (AccOps<Acc>::add(&s_acc[b], iv)) atomicOr(&s_bits[b >> 5], 1u << (b & 31));
-        }
-        magsum += AccOps<Acc>::mag(iv) * nh;
+#pragma unroll 1
+        for (int t = 0; t < nh; t++) hit<Acc>(b0 + t, iv, s_acc);
+        magsum += (unsigned long long)AccOps<Acc>::mag(iv) * (unsigned)nh;
     } else {
         const int m0 = map_ptr[g], m1 = map_ptr[g + 1];
-        for (int m = m0; m < m1; m++) {
-            const int b = map_bin[m];
-            if (AccOps<Acc>::add(&s_acc[b], iv)) atomicOr(&s_bits[b >> 5], 1u << (b & 31));
-        }
-        magsum += AccOps<Acc>::mag(iv) * (m1 - m0);
+#pragma unroll 1
+        for (int m = m0; m < m1; m++) hit<Acc>(map_bin[m], iv, s_acc);
+        magsum += (unsigned long long)AccOps<Acc>::mag(iv) * (unsigned)(m1 - m0);
     }
 }
 
 template <typename Acc>
-__global__ void __launch_bounds__(FILL_THREADS)
+__device__ __forceinline__ void scatter_entry(int g, double v, Acc *s_acc,
+                                              const uint32_t *__restrict__ gmap,
+                                              const int32_t *__restrict__ map_ptr,
+                                              const int32_t *__restrict__ map_bin, bool &inexact,
+                                              unsigned long long &magsum)
+{
+    Acc iv;
+    if (!AccOps<Acc>::conv(v, iv)) inexact = true;
+    const uint32_t w = __ldg(gmap + g);
+    const unsigned nh = w >> 20;
+    if (nh - 1u < 2u) { // one or two contiguous bins: 98 % of the genes over 200-kb tiles
+        const int b0 = w & 0xFFFFF;
+        hit<Acc>(b0, iv, s_acc);
+        if (nh == 2u) hit<Acc>(b0 + 1, iv, s_acc);
+        magsum += (unsigned long long)AccOps<Acc>::mag(iv) * nh;
+    } else if (w != 0u) {
+        scatter_wide<Acc>(g, w, iv, s_acc, map_ptr, map_bin, magsum);
+    }
+}
+
+template <typename Acc>
+__global__ void __launch_bounds__(FILL_THREADS, 3)
 bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
                 const int32_t *__restrict__ rowidx, const double *__restrict__ x,
                 const uint32_t *__restrict__ gmap, const int32_t *__restrict__ map_ptr,
@@ -233,45 +249,69 @@ bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
                 int *__restrict__ counts_actual, int *__restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const int words = (B + 31) >> 5;
+    // every thread owns a contiguous run of PER bins (a multiple of 32) of the accumulator array
+    const int PER = (((B + FILL_THREADS - 1) / FILL_THREADS) + 31) & ~31;
+    const int BP = (B + 31) & ~31; // accumulators, padded to a multiple of 32
     Acc *s_acc = reinterpret_cast<Acc *>(s_raw);
-    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_acc + B);
-    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_bits + words);
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_acc + BP);
     __shared__ int s_warp[FILL_THREADS / 32 + 1];
-    __shared__ double s_mag[FILL_THREADS / 32];
+    __shared__ unsigned long long s_mag[FILL_THREADS / 32];
 
     if (out_colptr[N] > out_cap) { // caller's buffers too small: report, write nothing
         if (blockIdx.x == 0 && threadIdx.x == 0) flags[FLAG_CAP] = 1;
         return;
     }
-    for (int b = threadIdx.x; b < B; b += FILL_THREADS) s_acc[b] = 0;
-    for (int w = threadIdx.x; w < words; w += FILL_THREADS) s_bits[w] = 0;
+    for (int b = threadIdx.x; b < BP; b += FILL_THREADS) s_acc[b] = 0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int wpt = (words + FILL_THREADS - 1) / FILL_THREADS; // bitmap words per thread
+    constexpr int MAXW = 4; // PER <= 128 bins per thread (B <= 65535)
+    const int nw = PER >> 5;
+    const int bin0 = threadIdx.x * PER;
+
+    // the first 128-bit group of every thread is fetched one column ahead, so that its HBM
+    // latency hides behind the compaction of the current column
+    int4 pg4 = make_int4(0, 0, 0, 0);
+    double2 pv01 = make_double2(0, 0), pv23 = make_double2(0, 0);
+    auto prefetch = [&](int col) {
+        if (col < N) {
+            const int64_t a0 = colptr[col], a1 = colptr[col + 1];
+            const int64_t ab = min((a0 + 3) & ~(int64_t)3, a1), ae = max(ab, a1 & ~(int64_t)3);
+            const int64_t e = ab + 4 * (int64_t)threadIdx.x;
+            if (e < ae) {
+                pg4 = __ldcs(reinterpret_cast<const int4 *>(rowidx + e));
+                pv01 = __ldcs(reinterpret_cast<const double2 *>(x + e));
+                pv23 = __ldcs(reinterpret_cast<const double2 *>(x + e + 2));
+            }
+        }
+    };
+    prefetch(blockIdx.x);
 
     for (int c = blockIdx.x; c < N; c += gridDim.x) {
         const int64_t e0 = colptr[c], e1 = colptr[c + 1];
         bool inexact = false;
-        double magsum = 0.0;
+        unsigned long long magsum = 0;
         // 128-bit body: 4 row indices + 4 values per thread per step
         const int64_t eb = min((e0 + 3) & ~(int64_t)3, e1), ee = max(eb, e1 & ~(int64_t)3);
         for (int64_t e = eb + 4 * (int64_t)threadIdx.x; e < ee; e += 4 * FILL_THREADS) {
-            const int4 g4 = __ldcs(reinterpret_cast<const int4 *>(rowidx + e));
-            const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(x + e));
-            const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(x + e + 2));
-            scatter_entry<Acc>(g4.x, v01.x, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
-            scatter_entry<Acc>(g4.y, v01.y, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
-            scatter_entry<Acc>(g4.z, v23.x, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
-            scatter_entry<Acc>(g4.w, v23.y, s_acc, s_bits, gmap, map_ptr, map_bin, inexact, magsum);
+            int4 g4 = pg4;
+            double2 v01 = pv01, v23 = pv23;
+            if (e >= eb + 4 * (int64_t)FILL_THREADS) { // columns longer than one round of the CTA
+                g4 = __ldcs(reinterpret_cast<const int4 *>(rowidx + e));
+                v01 = __ldcs(reinterpret_cast<const double2 *>(x + e));
+                v23 = __ldcs(reinterpret_cast<const double2 *>(x + e + 2));
+            }
+            scatter_entry<Acc>(g4.x, v01.x, s_acc, gmap, map_ptr, map_bin, inexact, magsum);
+            scatter_entry<Acc>(g4.y, v01.y, s_acc, gmap, map_ptr, map_bin, inexact, magsum);
+            scatter_entry<Acc>(g4.z, v23.x, s_acc, gmap, map_ptr, map_bin, inexact, magsum);
+            scatter_entry<Acc>(g4.w, v23.y, s_acc, gmap, map_ptr, map_bin, inexact, magsum);
         }
         { // unaligned head and tail (at most 3 + 3 entries)
             const int nhead = (int)(eb - e0), ntail = (int)(e1 - ee);
             if ((int)threadIdx.x < nhead + ntail) {
                 const int64_t e = ((int)threadIdx.x < nhead) ? e0 + threadIdx.x
                                                              : ee + (threadIdx.x - nhead);
-                scatter_entry<Acc>(rowidx[e], x[e], s_acc, s_bits, gmap, map_ptr, map_bin, inexact,
+                scatter_entry<Acc>(rowidx[e], x[e], s_acc, gmap, map_ptr, map_bin, inexact,
                                    magsum);
             }
         }
@@ -279,22 +319,25 @@ bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
         for (int off = 16; off >= 1; off >>= 1) magsum += __shfl_xor_sync(CS_FULL, magsum, off);
         if (lane == 0) s_mag[wid] = magsum;
         if (inexact) flags[FLAG_INEXACT] = 1;
+        prefetch(c + gridDim.x);
         __syncthreads();
 
-        // compaction: drop zero sums, count, scan, list ascending bins
+        // compaction: the nonzero accumulators are the output (zero sums are dropped, as
+        // Matrix(sparse=TRUE) does); one mask of 32 bins per register
         int cnt = 0;
-        const int w0 = threadIdx.x * wpt;
-        for (int j = 0; j < wpt; j++) {
-            const int w = w0 + j;
-            if (w >= words) break;
-            uint32_t bits = s_bits[w], keep = bits;
-            while (bits) {
-                const int t = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (s_acc[(w << 5) + t] == (Acc)0) keep &= ~(1u << t);
+        uint32_t mask[MAXW];
+#pragma unroll
+        for (int j = 0; j < MAXW; j++) {
+            mask[j] = 0;
+            if (j < nw && bin0 + 32 * j < BP) {
+                const Acc *a = s_acc + bin0 + 32 * j;
+#pragma unroll
+                for (int t = 0; t < 32; t++) { // rotated per lane: the 32 lanes read 32 different banks
+                    const int q = (t + lane) & 31;
+                    mask[j] |= (a[q] != (Acc)0) ? (1u << q) : 0u;
+                }
+                cnt += __popc(mask[j]);
             }
-            s_bits[w] = keep;
-            cnt += __popc(keep);
         }
         int inc = cnt;
         for (int off = 1; off < 32; off <<= 1) {
@@ -311,40 +354,42 @@ bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
             }
             if (lane < FILL_THREADS / 32) s_warp[lane] = winc - w;
             if (lane == FILL_THREADS / 32 - 1) s_warp[FILL_THREADS / 32] = winc;
-            double m = (lane < FILL_THREADS / 32) ? s_mag[lane] : 0.0;
+            unsigned long long m = (lane < FILL_THREADS / 32) ? s_mag[lane] : 0ull;
             for (int off = 16; off >= 1; off >>= 1) m += __shfl_xor_sync(CS_FULL, m, off);
-            if (lane == 0 && m >= 2147483647.0) flags[FLAG_INEXACT] = 1;
+            if (lane == 0 && m >= 2147483647ull) flags[FLAG_INEXACT] = 1;
         }
         __syncthreads();
-        int rank = s_warp[wid] + inc - cnt;
+        const int rank0 = s_warp[wid] + inc - cnt;
         const int total = s_warp[FILL_THREADS / 32];
-        for (int j = 0; j < wpt; j++) {
-            const int w = w0 + j;
-            if (w >= words) break;
-            uint32_t bits = s_bits[w];
-            s_bits[w] = 0;
-            while (bits) {
-                const int t = __ffs(bits) - 1;
-                bits &= bits - 1;
-                s_list[rank++] = (uint16_t)((w << 5) + t);
-            }
-        }
-        __syncthreads();
         const int64_t o = out_colptr[c];
-        for (int i = threadIdx.x; i < total; i += FILL_THREADS) {
-            const int b = s_list[i];
-            __stcs(out_rowidx + o + i, b);
-            __stcs(out_x + o + i, (double)s_acc[b]);
+        // the staging list holds LIST_CAP ranks; columns with more outputs go out in rounds
+        for (int base = 0; base < total; base += LIST_CAP) {
+            int rank = rank0 - base;
+#pragma unroll
+            for (int j = 0; j < MAXW; j++) {
+                uint32_t bits = mask[j];
+                while (bits) {
+                    const int t = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if ((unsigned)rank < (unsigned)LIST_CAP) s_list[rank] = (uint16_t)(bin0 + 32 * j + t);
+                    rank++;
+                }
+            }
+            __syncthreads();
+            const int n = min(LIST_CAP, total - base);
+            for (int i = threadIdx.x; i < n; i += FILL_THREADS) {
+                const int b = s_list[i];
+                __stcs(out_rowidx + o + base + i, b);
+                __stcs(out_x + o + base + i, (double)s_acc[b]);
+                s_acc[b] = (Acc)0;
+            }
+            __syncthreads();
         }
-        // re-zero every accumulator this column touched (incl. dropped zero sums)
-        if (total == (int)(out_colptr[c + 1] - o)) {
-            for (int i = threadIdx.x; i < total; i += FILL_THREADS) s_acc[s_list[i]] = 0;
-        } else {
-            __syncthreads(); // the stores above read accumulators this sweep clears
-            for (int b = threadIdx.x; b < B; b += FILL_THREADS) s_acc[b] = 0;
-            if (threadIdx.x == 0) flags[FLAG_SHRUNK] = 1;
+        // touched bins whose sum is zero were dropped: their accumulators already hold zero
+        if (threadIdx.x == 0) {
+            counts_actual[c] = total;
+            if (total != (int)(out_colptr[c + 1] - o)) flags[FLAG_SHRUNK] = 1;
         }
-        if (threadIdx.x == 0) counts_actual[c] = total;
         __syncthreads();
     }
 }
@@ -462,8 +507,7 @@ struct cs_bin_plan {
 
 static size_t fill_smem_bytes(int B, size_t acc_size)
 {
-    const size_t words = (B + 31) / 32;
-    return (size_t)B * acc_size + words * 4 + (size_t)B * 2 + 16;
+    return (size_t)((B + 31) & ~31) * acc_size + (size_t)(B < LIST_CAP ? B : LIST_CAP) * 2 + 16;
 }
 
 extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const int32_t *map_bin,
