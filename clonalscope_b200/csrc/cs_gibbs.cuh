@@ -45,6 +45,7 @@ struct ChainDev {
     int *icur;        // N          fill cursors
     unsigned *inv;    // N x R      (cell << 10 | segment) entries grouped by source cell
     double *inv_x;    // N x R      X[cell][segment] of the same entries
+    int *nd;          // N          nearest later cell whose proposal copies this cell
     long long *tile_sums; // scan scratch
     double *mean;     // kcap x R cluster means
     double *psum;     // partial sums workspace

@@ -44,8 +44,9 @@ namespace {
 constexpr int PREP_THREADS = 256;
 constexpr int SCAN_THREADS = 1024;  // sequential kernel: one warp per cell
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
-constexpr int WIN_THREADS = 256;    // windowed kernel: one thread per cell of the window ...
-constexpr int WIN_CELLS = 128;      // ... one warp per scheduler draws, all threads correct dependents
+constexpr int WIN_THREADS = 512;    // windowed kernel: one thread per cell of the window;
+constexpr int WIN_MIN = 128;        // the window grows 128 -> 512 cells while rounds find no event
+constexpr int WIN_CELLS = WIN_THREADS; // and shrinks again when they are cut short
 constexpr double Q_SCALE = 1.0 / 4294967296.0;
 
 template <int NCH>
@@ -314,34 +315,53 @@ __device__ __forceinline__ int draw_cell_thread(const double *Qc, const double *
 }
 
 // the common case of the windowed scan: at most 32 live clusters, all exponentials cached,
-// candidate set as at the start of the sweep.  One pass, cumulative sums kept in registers.
-// s_npd[s] / s_npd1[s] = (double) np[s] / (double)(np[s] - 1), 0 when not positive.
+// candidate set as at the start of the sweep.  One pass; the cumulative sums also go to shared
+// memory (s_cum[s * WIN_CELLS + t]) so that the two that bracket the draw can be fetched by
+// index.  s_npd[s] / s_npd1[s] = (double) np[s] / (double)(np[s] - 1), 0 when not positive.
+//
+// *margin receives how far every cumulative sum and the threshold may move before this draw
+// could change: half the distance from t = u * total to the nearer of the two cumulative sums
+// that bracket it, minus a rounding allowance (the sums have at most 33 non-negative terms:
+// their floating-point error is below 1e-14 * total; 1e-12 is charged).  An event that moves
+// one cell from slot a to slot b moves every sum and t by at most E[a] + E[b].
 __device__ __forceinline__ int draw_cell_fast32(const double *Ec, size_t stride, int nlive, const double *s_npd,
-                                                const double *s_npd1, int zold, double w_new, double ua)
+                                                const double *s_npd1, int zold, double w_new, double ua,
+                                                double *s_cum, double *margin)
 {
-    double cum[32];
     unsigned pos = 0;
     double run = 0.0;
 #pragma unroll
     for (int s = 0; s < 32; s++) {
-        cum[s] = 0.0;
         if (s < nlive) {
             const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
             const double w = __dmul_rn(nd, Ec[(size_t)s * stride]);
             run = __dadd_rn(run, w);
-            cum[s] = run;
+            s_cum[s * WIN_CELLS] = run;
             if (w > 0.0) pos |= 1u << s;
         }
     }
-    const double t = __dmul_rn(ua, __dadd_rn(run, w_new));
-    unsigned hit = 0;
+    const double tot = __dadd_rn(run, w_new);
+    const double t = __dmul_rn(ua, tot);
+    unsigned le = 0; // cumulative sums are non-decreasing: those <= t form a prefix
 #pragma unroll
     for (int s = 0; s < 32; s++)
-        if (cum[s] > t) hit |= 1u << s;
-    hit &= pos;
-    if (hit) return __ffs(hit) - 1;
-    if (w_new > 0.0) return nlive;
-    return pos ? 31 - __clz(pos) : -1;
+        if (s < nlive && !(s_cum[s * WIN_CELLS] > t)) le |= 1u << s;
+    const int k = __popc(le); // first slot whose cumulative sum exceeds t (it has positive weight)
+    int z;
+    double gap;
+    const double below = t - (k > 0 ? s_cum[(k - 1) * WIN_CELLS] : 0.0);
+    if (k < nlive) {
+        z = k;
+        gap = fmin(below, s_cum[k * WIN_CELLS] - t);
+    } else if (w_new > 0.0) {
+        z = nlive;
+        gap = below;
+    } else {
+        z = pos ? 31 - __clz(pos) : -1;
+        gap = 0.0;
+    }
+    *margin = 0.5 * gap - 1e-12 * tot;
+    return z;
 }
 
 // ---------------------------------------------------------------- prepare (all SMs)
@@ -484,13 +504,17 @@ __global__ void index_fill_kernel(ChainDev D)
         const int j = D.J[e];
         if (j >= 0) {
             const int p = atomicAdd(&D.icur[j], 1);
-            D.inv[p] = ((unsigned)(e / (size_t)D.R) << 10) | (unsigned)(e % (size_t)D.R);
+            const int cc = (int)(e / (size_t)D.R);
+            D.inv[p] = ((unsigned)cc << 10) | (unsigned)(e % (size_t)D.R);
+            if (cc > j) atomicMin(&D.nd[j], cc); // nearest later cell whose proposal copies cell j
             D.inv_x[p] = D.X[e]; // the value the correction needs rides along: one dependent load less
         }
     }
 }
 
 // ---------------------------------------------------------------- scan (one CTA, thread per cell)
+constexpr int MAX_EV = 16; // events committed per window round
+
 template <int NCH>
 __global__ void __launch_bounds__(WIN_THREADS)
 scan_kernel(ChainDev D, int tt)
@@ -499,13 +523,12 @@ scan_kernel(ChainDev D, int tt)
     double *s_isig16 = s_dyn;                 // R
     double *s_npd = s_dyn + D.R;              // kcap : (double) np[s]      (0 when np <= 0)
     double *s_npd1 = s_npd + D.kcap;          // kcap : (double)(np[s] - 1) (0 when np <= 1)
-    int *s_np = reinterpret_cast<int *>(s_npd1 + D.kcap);
+    double *s_cum = s_npd1 + D.kcap;          // 32 x WIN_CELLS cumulative sums of the fast draw
+    int *s_np = reinterpret_cast<int *>(s_cum + 32 * WIN_CELLS);
     int *s_label = s_np + D.kcap;
     int *s_np0 = s_label + D.kcap;            // counts at the start of the sweep
-    // s_fmin[k % 3] collects window k's first event; slot (k+2) % 3 is reset right after window
-    // k's barrier: its last readers (window k-1) are behind that barrier and its next writers
-    // (window k+2) are beyond the next one, so one barrier per event-free window suffices
-    __shared__ int s_nlive, s_kt, s_fmin[3], s_err, s_z, s_zold, s_e0, s_e1;
+    __shared__ int s_nlive, s_kt, s_err, s_first, s_inval, s_z, s_zold, s_e0, s_e1, s_stop;
+    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV];
     __shared__ long long s_scanned, s_events;
 
     const int f0 = D.scal->first_event;
@@ -522,20 +545,24 @@ scan_kernel(ChainDev D, int tt)
     if (threadIdx.x == 0) {
         s_nlive = D.scal->nlive;
         s_kt = D.scal->kt;
-        s_fmin[0] = s_fmin[1] = s_fmin[2] = INT_MAX;
         s_err = 0;
+        s_first = INT_MAX;
+        s_inval = INT_MAX;
         s_scanned = 0;
         s_events = 0;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t N = (size_t)D.N;
-    int pos = f0, round = 0;
+    int pos = f0, W = WIN_MIN;
     while (pos < D.N) {
+        // ---- every cell of the window is re-drawn exactly against the committed state
         const int c = pos + threadIdx.x;
+        const bool active = threadIdx.x < W && c < D.N;
         const int nlive = s_nlive;
-        int z = -1, zold = -1, ev = INT_MAX, e0 = 0, e1 = 0;
-        if (threadIdx.x < WIN_CELLS && c < D.N) {
+        int z = -1, zold = -1, e0 = 0, e1 = 0;
+        double margin = 0.0; // what this draw tolerates before it has to be redone
+        if (active) {
             zold = D.Zs[c];
             const long long qi = __ldcg(D.qnew_i + c);
             const double q_new = (double)qi * Q_SCALE;
@@ -556,80 +583,104 @@ scan_kernel(ChainDev D, int tt)
                     D.wn_q[c] = qi;
                     D.wn_w[c] = w_new;
                 }
-                z = draw_cell_fast32(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua);
+                z = draw_cell_fast32(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, s_cum + threadIdx.x, &margin);
             } else {
                 z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, s_np, zold, q_new, qmin, D.beta, ua);
             }
             if (z != zold) {
-                ev = c;
                 e0 = D.icnt[c]; // dependents' range, fetched while the window is being reduced
                 e1 = D.icnt[c + 1];
-                // candidates that lose this round usually still are events in a later one:
-                // pull their dependents towards the SM now
-                for (int e = e0; e < e1; e += 16) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(D.inv_x + e));
-                    if (((e - e0) & 16) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(D.inv + e));
-                }
             }
         }
-        const int wev = __reduce_min_sync(CS_FULL, ev);
-        if (lane == 0 && wev != INT_MAX) atomicMin(&s_fmin[round % 3], wev);
-        __syncthreads();
-        const int f = s_fmin[round % 3];
-        if (threadIdx.x == 0) {
-            s_scanned += (f != INT_MAX ? (f - pos + 1) : min(WIN_CELLS, D.N - pos));
-            s_fmin[(round + 2) % 3] = INT_MAX;
-        }
-        round++;
-        if (f == INT_MAX) { // no event in the window: everything in it keeps its label
-            pos += WIN_CELLS;
-            continue;
-        }
-        if (c == f) {
-            s_z = z;
-            s_zold = zold;
-            s_e0 = e0;
-            s_e1 = e1;
-        }
-        __syncthreads();
-        // ---- commit the event at cell f: it moves from slot a to slot b
-        const int a = s_zold;
-        const int b = s_z;
-        const bool opens = (b == nlive);
-        if (opens) { // :209-212 open a new cluster with the proposed per-segment states
-            if (nlive >= D.kcap) {
-                if (threadIdx.x == 0) s_err = CS_ERR_KCAP;
-            } else {
-                double *urow = D.U + (size_t)nlive * D.R;
-                const int *Jrow = D.J + (size_t)f * D.R;
-                for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) {
-                    const int j = Jrow[r];
-                    urow[r] = (j >= 0) ? D.U[(size_t)D.Zs[j] * D.R + r] : fresh_state(D, f, r, tt, 0u);
-                }
+        // ---- commit events in order for as long as the draws behind them provably still hold
+        int nev = 0, lo = pos, limit = min(D.N, pos + W);
+        bool opened = false;
+        for (;;) {
+            int mc = INT_MAX, mv = INT_MAX;
+            if (active && c >= lo) {
+                if (z != zold) mc = c;
+                if (nev > 0 && !(margin > 0.0)) mv = c;
+            }
+            mc = __reduce_min_sync(CS_FULL, mc);
+            mv = __reduce_min_sync(CS_FULL, mv);
+            if (lane == 0) {
+                if (mc != INT_MAX) atomicMin(&s_first, mc);
+                if (mv != INT_MAX) atomicMin(&s_inval, mv);
             }
             __syncthreads();
-            if (s_err) break;
-        }
-        if (threadIdx.x == 0) {
-            const int na = s_np[a] - 1, nb = opens ? 1 : s_np[b] + 1;
-            s_np[a] = na;
-            s_npd[a] = na > 0 ? (double)na : 0.0;
-            s_npd1[a] = na > 1 ? (double)(na - 1) : 0.0;
-            s_np[b] = nb;
-            s_npd[b] = (double)nb;
-            s_npd1[b] = nb > 1 ? (double)(nb - 1) : 0.0;
-            if (opens) {
-                s_label[b] = ++s_kt;
-                s_nlive = nlive + 1;
+            const int f = s_first, v = min(s_inval, limit);
+            if (f == INT_MAX || f >= v) break; // nothing (more) that can be committed in this round
+            if (c == f) {
+                s_z = z;
+                s_zold = zold;
+                s_e0 = e0;
+                s_e1 = e1;
             }
-            D.Zs[f] = b;
-            s_events += 1;
+            __syncthreads();
+            // the event at cell f moves it from slot a to slot b
+            const int a = s_zold, b = s_z;
+            const bool opens = (b == s_nlive);
+            if (opens) { // :209-212 open a new cluster with the proposed per-segment states
+                if (b >= D.kcap) {
+                    if (threadIdx.x == 0) s_err = CS_ERR_KCAP;
+                } else {
+                    double *urow = D.U + (size_t)b * D.R;
+                    const int *Jrow = D.J + (size_t)f * D.R;
+                    for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) {
+                        const int j = Jrow[r];
+                        urow[r] = (j >= 0) ? D.U[(size_t)D.Zs[j] * D.R + r] : fresh_state(D, f, r, tt, 0u);
+                    }
+                }
+                __syncthreads();
+                if (s_err) break;
+            }
+            if (threadIdx.x == 0) {
+                const int na0 = s_np[a], nb0 = opens ? 0 : s_np[b];
+                const int na = na0 - 1, nb = nb0 + 1;
+                // does the set of candidates (np >= 1; np >= 2 for a cell's own cluster) change?
+                const bool cand = ((na0 >= 1) != (na >= 1)) || ((na0 >= 2) != (na >= 2)) ||
+                                  ((nb0 >= 1) != (nb >= 1)) || ((nb0 >= 2) != (nb >= 2));
+                s_np[a] = na;
+                s_npd[a] = na > 0 ? (double)na : 0.0;
+                s_npd1[a] = na > 1 ? (double)(na - 1) : 0.0;
+                s_np[b] = nb;
+                s_npd[b] = (double)nb;
+                s_npd1[b] = nb > 1 ? (double)(nb - 1) : 0.0;
+                if (opens) {
+                    s_label[b] = ++s_kt;
+                    s_nlive = b + 1;
+                }
+                D.Zs[f] = b;
+                s_events += 1;
+                s_ev_f[nev] = f;
+                s_ev_a[nev] = a;
+                s_ev_b[nev] = b;
+                s_ev_e0[nev] = s_e0;
+                s_ev_e1[nev] = s_e1;
+                // a changed candidate set or a new cluster invalidates the cached draws of the
+                // window wholesale: stop batching, the next round re-draws everything
+                s_stop = (opens || cand || nev + 1 == MAX_EV) ? 1 : 0;
+                s_first = INT_MAX;
+                s_inval = INT_MAX;
+            }
+            nev++;
+            lo = f + 1;
+            opened = opens;
+            // cells whose proposal copied cell f have a corrected distance coming: from the nearest
+            // of them on, this round's draws are void
+            limit = min(limit, __ldg(D.nd + f));
+            // every sum and threshold of the cells behind f moves by at most E[a] + E[b]
+            if (active && c > f && !opens)
+                margin -= (D.E[(size_t)a * N + c] + D.E[(size_t)b * N + c]) * 1.000000001;
+            __syncthreads();
+            if (s_stop) break;
         }
-        // ---- proposals that copied cell f's cluster state: correct their distance exactly
-        {
-            const int e1s = s_e1;
-            const double *ua_row = D.U + (size_t)a * D.R, *ub_row = D.U + (size_t)b * D.R;
-            for (int e = s_e0 + threadIdx.x; e < e1s; e += WIN_THREADS) {
+        if (s_err) break;
+        // ---- proposals that copied a moved cell's cluster state: correct their distance exactly
+        for (int i = 0; i < nev; i++) {
+            const int f = s_ev_f[i], e1s = s_ev_e1[i];
+            const double *ua_row = D.U + (size_t)s_ev_a[i] * D.R, *ub_row = D.U + (size_t)s_ev_b[i] * D.R;
+            for (int e = s_ev_e0[i] + threadIdx.x; e < e1s; e += WIN_THREADS) {
                 const unsigned cr = D.inv[e];
                 const double xv = D.inv_x[e];
                 const int cc = (int)(cr >> 10), r = (int)(cr & 1023u);
@@ -640,7 +691,8 @@ scan_kernel(ChainDev D, int tt)
             }
         }
         // ---- a new cluster is a new candidate for every later cell: score them now
-        if (opens) {
+        if (opened) {
+            const int f = s_ev_f[nev - 1], b = s_ev_b[nev - 1];
             double x[NCH];
             const double *urow = D.U + (size_t)b * D.R;
             for (int cc = f + 1 + warp; cc < D.N; cc += WIN_THREADS / 32) {
@@ -666,8 +718,17 @@ scan_kernel(ChainDev D, int tt)
                 }
             }
         }
+        if (threadIdx.x == 0) {
+            s_scanned += (nev ? lo - pos : min(W, D.N - pos));
+            s_first = INT_MAX;
+            s_inval = INT_MAX;
+        }
         __syncthreads(); // orders the corrections (L2 atomics) before the next window's .cg loads
-        pos = f + 1;
+        const int adv = nev ? lo - pos : W;
+        pos += adv;
+        // sparse events: wider windows (fewer rounds); dense events: narrower ones (cheaper rounds)
+        if (nev == 0) W = min(WIN_CELLS, W * 2);
+        else if (adv < W / 4 && nev < MAX_EV) W = max(WIN_MIN, W / 2);
     }
     __syncthreads();
     for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
@@ -1044,10 +1105,10 @@ template <int NCH>
 int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cudaStream_t st, cudaEvent_t *ev)
 {
     const size_t smem_prep = sizeof(double) * D.R + sizeof(int) * D.kcap;
-    const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap) + sizeof(int) * 3 * D.kcap + 16;
+    const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap + 32 * WIN_CELLS) + sizeof(int) * 3 * D.kcap + 16;
+    CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     if (smem_scan > 48 * 1024) {
         CS_CUDA(cudaFuncSetAttribute(prepare_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
-        CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         CS_CUDA(cudaFuncSetAttribute(seq_scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     }
     const bool reject_live = D.single && tt == 0;
@@ -1065,6 +1126,7 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
             seq_scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, 0, rej);
         } else {
             CS_CUDA(cudaMemsetAsync(D.icnt, 0, sizeof(int) * ((size_t)D.N + 1), st));
+            CS_CUDA(cudaMemsetAsync(D.nd, 0x7f, sizeof(int) * (size_t)D.N, st));
             index_count_kernel<<<nsm * 8, 256, 0, st>>>(D);
             index_scan_kernel<<<1, 1024, 0, st>>>(D);
             index_fill_kernel<<<nsm * 8, 256, 0, st>>>(D);
