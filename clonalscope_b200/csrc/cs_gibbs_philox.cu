@@ -324,14 +324,15 @@ __device__ __forceinline__ int draw_cell_thread(const double *Qc, const double *
 // that bracket it, minus a rounding allowance (the sums have at most 33 non-negative terms:
 // their floating-point error is below 1e-14 * total; 1e-12 is charged).  An event that moves
 // one cell from slot a to slot b moves every sum and t by at most E[a] + E[b].
-__device__ __forceinline__ int draw_cell_fast32(const double *Ec, size_t stride, int nlive, const double *s_npd,
-                                                const double *s_npd1, int zold, double w_new, double ua,
-                                                double *s_cum, double *margin)
+template <int KMAX>
+__device__ __forceinline__ int draw_cell_fast(const double *Ec, size_t stride, int nlive, const double *s_npd,
+                                              const double *s_npd1, int zold, double w_new, double ua,
+                                              double *s_cum, double *margin)
 {
     unsigned pos = 0;
     double run = 0.0;
 #pragma unroll
-    for (int s = 0; s < 32; s++) {
+    for (int s = 0; s < KMAX; s++) {
         if (s < nlive) {
             const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
             const double w = __dmul_rn(nd, Ec[(size_t)s * stride]);
@@ -344,7 +345,7 @@ __device__ __forceinline__ int draw_cell_fast32(const double *Ec, size_t stride,
     const double t = __dmul_rn(ua, tot);
     unsigned le = 0; // cumulative sums are non-decreasing: those <= t form a prefix
 #pragma unroll
-    for (int s = 0; s < 32; s++)
+    for (int s = 0; s < KMAX; s++)
         if (s < nlive && !(s_cum[s * WIN_CELLS] > t)) le |= 1u << s;
     const int k = __popc(le); // first slot whose cumulative sum exceeds t (it has positive weight)
     int z;
@@ -527,7 +528,8 @@ scan_kernel(ChainDev D, int tt)
     int *s_np = reinterpret_cast<int *>(s_cum + 32 * WIN_CELLS);
     int *s_label = s_np + D.kcap;
     int *s_np0 = s_label + D.kcap;            // counts at the start of the sweep
-    __shared__ int s_nlive, s_kt, s_err, s_first, s_inval, s_z, s_zold, s_e0, s_e1, s_stop;
+    __shared__ int s_nlive, s_kt, s_err, s_first, s_inval, s_stop;
+    __shared__ int s_cz[WIN_CELLS], s_czold[WIN_CELLS], s_ce0[WIN_CELLS], s_ce1[WIN_CELLS], s_cnd[WIN_CELLS]; // per candidate
     __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV];
     __shared__ long long s_scanned, s_events;
 
@@ -560,7 +562,7 @@ scan_kernel(ChainDev D, int tt)
         const int c = pos + threadIdx.x;
         const bool active = threadIdx.x < W && c < D.N;
         const int nlive = s_nlive;
-        int z = -1, zold = -1, e0 = 0, e1 = 0;
+        int z = -1, zold = -1;
         double margin = 0.0; // what this draw tolerates before it has to be redone
         if (active) {
             zold = D.Zs[c];
@@ -583,13 +585,20 @@ scan_kernel(ChainDev D, int tt)
                     D.wn_q[c] = qi;
                     D.wn_w[c] = w_new;
                 }
-                z = draw_cell_fast32(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, s_cum + threadIdx.x, &margin);
+                double *cum = s_cum + threadIdx.x;
+                if (nlive <= 8) z = draw_cell_fast<8>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
+                else if (nlive <= 16) z = draw_cell_fast<16>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
+                else if (nlive <= 24) z = draw_cell_fast<24>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
+                else z = draw_cell_fast<32>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
             } else {
                 z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, s_np, zold, q_new, qmin, D.beta, ua);
             }
-            if (z != zold) {
-                e0 = D.icnt[c]; // dependents' range, fetched while the window is being reduced
-                e1 = D.icnt[c + 1];
+            if (z != zold) { // an event candidate leaves what its commit needs where all threads can read it
+                s_cz[threadIdx.x] = z;
+                s_czold[threadIdx.x] = zold;
+                s_ce0[threadIdx.x] = D.icnt[c];     // range of its dependents in the inverse index
+                s_ce1[threadIdx.x] = D.icnt[c + 1];
+                s_cnd[threadIdx.x] = D.nd[c];       // nearest later cell whose proposal copies it
             }
         }
         // ---- commit events in order for as long as the draws behind them provably still hold
@@ -610,15 +619,8 @@ scan_kernel(ChainDev D, int tt)
             __syncthreads();
             const int f = s_first, v = min(s_inval, limit);
             if (f == INT_MAX || f >= v) break; // nothing (more) that can be committed in this round
-            if (c == f) {
-                s_z = z;
-                s_zold = zold;
-                s_e0 = e0;
-                s_e1 = e1;
-            }
-            __syncthreads();
             // the event at cell f moves it from slot a to slot b
-            const int a = s_zold, b = s_z;
+            const int a = s_czold[f - pos], b = s_cz[f - pos];
             const bool opens = (b == s_nlive);
             if (opens) { // :209-212 open a new cluster with the proposed per-segment states
                 if (b >= D.kcap) {
@@ -655,8 +657,8 @@ scan_kernel(ChainDev D, int tt)
                 s_ev_f[nev] = f;
                 s_ev_a[nev] = a;
                 s_ev_b[nev] = b;
-                s_ev_e0[nev] = s_e0;
-                s_ev_e1[nev] = s_e1;
+                s_ev_e0[nev] = s_ce0[f - pos];
+                s_ev_e1[nev] = s_ce1[f - pos];
                 // a changed candidate set or a new cluster invalidates the cached draws of the
                 // window wholesale: stop batching, the next round re-draws everything
                 s_stop = (opens || cand || nev + 1 == MAX_EV) ? 1 : 0;
@@ -668,7 +670,7 @@ scan_kernel(ChainDev D, int tt)
             opened = opens;
             // cells whose proposal copied cell f have a corrected distance coming: from the nearest
             // of them on, this round's draws are void
-            limit = min(limit, __ldg(D.nd + f));
+            limit = min(limit, s_cnd[f - pos]);
             // every sum and threshold of the cells behind f moves by at most E[a] + E[b]
             if (active && c > f && !opens)
                 margin -= (D.E[(size_t)a * N + c] + D.E[(size_t)b * N + c]) * 1.000000001;
@@ -677,15 +679,24 @@ scan_kernel(ChainDev D, int tt)
         }
         if (s_err) break;
         // ---- proposals that copied a moved cell's cluster state: correct their distance exactly
-        for (int i = 0; i < nev; i++) {
-            const int f = s_ev_f[i], e1s = s_ev_e1[i];
-            const double *ua_row = D.U + (size_t)s_ev_a[i] * D.R, *ub_row = D.U + (size_t)s_ev_b[i] * D.R;
-            for (int e = s_ev_e0[i] + threadIdx.x; e < e1s; e += WIN_THREADS) {
+        // (the lists of all events of the round are walked as one range, so their loads overlap)
+        {
+            int tot_e = 0;
+            for (int i = 0; i < nev; i++) tot_e += s_ev_e1[i] - s_ev_e0[i];
+            for (int g = threadIdx.x; g < tot_e; g += WIN_THREADS) {
+                int i = 0, e = g;
+                while (e >= s_ev_e1[i] - s_ev_e0[i]) {
+                    e -= s_ev_e1[i] - s_ev_e0[i];
+                    i++;
+                }
+                e += s_ev_e0[i];
+                const int f = s_ev_f[i];
                 const unsigned cr = D.inv[e];
                 const double xv = D.inv_x[e];
                 const int cc = (int)(cr >> 10), r = (int)(cr & 1023u);
                 if (cc > f && !cs_isna(xv)) {
-                    const long long d = tint(xv, ub_row[r], s_isig16[r]) - tint(xv, ua_row[r], s_isig16[r]);
+                    const long long d = tint(xv, D.U[(size_t)s_ev_b[i] * D.R + r], s_isig16[r]) -
+                                        tint(xv, D.U[(size_t)s_ev_a[i] * D.R + r], s_isig16[r]);
                     if (d) atomicAdd(reinterpret_cast<unsigned long long *>(D.qnew_i + cc), (unsigned long long)d);
                 }
             }

@@ -25,7 +25,7 @@ for t in range(niter):
     sc, ev, rj = C.c_int64(), C.c_int64(), C.c_int64()
     L.cs_chain_stats(ch, C.byref(sc), C.byref(ev), C.byref(rj))
     print(f"sweep {t:3d}: run {ms[0].value:8.2f} ms  prepare {ms[1].value:6.2f}  scan {ms[2].value:8.2f}  eos {ms[3].value:6.2f}"
-          f" | events {ev.value - pe:6d} scanned {sc.value - ps:7d} slow {rj.value}")
+          f" | events {ev.value - pe:6d} rounds {((sc.value - ps) >> 40) & 0xfff:5d} empty {(sc.value - ps) >> 52:4d}")
     pe, ps = ev.value, sc.value
 kt = np.zeros(niter, dtype=np.int32)
 Zall = np.zeros((niter, N), dtype=np.int32, order="F")
