@@ -890,21 +890,28 @@ stats_partial_kernel(ChainDev D, int smem_doubles)
             cnt[e] = 0;
         }
         __syncthreads();
-        for (int i = i0; i < i1; i++) {
-            const int s = D.Zs[i] - t0;
-            if (s < 0 || s >= ns) continue;
-            const double *x = D.X + (size_t)i * R;
-            for (int r = threadIdx.x; r < R; r += blockDim.x) {
-                const double v = x[r];
-                if (!cs_isna(v)) {
-                    acc[s * R + r] += v;
-                    cnt[s * R + r] += 1;
+        // a thread owns segment r: cells in order (fixed summation order), 8 loads in flight
+        for (int r = threadIdx.x; r < R; r += blockDim.x) {
+            for (int i = i0; i < i1; i += 8) {
+                int sl[8];
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    sl[u] = (i + u < i1) ? D.Zs[i + u] - t0 : -1;
+                    v[u] = (i + u < i1) ? D.X[(size_t)(i + u) * R + r] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (sl[u] >= 0 && sl[u] < ns && !cs_isna(v[u])) {
+                        acc[sl[u] * R + r] += v[u];
+                        cnt[sl[u] * R + r] += 1;
+                    }
                 }
             }
         }
         __syncthreads();
         for (int e = threadIdx.x; e < ns * R; e += blockDim.x) {
-            const size_t o = ((size_t)blockIdx.x * D.kcap + t0) * R + e;
+            const size_t o = ((size_t)blockIdx.x * nlive + t0) * R + e; // partials are packed by nlive
             D.psum[o] = acc[e];
             D.pcnt[o] = cnt[e];
         }
@@ -920,7 +927,7 @@ __global__ void stats_final_kernel(ChainDev D, int nchunks)
     double s = 0.0;
     long long c = 0;
     for (int ch = 0; ch < nchunks; ch++) {
-        const size_t o = (size_t)ch * D.kcap * D.R + e;
+        const size_t o = (size_t)ch * nlive * D.R + e;
         s += D.psum[o];
         c += D.pcnt[o];
     }
@@ -971,32 +978,55 @@ sigma_partial_kernel(ChainDev D)
     for (int r = threadIdx.x; r < D.R; r += blockDim.x) {
         double s = 0.0;
         int c = 0;
-        for (int i = i0; i < i1; i++) {
-            const double x = D.X[(size_t)i * D.R + r];
-            if (cs_isna(x)) continue;
-            c++;
-            const double d = x - D.U[(size_t)D.Zs[i] * D.R + r];
-            if (!cs_isna(d)) s = __fma_rn(d, d, s);
+        for (int i = i0; i < i1; i += 8) { // cells in order, 8 (x, u) pairs in flight
+            double x[8], u[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const bool ok = i + k < i1;
+                x[k] = ok ? D.X[(size_t)(i + k) * D.R + r] : NAN;
+                u[k] = ok ? D.U[(size_t)D.Zs[i + k] * D.R + r] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (cs_isna(x[k])) continue;
+                c++;
+                const double d = x[k] - u[k];
+                if (!cs_isna(d)) s = __fma_rn(d, d, s);
+            }
         }
         D.psum[(size_t)blockIdx.x * D.R + r] = s;
         D.pcnt[(size_t)blockIdx.x * D.R + r] = c;
     }
 }
 
-__global__ void sigma_final_kernel(ChainDev D, int nchunks, int tt)
+// sigma_r = sqrt(S_r / c_r) with S_r the squared residuals and c_r the non-NA count of segment
+// r (:234).  The total log-likelihood at the state just recorded (:245) follows from the same
+// sums: sum_i sum_r dnorm(x; u, sigma_r, log) = -sum_r [c_r (ln sqrt(2 pi) + ln sigma_r) +
+// S_r / (2 sigma_r^2)] — no second pass over the data.  One CTA; fixed summation order.
+__global__ void __launch_bounds__(256) sigma_final_kernel(ChainDev D, int nchunks, int tt)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= D.R) return;
-    double s = 0.0;
-    long long c = 0;
-    for (int ch = 0; ch < nchunks; ch++) {
-        s += D.psum[(size_t)ch * D.R + r];
-        c += D.pcnt[(size_t)ch * D.R + r];
+    __shared__ double s_ll[256];
+    double ll = 0.0;
+    for (int r = threadIdx.x; r < D.R; r += 256) {
+        double s = 0.0;
+        long long c = 0;
+        for (int ch = 0; ch < nchunks; ch++) {
+            s += D.psum[(size_t)ch * D.R + r];
+            c += D.pcnt[(size_t)ch * D.R + r];
+        }
+        const double sg = sqrt((1.0 / (double)c) * s);
+        D.sig[r] = sg;
+        D.isig[r] = 1.0 / sg;
+        D.sigma_all[(size_t)tt * D.R + r] = sg;
+        if (c > 0) ll -= (double)c * (CS_LN_SQRT_2PI + log(sg)) + 0.5 * s / (sg * sg);
     }
-    const double sg = sqrt((1.0 / (double)c) * s);
-    D.sig[r] = sg;
-    D.isig[r] = 1.0 / sg;
-    if (tt >= 0) D.sigma_all[(size_t)tt * D.R + r] = sg;
+    s_ll[threadIdx.x] = ll;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 256; i++) t += s_ll[i];
+        D.LL[tt] = t;
+    }
 }
 
 // total fixed-state log-likelihood (R/BayesNonparCluster.R:133,245): per-chunk partials
@@ -1176,9 +1206,7 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
     stats_final_kernel<<<(D.kcap * D.R + 255) / 256, 256, 0, st>>>(D, nchunks);
     redraw_kernel<<<D.kcap, 128, 0, st>>>(D, tt, last);
     sigma_partial_kernel<<<nchunks, 256, 0, st>>>(D);
-    sigma_final_kernel<<<(D.R + 127) / 128, 128, 0, st>>>(D, nchunks, tt);
-    ll_partial_kernel<<<nchunks, 256, 0, st>>>(D, D.U, D.Zs, D.sig);
-    ll_final_kernel<<<1, 32, 0, st>>>(D, nchunks, D.LL + tt);
+    sigma_final_kernel<<<1, 256, 0, st>>>(D, nchunks, tt);
     record_kernel<<<1, 256, 0, st>>>(D, tt);
     relabel_kernel<<<(D.N + 255) / 256, 256, 0, st>>>(D, tt);
     compact_kernel<<<1, 256, 0, st>>>(D, rej, D.single && tt == 0);
