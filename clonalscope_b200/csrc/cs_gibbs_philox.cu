@@ -445,7 +445,7 @@ __global__ void index_count_kernel(ChainDev D)
     const size_t n = (size_t)D.N * D.R;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
         const int j = D.J[e];
-        if (j >= 0) atomicAdd(&D.icnt[j], 1);
+        if (j >= 0 && (int)(e / (size_t)D.R) > j) atomicAdd(&D.icnt[j], 1); // only later cells are ever corrected
     }
 }
 
@@ -503,12 +503,12 @@ __global__ void index_fill_kernel(ChainDev D)
     const size_t n = (size_t)D.N * D.R;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
         const int j = D.J[e];
-        if (j >= 0) {
+        const int cc = (int)(e / (size_t)D.R);
+        if (j >= 0 && cc > j) {
             const int p = atomicAdd(&D.icur[j], 1);
-            const int cc = (int)(e / (size_t)D.R);
             D.inv[p] = ((unsigned)cc << 10) | (unsigned)(e % (size_t)D.R);
-            if (cc > j) atomicMin(&D.nd[j], cc); // nearest later cell whose proposal copies cell j
-            D.inv_x[p] = D.X[e]; // the value the correction needs rides along: one dependent load less
+            atomicMin(&D.nd[j], cc); // nearest later cell whose proposal copies cell j
+            D.inv_x[p] = D.X[e];     // the value the correction needs rides along: one dependent load less
         }
     }
 }
@@ -926,10 +926,20 @@ __global__ void stats_final_kernel(ChainDev D, int nchunks)
     if (e >= nlive * D.R) return;
     double s = 0.0;
     long long c = 0;
-    for (int ch = 0; ch < nchunks; ch++) {
-        const size_t o = (size_t)ch * nlive * D.R + e;
-        s += D.psum[o];
-        c += D.pcnt[o];
+    for (int ch = 0; ch < nchunks; ch += 8) { // chunks in order, 8 loads in flight
+        double ps[8];
+        int pc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const size_t o = (size_t)(ch + k) * nlive * D.R + e;
+            ps[k] = (ch + k < nchunks) ? D.psum[o] : 0.0;
+            pc[k] = (ch + k < nchunks) ? D.pcnt[o] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            s += ps[k];
+            c += pc[k];
+        }
     }
     D.mean[e] = c ? s / (double)c : 0.0;
 }
@@ -1010,9 +1020,19 @@ __global__ void __launch_bounds__(256) sigma_final_kernel(ChainDev D, int nchunk
     for (int r = threadIdx.x; r < D.R; r += 256) {
         double s = 0.0;
         long long c = 0;
-        for (int ch = 0; ch < nchunks; ch++) {
-            s += D.psum[(size_t)ch * D.R + r];
-            c += D.pcnt[(size_t)ch * D.R + r];
+        for (int ch = 0; ch < nchunks; ch += 8) { // chunks in order, 8 loads in flight
+            double ps[8];
+            int pc[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                ps[k] = (ch + k < nchunks) ? D.psum[(size_t)(ch + k) * D.R + r] : 0.0;
+                pc[k] = (ch + k < nchunks) ? D.pcnt[(size_t)(ch + k) * D.R + r] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                s += ps[k];
+                c += pc[k];
+            }
         }
         const double sg = sqrt((1.0 / (double)c) * s);
         D.sig[r] = sg;
