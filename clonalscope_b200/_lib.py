@@ -18,7 +18,7 @@ SYMBOLS = [
     "cs_bin_counts_begin", "cs_bin_counts_fetch", "cs_bin_counts_free",
     "cs_bin_plan_create", "cs_bin_plan_destroy", "cs_bin_plan_timing", "cs_bin_counts_dev",
     "cs_loglik_matrix", "cs_loglik_matrix_dev",
-    "cs_ncrp_gibbs", "cs_chain_create", "cs_chain_init", "cs_chain_run", "cs_chain_sync",
+    "cs_ncrp_gibbs", "cs_release_cached", "cs_chain_create", "cs_chain_init", "cs_chain_run", "cs_chain_sync",
     "cs_chain_sweeps_done", "cs_chain_timing", "cs_chain_stats", "cs_chain_fetch", "cs_chain_destroy",
     "cs_ncrp_gibbs_allele",
     "cs_majority_vote", "cs_majority_vote_dev",
@@ -57,5 +57,6 @@ def lib():
         L.cs_bin_counts_free.restype = None
         L.cs_bin_plan_destroy.restype = None
         L.cs_chain_destroy.restype = None
+        L.cs_release_cached.restype = None
         _LIB = L
     return _LIB

@@ -46,6 +46,8 @@ struct cs_chain {
 };
 
 static const int kDefaultKcapPhilox = 256, kDefaultLcapR = 4096;
+static thread_local cs_chain *g_cached = nullptr; // see cs_ncrp_gibbs
+static thread_local int g_cached_dev = -1;
 
 extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mode, cs_chain **out)
 {
@@ -375,15 +377,36 @@ extern "C" int cs_ncrp_gibbs(int N, int R, const double *X, int K0, const double
     if (opts) o = *opts;
     CS_REQUIRE(niter >= 1, "niter=%d must be >= 1", niter);
     if (o.device >= 0) CS_CUDA(cudaSetDevice(o.device));
-    cs_chain *c = nullptr;
     int kcap = o.kcap;
     if (kcap > 0 && kcap < K0) kcap = K0;
-    int rc = cs_chain_create(N, R, kcap, niter, o.rng_mode, &c);
-    if (rc) return rc;
-    struct Guard {
+    if (kcap <= 0) kcap = o.rng_mode == CS_RNG_PHILOX ? kDefaultKcapPhilox : kDefaultLcapR;
+    int dev = 0;
+    CS_CUDA(cudaGetDevice(&dev));
+    // the device buffers of one chain (~1.5 GB at 100k x 300) are kept between calls of the same
+    // shape: RunCovCluster calls the sampler up to ten times on same-sized inputs
+    cs_chain *c = g_cached;
+    g_cached = nullptr;
+    int rc;
+    if (!(c && g_cached_dev == dev && c->N == N && c->R == R && c->kcap == kcap && c->niter_cap == niter &&
+          c->rng_mode == o.rng_mode)) {
+        cs_chain_destroy(c);
+        c = nullptr;
+        if ((rc = cs_chain_create(N, R, kcap, niter, o.rng_mode, &c))) return rc;
+    }
+    struct Guard { // an error drops the chain; success hands it back to the cache
         cs_chain *c;
-        ~Guard() { cs_chain_destroy(c); }
-    } guard{c};
+        int dev;
+        bool ok = false;
+        ~Guard()
+        {
+            if (ok) {
+                g_cached = c;
+                g_cached_dev = dev;
+            } else {
+                cs_chain_destroy(c);
+            }
+        }
+    } guard{c, dev};
     if ((rc = cs_chain_init(c, X, K0, U0, Z0, sigmas0, alpha, beta, seed, o.flags))) return rc;
     if ((rc = cs_chain_run(c, niter, 1, 1))) return rc;
     if ((rc = cs_chain_fetch(c, Zall, sigma_all, LL, L0, kt_all, ucap_rows, u_off, u_labels, u_rows))) return rc;
@@ -397,5 +420,12 @@ extern "C" int cs_ncrp_gibbs(int N, int R, const double *X, int K0, const double
         rng_state_out[0] = h.mt_pos;
         CS_CUDA(cudaMemcpy(rng_state_out + 1, c->D.mt, sizeof(uint32_t) * 624, cudaMemcpyDeviceToHost));
     }
+    guard.ok = true;
     return CS_OK;
+}
+
+extern "C" void cs_release_cached(void)
+{
+    cs_chain_destroy(g_cached);
+    g_cached = nullptr;
 }

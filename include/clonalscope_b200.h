@@ -135,6 +135,10 @@ int cs_ncrp_gibbs(int N, int R, const double *X /* N x R col-major */,
                   int32_t *rng_state_out /* R mode: 625 ints = .Random.seed[-1] after the
                                             run; may be NULL */);
 
+/* cs_ncrp_gibbs keeps the device buffers of its last chain for a same-shaped next call
+ * (per host thread); this frees them. */
+void cs_release_cached(void);
+
 /* Device-resident chain (what bench.py times as `value`). */
 typedef struct cs_chain cs_chain;
 int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mode, cs_chain **c);
