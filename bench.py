@@ -34,6 +34,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "nCRP Gibbs cell-updates/sec at 100k cells x 300 segs; bin-count GB/s vs HBM"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+# captures (profiles/r1_scan_full.txt: sweep 12 of the bench workload; profiles/r1_prepare_full.txt)
+SCAN_TRAFFIC_BYTES = 24_330_752
+PREPARE_TRAFFIC_BYTES = 350_580_480
 
 
 def peaks():
@@ -230,7 +234,7 @@ def run_ours(a):
         assert rc == 0, L.cs_last_error()
         rc = L.cs_chain_run(chain, niter, 1, 1)
         assert rc == 0, L.cs_last_error()
-        ms = [C.c_double() for _ in range(4)]
+        ms = [C.c_double() for _ in range(5)]
         rc = L.cs_chain_timing(chain, *[C.byref(m) for m in ms])
         assert rc == 0, L.cs_last_error()
         return [m.value for m in ms]
@@ -369,9 +373,9 @@ def run_ours(a):
                    binning_sample=f"sparse restatement, {nb3} cells, 1 core")
 
     if rank == 0:
-        prep_ms = prof[1] / niter
-        alg_bytes = N * R * 8
-        ach = alg_bytes / (prep_ms * 1e-3) / 1e9
+        scan_ms = prof[3] / niter  # dominant kernel of the step: the one-CTA sequential commit
+        alg_bytes = N * R * 8      # S*8 bytes per cell-update, N cell-updates per launch
+        ach = alg_bytes / (scan_ms * 1e-3) / 1e9
         line = dict(
             metric=METRIC, value=value, unit="cell-updates/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
             ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
@@ -381,11 +385,16 @@ def run_ours(a):
                         step="one full chain of niter sweeps", l2="per-sweep working set (X 240 MB + Q + J) exceeds the 126 MB L2",
                         binning=f"{NB} cells x {G} genes -> {B} bins per GPU"),
             e2e=e2e, gpu_launches=int(a.steps * niter * 13),
-            roofline=dict(bound="hbm", kernel="prepare_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
-                          frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
-                          note="latency/FP64-issue bound sweep: algorithmic bytes are only N*S*8 per launch",
-                          ms_per_launch=prep_ms, share_of_step=prof[1] / max(prof[0], 1e-9)),
-            sweep_split_ms=dict(run=prof[0], prepare=prof[1], scan=prof[2], end_of_sweep=prof[3]),
+            roofline=dict(bound="hbm", kernel="scan_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
+                          frac=ach / hbm_peak, traffic=SCAN_TRAFFIC_BYTES, peak_source=peak_src,
+                          note="latency-bound sequential commit (one CTA by contract of the sweep order): "
+                               "algorithmic bytes are N*S*8 per launch, the kernel itself touches far less",
+                          ms_per_launch=scan_ms, share_of_step=prof[3] / max(prof[0], 1e-9),
+                          prepare_kernel=dict(ms_per_launch=prof[1] / niter,
+                                              achieved=alg_bytes / (prof[1] / niter * 1e-3) / 1e9,
+                                              frac=alg_bytes / (prof[1] / niter * 1e-3) / 1e9 / hbm_peak,
+                                              traffic=PREPARE_TRAFFIC_BYTES)),
+            sweep_split_ms=dict(run=prof[0], prepare=prof[1], index=prof[2], scan=prof[3], end_of_sweep=prof[4]),
             scan=dict(cells_scanned=int(sc.value), events=int(ev.value)),
             binning=binning, clocks=clocks)
         if cpu:

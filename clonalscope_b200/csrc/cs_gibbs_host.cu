@@ -242,7 +242,7 @@ extern "C" int cs_chain_run(cs_chain *c, int nsweeps, int is_last, int sync)
     int rc = CS_OK;
     const bool prof = (c->flags & 2) != 0 && c->rng_mode == CS_RNG_PHILOX;
     if (prof) {
-        while ((int)c->sweep_ev.size() < 4 * nsweeps) {
+        while ((int)c->sweep_ev.size() < 5 * nsweeps) {
             cudaEvent_t e;
             CS_CUDA(cudaEventCreate(&e));
             c->sweep_ev.push_back(e);
@@ -255,7 +255,7 @@ extern "C" int cs_chain_run(cs_chain *c, int nsweeps, int is_last, int sync)
     } else {
         for (int tt = t0; tt < t1 && rc == CS_OK; tt++) {
             rc = cs_philox_sweep(c->D, tt, is_last && tt == t1 - 1, c->flags & 1, c->rej.p, c->st,
-                                 prof ? &c->sweep_ev[4 * (size_t)(tt - t0)] : nullptr);
+                                 prof ? &c->sweep_ev[5 * (size_t)(tt - t0)] : nullptr);
             double *t = c->D.U;
             c->D.U = c->D.Unext;
             c->D.Unext = t;
@@ -291,7 +291,8 @@ extern "C" int cs_chain_sync(cs_chain *c)
 
 extern "C" int cs_chain_sweeps_done(cs_chain *c) { return c ? c->sweeps_done : -1; }
 
-extern "C" int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *scan_ms, double *eos_ms)
+extern "C" int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *index_ms, double *scan_ms,
+                               double *eos_ms)
 {
     CS_REQUIRE(c != nullptr, "cs_chain_timing: NULL chain");
     CS_CUDA(cudaStreamSynchronize(c->st));
@@ -300,17 +301,27 @@ extern "C" int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, 
         CS_CUDA(cudaEventElapsedTime(&ms, c->run_ev[0], c->run_ev[1]));
         *run_ms = ms;
     }
-    double a = 0, b = 0, d = 0;
+    double a = 0, ix = 0, b = 0, d = 0;
     for (int s = 0; s < c->prof_sweeps; s++) {
-        cudaEvent_t *e = &c->sweep_ev[4 * (size_t)s];
+        cudaEvent_t *e = &c->sweep_ev[5 * (size_t)s];
         CS_CUDA(cudaEventElapsedTime(&ms, e[0], e[1]));
         a += ms;
-        CS_CUDA(cudaEventElapsedTime(&ms, e[1], e[2]));
-        b += ms;
+        // the sequential kernel (test hook, first sweep of a single-cluster start) builds no index
+        const bool has_index = !(c->flags & 1) && !(c->D.single && c->sweeps_done - c->prof_sweeps + s == 0);
+        if (has_index) {
+            CS_CUDA(cudaEventElapsedTime(&ms, e[1], e[4]));
+            ix += ms;
+            CS_CUDA(cudaEventElapsedTime(&ms, e[4], e[2]));
+            b += ms;
+        } else {
+            CS_CUDA(cudaEventElapsedTime(&ms, e[1], e[2]));
+            b += ms;
+        }
         CS_CUDA(cudaEventElapsedTime(&ms, e[2], e[3]));
         d += ms;
     }
     if (prepare_ms) *prepare_ms = a;
+    if (index_ms) *index_ms = ix;
     if (scan_ms) *scan_ms = b;
     if (eos_ms) *eos_ms = d;
     return CS_OK;

@@ -1191,6 +1191,7 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
             index_count_kernel<<<nsm * 8, 256, 0, st>>>(D);
             index_scan_kernel<<<1, 1024, 0, st>>>(D);
             index_fill_kernel<<<nsm * 8, 256, 0, st>>>(D);
+            if (ev) CS_CUDA(cudaEventRecord(ev[4], st));
             scan_kernel<NCH><<<1, WIN_THREADS, smem_scan, st>>>(D, tt);
         }
     }

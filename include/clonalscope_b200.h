@@ -151,9 +151,10 @@ int cs_chain_run(cs_chain *c, int nsweeps, int is_last, int sync);
 int cs_chain_sync(cs_chain *c);
 int cs_chain_sweeps_done(cs_chain *c);
 /* device time of the last cs_chain_run (CUDA events on the chain's stream); with init flag
- * bit 1 set also the per-sweep totals of the prepare kernel, the scan kernel and the
- * end-of-sweep kernels.  Synchronises the chain. */
-int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *scan_ms, double *eos_ms);
+ * bit 1 set also the per-sweep totals of the prepare kernel, the inverse-index kernels, the
+ * scan kernel and the end-of-sweep kernels.  Synchronises the chain. */
+int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *index_ms, double *scan_ms,
+                    double *eos_ms);
 /* number of cells the sequential scan kernel had to process (diagnostics) */
 int cs_chain_stats(cs_chain *c, int64_t *cells_scanned, int64_t *n_events, int64_t *n_reject);
 int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double *LL, double *L0,

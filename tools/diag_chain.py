@@ -20,12 +20,12 @@ assert L.cs_chain_init(ch, dp(X, C.c_double), 2, dp(U0, C.c_double), dp(Z0, C.c_
 pe = ps = 0
 for t in range(niter):
     assert L.cs_chain_run(ch, 1, int(t == niter - 1), 1) == 0, L.cs_last_error()
-    ms = [C.c_double() for _ in range(4)]
+    ms = [C.c_double() for _ in range(5)]
     L.cs_chain_timing(ch, *[C.byref(m) for m in ms])
     sc, ev, rj = C.c_int64(), C.c_int64(), C.c_int64()
     L.cs_chain_stats(ch, C.byref(sc), C.byref(ev), C.byref(rj))
-    print(f"sweep {t:3d}: run {ms[0].value:8.2f} ms  prepare {ms[1].value:6.2f}  scan {ms[2].value:8.2f}  eos {ms[3].value:6.2f}"
-          f" | events {ev.value - pe:6d} rounds {((sc.value - ps) >> 40) & 0xfff:5d} empty {(sc.value - ps) >> 52:4d}")
+    print(f"sweep {t:3d}: run {ms[0].value:8.2f} ms  prepare {ms[1].value:6.2f}  index {ms[2].value:6.2f}  scan {ms[3].value:8.2f}  eos {ms[4].value:6.2f}"
+          f" | events {ev.value - pe:6d}")
     pe, ps = ev.value, sc.value
 kt = np.zeros(niter, dtype=np.int32)
 Zall = np.zeros((niter, N), dtype=np.int32, order="F")
