@@ -238,7 +238,7 @@ def _ari(a, b):
     return adjusted_rand_score(a, b)
 
 
-@pytest.mark.parametrize("name,niter", [("P5931", 200), ("P5931_updated1", 200), ("BC_ductal2", 200 if FULL else 30),
+@pytest.mark.parametrize("name,niter", [("P5931", 200), ("P5931_updated1", 200), ("BC_ductal2", 200),
                                         ("P5847_tumor", 200 if FULL else 25),
                                         ("P5847_allcells", 200 if FULL else 12)])
 def test_sampler_r_mode_reproduces_reference_outputs(cs, name, niter):
