@@ -639,9 +639,6 @@ scan_kernel(ChainDev D, int tt)
             if (threadIdx.x == 0) {
                 const int na0 = s_np[a], nb0 = opens ? 0 : s_np[b];
                 const int na = na0 - 1, nb = nb0 + 1;
-                // does the set of candidates (np >= 1; np >= 2 for a cell's own cluster) change?
-                const bool cand = ((na0 >= 1) != (na >= 1)) || ((na0 >= 2) != (na >= 2)) ||
-                                  ((nb0 >= 1) != (nb >= 1)) || ((nb0 >= 2) != (nb >= 2));
                 s_np[a] = na;
                 s_npd[a] = na > 0 ? (double)na : 0.0;
                 s_npd1[a] = na > 1 ? (double)(na - 1) : 0.0;
@@ -659,9 +656,12 @@ scan_kernel(ChainDev D, int tt)
                 s_ev_b[nev] = b;
                 s_ev_e0[nev] = s_ce0[f - pos];
                 s_ev_e1[nev] = s_ce1[f - pos];
-                // a changed candidate set or a new cluster invalidates the cached draws of the
-                // window wholesale: stop batching, the next round re-draws everything
-                s_stop = (opens || cand || nev + 1 == MAX_EV) ? 1 : 0;
+                // A cluster that stops (or starts) being a candidate for some cell needs no special
+                // case: its weight n * E[.] changes by at most E[.], which the margins are charged
+                // with below, and re-referencing the exponentials to another minimum rescales all
+                // weights of a cell by one factor (relative effect ~1e-15, inside the allowance).
+                // A new cluster adds a column the window has not scored: the round ends there.
+                s_stop = (opens || nev + 1 == MAX_EV) ? 1 : 0;
                 s_first = INT_MAX;
                 s_inval = INT_MAX;
             }
