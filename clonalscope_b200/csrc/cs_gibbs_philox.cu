@@ -44,9 +44,10 @@ namespace {
 constexpr int PREP_THREADS = 256;
 constexpr int SCAN_THREADS = 1024;  // sequential kernel: one warp per cell
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
-constexpr int WIN_THREADS = 512;    // windowed kernel: one thread per cell of the window;
-constexpr int WIN_MIN = 128;        // the window grows 128 -> 512 cells while rounds find no event
-constexpr int WIN_CELLS = WIN_THREADS; // and shrinks again when they are cut short
+constexpr int WIN_THREADS = 512;    // windowed kernel: one thread per cell of the window (the upper
+                                    // half only helps with corrections and new columns);
+constexpr int WIN_MIN = 128;        // the window grows 128 -> 256 cells while rounds find no event
+constexpr int WIN_CELLS = 256;      // and shrinks again when they are cut short
 constexpr double Q_SCALE = 1.0 / 4294967296.0;
 
 template <int NCH>
@@ -327,7 +328,7 @@ __device__ __forceinline__ int draw_cell_thread(const double *Qc, const double *
 template <int KMAX>
 __device__ __forceinline__ int draw_cell_fast(const double *Ec, size_t stride, int nlive, const double *s_npd,
                                               const double *s_npd1, int zold, double w_new, double ua,
-                                              double *s_cum, double *margin)
+                                              double *s_cum, double *s_e, double *margin)
 {
     unsigned pos = 0;
     double run = 0.0;
@@ -335,7 +336,9 @@ __device__ __forceinline__ int draw_cell_fast(const double *Ec, size_t stride, i
     for (int s = 0; s < KMAX; s++) {
         if (s < nlive) {
             const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
-            const double w = __dmul_rn(nd, Ec[(size_t)s * stride]);
+            const double e = Ec[(size_t)s * stride];
+            s_e[s * WIN_CELLS] = e; // the margins are charged with these while events are committed
+            const double w = __dmul_rn(nd, e);
             run = __dadd_rn(run, w);
             s_cum[s * WIN_CELLS] = run;
             if (w > 0.0) pos |= 1u << s;
@@ -525,10 +528,11 @@ scan_kernel(ChainDev D, int tt)
     double *s_npd = s_dyn + D.R;              // kcap : (double) np[s]      (0 when np <= 0)
     double *s_npd1 = s_npd + D.kcap;          // kcap : (double)(np[s] - 1) (0 when np <= 1)
     double *s_cum = s_npd1 + D.kcap;          // 32 x WIN_CELLS cumulative sums of the fast draw
-    int *s_np = reinterpret_cast<int *>(s_cum + 32 * WIN_CELLS);
+    double *s_e = s_cum + 32 * WIN_CELLS;     // 32 x WIN_CELLS exponentials of the window's cells
+    int *s_np = reinterpret_cast<int *>(s_e + 32 * WIN_CELLS);
     int *s_label = s_np + D.kcap;
     int *s_np0 = s_label + D.kcap;            // counts at the start of the sweep
-    __shared__ int s_nlive, s_kt, s_err, s_first, s_inval, s_stop;
+    __shared__ int s_nlive, s_kt, s_err, s_first[3], s_inval[3];
     __shared__ int s_cz[WIN_CELLS], s_czold[WIN_CELLS], s_ce0[WIN_CELLS], s_ce1[WIN_CELLS], s_cnd[WIN_CELLS]; // per candidate
     __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV];
     __shared__ long long s_scanned, s_events;
@@ -548,15 +552,14 @@ scan_kernel(ChainDev D, int tt)
         s_nlive = D.scal->nlive;
         s_kt = D.scal->kt;
         s_err = 0;
-        s_first = INT_MAX;
-        s_inval = INT_MAX;
+        for (int k = 0; k < 3; k++) s_first[k] = s_inval[k] = INT_MAX;
         s_scanned = 0;
         s_events = 0;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t N = (size_t)D.N;
-    int pos = f0, W = WIN_MIN;
+    int pos = f0, W = WIN_MIN, gi = 0;
     while (pos < D.N) {
         // ---- every cell of the window is re-drawn exactly against the committed state
         const int c = pos + threadIdx.x;
@@ -576,7 +579,9 @@ scan_kernel(ChainDev D, int tt)
             // opened this sweep clear kmin themselves; the cell's own cluster joins the candidates
             // when it stops being a singleton)
             const int km = D.kmin[c];
-            bool fast = nlive <= 32 && km != 255 && q_new >= qmin && s_np[km] - (km == zold ? 1 : 0) > 0;
+            // (when only the proposal attained the cached minimum, it must still sit exactly there)
+            bool fast = nlive <= 32 &&
+                        (km != 255 ? (q_new >= qmin && s_np[km] - (km == zold ? 1 : 0) > 0) : q_new == qmin);
             if (fast && s_np0[zold] < 2 && s_np[zold] >= 2 && D.Q[(size_t)zold * N + c] < qmin) fast = false;
             if (fast) {
                 double w_new = D.wn_w[c];
@@ -586,10 +591,10 @@ scan_kernel(ChainDev D, int tt)
                     D.wn_w[c] = w_new;
                 }
                 double *cum = s_cum + threadIdx.x;
-                if (nlive <= 8) z = draw_cell_fast<8>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
-                else if (nlive <= 16) z = draw_cell_fast<16>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
-                else if (nlive <= 24) z = draw_cell_fast<24>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
-                else z = draw_cell_fast<32>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, &margin);
+                if (nlive <= 8) z = draw_cell_fast<8>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, s_e + threadIdx.x, &margin);
+                else if (nlive <= 16) z = draw_cell_fast<16>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, s_e + threadIdx.x, &margin);
+                else if (nlive <= 24) z = draw_cell_fast<24>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, s_e + threadIdx.x, &margin);
+                else z = draw_cell_fast<32>(D.E + c, N, nlive, s_npd, s_npd1, zold, w_new, ua, cum, s_e + threadIdx.x, &margin);
             } else {
                 z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, s_np, zold, q_new, qmin, D.beta, ua);
             }
@@ -601,10 +606,14 @@ scan_kernel(ChainDev D, int tt)
                 s_cnd[threadIdx.x] = D.nd[c];       // nearest later cell whose proposal copies it
             }
         }
-        // ---- commit events in order for as long as the draws behind them provably still hold
-        int nev = 0, lo = pos, limit = min(D.N, pos + W);
+        // ---- commit events in order for as long as the draws behind them provably still hold.
+        // One barrier per event: the two minima are collected in a rotating triple of slots
+        // (slot (gi+2)%3 is reset right after iteration gi's barrier: its last readers are
+        // behind that barrier, its next writers beyond the next one), and the bookkeeping of a
+        // commit is spread over four threads whose writes the next barrier publishes.
+        int nev = 0, lo = pos, limit = min(D.N, pos + W), nl = nlive;
         bool opened = false;
-        for (;;) {
+        for (;; gi++) {
             int mc = INT_MAX, mv = INT_MAX;
             if (active && c >= lo) {
                 if (z != zold) mc = c;
@@ -613,15 +622,22 @@ scan_kernel(ChainDev D, int tt)
             mc = __reduce_min_sync(CS_FULL, mc);
             mv = __reduce_min_sync(CS_FULL, mv);
             if (lane == 0) {
-                if (mc != INT_MAX) atomicMin(&s_first, mc);
-                if (mv != INT_MAX) atomicMin(&s_inval, mv);
+                if (mc != INT_MAX) atomicMin(&s_first[gi % 3], mc);
+                if (mv != INT_MAX) atomicMin(&s_inval[gi % 3], mv);
             }
             __syncthreads();
-            const int f = s_first, v = min(s_inval, limit);
-            if (f == INT_MAX || f >= v) break; // nothing (more) that can be committed in this round
+            const int f = s_first[gi % 3], v = min(s_inval[gi % 3], limit);
+            if (threadIdx.x == 0) {
+                s_first[(gi + 2) % 3] = INT_MAX;
+                s_inval[(gi + 2) % 3] = INT_MAX;
+            }
+            if (f == INT_MAX || f >= v) { // nothing (more) that can be committed in this round
+                gi++;
+                break;
+            }
             // the event at cell f moves it from slot a to slot b
             const int a = s_czold[f - pos], b = s_cz[f - pos];
-            const bool opens = (b == s_nlive);
+            const bool opens = (b == nl);
             if (opens) { // :209-212 open a new cluster with the proposed per-segment states
                 if (b >= D.kcap) {
                     if (threadIdx.x == 0) s_err = CS_ERR_KCAP;
@@ -637,11 +653,12 @@ scan_kernel(ChainDev D, int tt)
                 if (s_err) break;
             }
             if (threadIdx.x == 0) {
-                const int na0 = s_np[a], nb0 = opens ? 0 : s_np[b];
-                const int na = na0 - 1, nb = nb0 + 1;
+                const int na = s_np[a] - 1;
                 s_np[a] = na;
                 s_npd[a] = na > 0 ? (double)na : 0.0;
                 s_npd1[a] = na > 1 ? (double)(na - 1) : 0.0;
+            } else if (threadIdx.x == 32) {
+                const int nb = opens ? 1 : s_np[b] + 1;
                 s_np[b] = nb;
                 s_npd[b] = (double)nb;
                 s_npd1[b] = nb > 1 ? (double)(nb - 1) : 0.0;
@@ -649,21 +666,15 @@ scan_kernel(ChainDev D, int tt)
                     s_label[b] = ++s_kt;
                     s_nlive = b + 1;
                 }
-                D.Zs[f] = b;
-                s_events += 1;
+            } else if (threadIdx.x == 64) {
                 s_ev_f[nev] = f;
                 s_ev_a[nev] = a;
                 s_ev_b[nev] = b;
                 s_ev_e0[nev] = s_ce0[f - pos];
                 s_ev_e1[nev] = s_ce1[f - pos];
-                // A cluster that stops (or starts) being a candidate for some cell needs no special
-                // case: its weight n * E[.] changes by at most E[.], which the margins are charged
-                // with below, and re-referencing the exponentials to another minimum rescales all
-                // weights of a cell by one factor (relative effect ~1e-15, inside the allowance).
-                // A new cluster adds a column the window has not scored: the round ends there.
-                s_stop = (opens || nev + 1 == MAX_EV) ? 1 : 0;
-                s_first = INT_MAX;
-                s_inval = INT_MAX;
+            } else if (threadIdx.x == 96) {
+                D.Zs[f] = b;
+                s_events += 1;
             }
             nev++;
             lo = f + 1;
@@ -671,12 +682,20 @@ scan_kernel(ChainDev D, int tt)
             // cells whose proposal copied cell f have a corrected distance coming: from the nearest
             // of them on, this round's draws are void
             limit = min(limit, s_cnd[f - pos]);
+            // A cluster that stops (or starts) being a candidate for some cell needs no special
+            // case: its weight n * E[.] changes by at most E[.], which the margins are charged
+            // with here, and re-referencing the exponentials to another minimum rescales all
+            // weights of a cell by one factor (relative effect ~1e-15, inside the allowance).
+            // A new cluster adds a column the window has not scored: the round ends there.
+            if (opens || nev == MAX_EV) {
+                gi++;
+                break;
+            }
             // every sum and threshold of the cells behind f moves by at most E[a] + E[b]
-            if (active && c > f && !opens)
-                margin -= (D.E[(size_t)a * N + c] + D.E[(size_t)b * N + c]) * 1.000000001;
-            __syncthreads();
-            if (s_stop) break;
+            if (active && c > f && margin > 0.0)
+                margin -= (s_e[a * WIN_CELLS + threadIdx.x] + s_e[b * WIN_CELLS + threadIdx.x]) * 1.000000001;
         }
+        __syncthreads(); // the commits above are visible from here on
         if (s_err) break;
         // ---- proposals that copied a moved cell's cluster state: correct their distance exactly
         // (the lists of all events of the round are walked as one range, so their loads overlap)
@@ -729,11 +748,7 @@ scan_kernel(ChainDev D, int tt)
                 }
             }
         }
-        if (threadIdx.x == 0) {
-            s_scanned += (nev ? lo - pos : min(W, D.N - pos));
-            s_first = INT_MAX;
-            s_inval = INT_MAX;
-        }
+        if (threadIdx.x == 0) s_scanned += (nev ? lo - pos : min(W, D.N - pos));
         __syncthreads(); // orders the corrections (L2 atomics) before the next window's .cg loads
         const int adv = nev ? lo - pos : W;
         pos += adv;
@@ -1166,7 +1181,7 @@ template <int NCH>
 int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cudaStream_t st, cudaEvent_t *ev)
 {
     const size_t smem_prep = sizeof(double) * D.R + sizeof(int) * D.kcap;
-    const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap + 32 * WIN_CELLS) + sizeof(int) * 3 * D.kcap + 16;
+    const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap + 64 * WIN_CELLS) + sizeof(int) * 3 * D.kcap + 16;
     CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     if (smem_scan > 48 * 1024) {
         CS_CUDA(cudaFuncSetAttribute(prepare_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
