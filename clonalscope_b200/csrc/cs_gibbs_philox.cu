@@ -517,7 +517,7 @@ __global__ void index_fill_kernel(ChainDev D)
 }
 
 // ---------------------------------------------------------------- scan (one CTA, thread per cell)
-constexpr int MAX_EV = 16; // events committed per window round
+constexpr int MAX_EV = 32; // events committed per window round
 
 template <int NCH>
 __global__ void __launch_bounds__(WIN_THREADS)
@@ -532,9 +532,9 @@ scan_kernel(ChainDev D, int tt)
     int *s_np = reinterpret_cast<int *>(s_e + 32 * WIN_CELLS);
     int *s_label = s_np + D.kcap;
     int *s_np0 = s_label + D.kcap;            // counts at the start of the sweep
-    __shared__ int s_nlive, s_kt, s_err, s_first[3], s_inval[3];
-    __shared__ int s_cz[WIN_CELLS], s_czold[WIN_CELLS], s_ce0[WIN_CELLS], s_ce1[WIN_CELLS], s_cnd[WIN_CELLS]; // per candidate
-    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV];
+    __shared__ int s_nlive, s_kt, s_err, s_block, s_wcnt[WIN_THREADS / 32];
+    // the round's event candidates in cell order: cell, old slot, new slot, dependents' range, nearest dependent
+    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV], s_ev_nd[MAX_EV];
     __shared__ long long s_scanned, s_events;
 
     const int f0 = D.scal->first_event;
@@ -552,14 +552,13 @@ scan_kernel(ChainDev D, int tt)
         s_nlive = D.scal->nlive;
         s_kt = D.scal->kt;
         s_err = 0;
-        for (int k = 0; k < 3; k++) s_first[k] = s_inval[k] = INT_MAX;
         s_scanned = 0;
         s_events = 0;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t N = (size_t)D.N;
-    int pos = f0, W = WIN_MIN, gi = 0;
+    int pos = f0, W = WIN_MIN;
     while (pos < D.N) {
         // ---- every cell of the window is re-drawn exactly against the committed state
         const int c = pos + threadIdx.x;
@@ -598,104 +597,100 @@ scan_kernel(ChainDev D, int tt)
             } else {
                 z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, s_np, zold, q_new, qmin, D.beta, ua);
             }
-            if (z != zold) { // an event candidate leaves what its commit needs where all threads can read it
-                s_cz[threadIdx.x] = z;
-                s_czold[threadIdx.x] = zold;
-                s_ce0[threadIdx.x] = D.icnt[c];     // range of its dependents in the inverse index
-                s_ce1[threadIdx.x] = D.icnt[c + 1];
-                s_cnd[threadIdx.x] = D.nd[c];       // nearest later cell whose proposal copies it
+        }
+        // ---- the window's event candidates, in cell order (ballot + prefix over the warps)
+        const bool cand = active && z != zold;
+        const unsigned bal = __ballot_sync(CS_FULL, cand);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int jc = __popc(bal & ((1u << lane) - 1u)), ncand = 0; // candidates in front of this cell
+        for (int w = 0; w < WIN_THREADS / 32; w++) {
+            const int cw = s_wcnt[w];
+            if (w < warp) jc += cw;
+            ncand += cw;
+        }
+        if (cand && jc < MAX_EV) { // what a commit needs, where all threads can read it
+            s_ev_f[jc] = c;
+            s_ev_a[jc] = zold;
+            s_ev_b[jc] = z;
+            s_ev_e0[jc] = D.icnt[c];     // range of its dependents in the inverse index
+            s_ev_e1[jc] = D.icnt[c + 1];
+            s_ev_nd[jc] = D.nd[c];       // nearest later cell whose proposal copies it
+        }
+        if (threadIdx.x == 0) s_block = INT_MAX;
+        __syncthreads();
+        // ---- how many of them can be committed in this round, in order, with every draw in front
+        // of each provably unchanged.  Candidate j is out when it lies behind the nearest cell
+        // whose proposal copied an earlier candidate of the round (that cell's distance is about
+        // to be corrected) or behind a candidate that opens a cluster (a column the window has not
+        // scored) ...
+        int K = min(ncand, MAX_EV);
+        {
+            int lim = min(D.N, pos + W);
+            for (int j = 0; j < K; j++) {
+                if (s_ev_f[j] >= lim) {
+                    K = j;
+                    break;
+                }
+                if (s_ev_b[j] == nlive) {
+                    K = j + 1;
+                    break;
+                }
+                lim = min(lim, s_ev_nd[j]);
             }
         }
-        // ---- commit events in order for as long as the draws behind them provably still hold.
-        // One barrier per event: the two minima are collected in a rotating triple of slots
-        // (slot (gi+2)%3 is reset right after iteration gi's barrier: its last readers are
-        // behind that barrier, its next writers beyond the next one), and the bookkeeping of a
-        // commit is spread over four threads whose writes the next barrier publishes.
-        int nev = 0, lo = pos, limit = min(D.N, pos + W), nl = nlive;
-        bool opened = false;
-        for (;; gi++) {
-            int mc = INT_MAX, mv = INT_MAX;
-            if (active && c >= lo) {
-                if (z != zold) mc = c;
-                if (nev > 0 && !(margin > 0.0)) mv = c;
-            }
-            mc = __reduce_min_sync(CS_FULL, mc);
-            mv = __reduce_min_sync(CS_FULL, mv);
-            if (lane == 0) {
-                if (mc != INT_MAX) atomicMin(&s_first[gi % 3], mc);
-                if (mv != INT_MAX) atomicMin(&s_inval[gi % 3], mv);
-            }
-            __syncthreads();
-            const int f = s_first[gi % 3], v = min(s_inval[gi % 3], limit);
-            if (threadIdx.x == 0) {
-                s_first[(gi + 2) % 3] = INT_MAX;
-                s_inval[(gi + 2) % 3] = INT_MAX;
-            }
-            if (f == INT_MAX || f >= v) { // nothing (more) that can be committed in this round
-                gi++;
-                break;
-            }
-            // the event at cell f moves it from slot a to slot b
-            const int a = s_czold[f - pos], b = s_cz[f - pos];
-            const bool opens = (b == nl);
-            if (opens) { // :209-212 open a new cluster with the proposed per-segment states
-                if (b >= D.kcap) {
-                    if (threadIdx.x == 0) s_err = CS_ERR_KCAP;
-                } else {
-                    double *urow = D.U + (size_t)b * D.R;
-                    const int *Jrow = D.J + (size_t)f * D.R;
-                    for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) {
-                        const int j = Jrow[r];
-                        urow[r] = (j >= 0) ? D.U[(size_t)D.Zs[j] * D.R + r] : fresh_state(D, f, r, tt, 0u);
-                    }
+        // ... or when a cell between the previous candidate and itself (itself included) runs out
+        // of margin: each of the jc events in front of a cell moves its sums and threshold by at
+        // most E[a] + E[b].  (A cluster that stops or starts being a candidate for some cell needs
+        // no special case: its weight n * E[.] changes by at most E[.], and re-referencing the
+        // exponentials to another minimum rescales all weights of a cell by one factor — relative
+        // effect ~1e-15, inside the allowance.)
+        if (active && jc >= 1 && jc < K) {
+            double m = margin;
+            for (int i = 0; i < jc && m > 0.0; i++)
+                m -= (s_e[s_ev_a[i] * WIN_CELLS + threadIdx.x] + s_e[s_ev_b[i] * WIN_CELLS + threadIdx.x]) * 1.000000001;
+            if (!(m > 0.0)) atomicMin(&s_block, jc);
+        }
+        __syncthreads();
+        K = min(K, s_block);
+        const int nev = K;
+        const bool opened = nev > 0 && s_ev_b[nev - 1] == nlive;
+        const int lo = nev ? s_ev_f[nev - 1] + 1 : pos;
+        // ---- commit them: counts (order-free integer updates), assignments
+        if (threadIdx.x < nev) {
+            atomicAdd(&s_np[s_ev_a[threadIdx.x]], -1);
+            if (s_ev_b[threadIdx.x] == nlive) s_np[nlive] = 1; // (a slot past the live ones may hold a stale count)
+            else atomicAdd(&s_np[s_ev_b[threadIdx.x]], 1);
+            D.Zs[s_ev_f[threadIdx.x]] = s_ev_b[threadIdx.x];
+        }
+        __syncthreads();
+        if (opened) { // :209-212 the last event opens a cluster with its proposed per-segment states
+            const int f = s_ev_f[nev - 1], b = nlive;
+            if (b >= D.kcap) {
+                if (threadIdx.x == 0) s_err = CS_ERR_KCAP;
+            } else {
+                // (its own assignment is not a source of its proposal: restore the old slot for the gather)
+                double *urow = D.U + (size_t)b * D.R;
+                const int *Jrow = D.J + (size_t)f * D.R;
+                const int a_f = s_ev_a[nev - 1];
+                for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) {
+                    const int j = Jrow[r];
+                    const int zs = (j == f) ? a_f : ((j >= 0) ? D.Zs[j] : 0);
+                    urow[r] = (j >= 0) ? D.U[(size_t)zs * D.R + r] : fresh_state(D, f, r, tt, 0u);
                 }
-                __syncthreads();
-                if (s_err) break;
-            }
-            if (threadIdx.x == 0) {
-                const int na = s_np[a] - 1;
-                s_np[a] = na;
-                s_npd[a] = na > 0 ? (double)na : 0.0;
-                s_npd1[a] = na > 1 ? (double)(na - 1) : 0.0;
-            } else if (threadIdx.x == 32) {
-                const int nb = opens ? 1 : s_np[b] + 1;
-                s_np[b] = nb;
-                s_npd[b] = (double)nb;
-                s_npd1[b] = nb > 1 ? (double)(nb - 1) : 0.0;
-                if (opens) {
+                if (threadIdx.x == 0) {
                     s_label[b] = ++s_kt;
                     s_nlive = b + 1;
                 }
-            } else if (threadIdx.x == 64) {
-                s_ev_f[nev] = f;
-                s_ev_a[nev] = a;
-                s_ev_b[nev] = b;
-                s_ev_e0[nev] = s_ce0[f - pos];
-                s_ev_e1[nev] = s_ce1[f - pos];
-            } else if (threadIdx.x == 96) {
-                D.Zs[f] = b;
-                s_events += 1;
             }
-            nev++;
-            lo = f + 1;
-            opened = opens;
-            // cells whose proposal copied cell f have a corrected distance coming: from the nearest
-            // of them on, this round's draws are void
-            limit = min(limit, s_cnd[f - pos]);
-            // A cluster that stops (or starts) being a candidate for some cell needs no special
-            // case: its weight n * E[.] changes by at most E[.], which the margins are charged
-            // with here, and re-referencing the exponentials to another minimum rescales all
-            // weights of a cell by one factor (relative effect ~1e-15, inside the allowance).
-            // A new cluster adds a column the window has not scored: the round ends there.
-            if (opens || nev == MAX_EV) {
-                gi++;
-                break;
-            }
-            // every sum and threshold of the cells behind f moves by at most E[a] + E[b]
-            if (active && c > f && margin > 0.0)
-                margin -= (s_e[a * WIN_CELLS + threadIdx.x] + s_e[b * WIN_CELLS + threadIdx.x]) * 1.000000001;
         }
-        __syncthreads(); // the commits above are visible from here on
+        for (int sl = threadIdx.x; sl <= nlive && sl < D.kcap; sl += WIN_THREADS) {
+            const int n = s_np[sl];
+            s_npd[sl] = n > 0 ? (double)n : 0.0;
+            s_npd1[sl] = n > 1 ? (double)(n - 1) : 0.0;
+        }
+        if (threadIdx.x == 0) s_events += nev;
+        __syncthreads();
         if (s_err) break;
         // ---- proposals that copied a moved cell's cluster state: correct their distance exactly
         // (the lists of all events of the round are walked as one range, so their loads overlap)

@@ -25,10 +25,10 @@ for t in range(niter):
     sc, ev, rj = C.c_int64(), C.c_int64(), C.c_int64()
     L.cs_chain_stats(ch, C.byref(sc), C.byref(ev), C.byref(rj))
     print(f"sweep {t:3d}: run {ms[0].value:8.2f} ms  prepare {ms[1].value:6.2f}  index {ms[2].value:6.2f}  scan {ms[3].value:8.2f}  eos {ms[4].value:6.2f}"
-          f" | events {ev.value - pe:6d}")
+          f" | events {ev.value - pe:6d}  scanned {sc.value - ps:8d}")
     pe, ps = ev.value, sc.value
 kt = np.zeros(niter, dtype=np.int32)
 Zall = np.zeros((niter, N), dtype=np.int32, order="F")
 uoff = np.zeros(niter + 1, dtype=np.int64)
 L.cs_chain_fetch(ch, dp(Zall, C.c_int), None, None, None, dp(kt, C.c_int), C.c_int64(0), None, None, None)
-print("kt:", list(kt))
+print("kt:", [int(k) for k in kt])
