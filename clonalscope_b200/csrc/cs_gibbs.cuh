@@ -11,7 +11,8 @@ struct ChainScal {
     int err;          // CS_ERR_* raised on the device
     int mt_pos;       // R mode: Mersenne-Twister position
     int prop_valid;   // R mode scratch
-    int pad0, pad1;
+    int open_cell;    // Philox ring scan: command to the helper CTAs (cell that opened a cluster, -1 = leave)
+    int open_slot;    //                    the slot it opened
     long long cells_scanned, n_events, n_reject, u_used;
 };
 
@@ -37,7 +38,7 @@ struct ChainDev {
     double *ua;       // N          uniform of the categorical draw of this sweep
     long long *wn_q;  // N          proposal distance the cached new-table weight was computed at
     double *wn_w;     // N          beta * exp(-0.5 (q_new - qmin)) at wn_q
-    unsigned char *kmin; // N       a live cluster attaining qmin (255: only the proposal does)
+    int *kmin;        // N          a live cluster attaining qmin (255: only the proposal does)
     int *J;           // N x R      proposal sources (cell index, -1 = fresh Uniform state)
     int *zspec;       // N          speculative draws
     int *qcols;       // N          (sequential kernel) valid columns of Q

@@ -25,8 +25,7 @@ struct cs_chain {
     DevBuf<double> X, Xc, Ua, Ub, sig, isig, Q, E, qmin, ua, inv_x, mean, psum, sigma_all, LL, u_rows, L0;
     DevBuf<long long> qnew_i, tile_sums, wn_q;
     DevBuf<double> wn_w;
-    DevBuf<unsigned char> kmin;
-    DevBuf<int> icnt, icur, nd;
+    DevBuf<int> kmin, icnt, icur, nd;
     DevBuf<unsigned> inv;
     DevBuf<int> Zs, np, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
     DevBuf<long long> u_off;
@@ -100,7 +99,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
         CS_CUDA(c->E.alloc((size_t)N * kcap));
         CS_CUDA(c->qmin.alloc(N));
         CS_CUDA(c->ua.alloc(N));
-        CS_CUDA(c->qnew_i.alloc(N));
+        CS_CUDA(c->qnew_i.alloc((size_t)N + 2)); // (+2: the ring scan copies it in aligned pairs)
         CS_CUDA(c->wn_q.alloc(N));
         CS_CUDA(c->wn_w.alloc(N));
         CS_CUDA(c->kmin.alloc(N));

@@ -37,7 +37,10 @@
 // the CPU oracle's Philox mode uses the same definition.
 #include "cs_gibbs.cuh"
 
+#include <cooperative_groups.h>
 #include <limits.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -431,7 +434,7 @@ prepare_kernel(ChainDev D, int tt, int *__restrict__ rej)
             D.qnew_i[c] = qn;
             D.qmin[c] = qmin;
             D.ua[c] = ua;
-            D.kmin[c] = (unsigned char)km;
+            D.kmin[c] = km;
             D.wn_q[c] = qn;
             D.wn_w[c] = __dmul_rn(D.beta, exp(-0.5 * (q_new - qmin)));
             if (z != zold && c < first) first = c;
@@ -734,7 +737,7 @@ scan_kernel(ChainDev D, int tt)
                     if (lane == 0) {
                         D.Q[(size_t)b * N + cc] = qd;
                         D.qmin[cc] = qd;
-                        D.kmin[cc] = (unsigned char)(b < 255 ? b : 255);
+                        D.kmin[cc] = b < 255 ? b : 255;
                         D.wn_q[cc] = LLONG_MIN; // the cached new-table weight used the old reference
                     }
                 } else if (lane == 0) {
@@ -761,6 +764,478 @@ scan_kernel(ChainDev D, int tt)
         D.scal->kt = s_kt;
         D.scal->cells_scanned += s_scanned;
         D.scal->n_events += s_events;
+        if (s_err) D.scal->err = s_err;
+    }
+}
+
+// ---------------------------------------------------------------- scan, resident window (one cluster of CTAs)
+// The same walk as scan_kernel for sweeps with at most 32 live clusters, with what a re-draw
+// needs kept in shared memory: a ring of RING cells (cached exponentials, proposal distance,
+// reference, uniform, old slot, dependents' range) is filled by asynchronous copies well ahead
+// of the window, so a round touches global memory only for the corrections it commits.
+//   * copies are issued at the end of a round and waited for in the middle of the next one;
+//     a window never reaches past what has landed (RING - WIN_CELLS cells of slack);
+//   * a correction of a proposal distance goes to global memory AND, for cells already
+//     copied, to the ring.  No copy is in flight while corrections are applied, and the
+//     distances are copied past L1 (16-byte .cg), so a later copy sees every correction;
+//   * opening a cluster rewrites cached columns of all later cells: the other CTAs of the
+//     cluster (parked at the cluster barrier in between) score the new column together with
+//     this one, then the ring is filled again (cluster.sync invalidates L1);
+//   * when a 33rd cluster opens the walk is handed to scan_kernel at that cell.
+constexpr int RING = 512;
+constexpr int RMASK = RING - 1;
+constexpr int RING_SLOTS = 32;
+
+__device__ __forceinline__ void cp_async_4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16_cg(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct RingSmem {
+    long long *qi, *wq;             // proposal distance (fixed point); the one the cached weight is for
+    double *w, *qmin, *ua, *e;      // cached new-table weight, reference, uniform, exponentials [slot][cell]
+    double *npd, *npd1, *isig16;
+    int *z, *km, *i0, *i1, *nd;     // old slot, cluster at the reference, dependents' range, nearest dependent
+    int *np, *label, *np0;
+};
+
+__device__ __forceinline__ RingSmem ring_carve(unsigned char *raw, int R, int kcap)
+{
+    RingSmem S;
+    S.qi = reinterpret_cast<long long *>(raw);
+    S.wq = S.qi + RING;
+    S.w = reinterpret_cast<double *>(S.wq + RING);
+    S.qmin = S.w + RING;
+    S.ua = S.qmin + RING;
+    S.e = S.ua + RING;
+    S.npd = S.e + (size_t)RING_SLOTS * RING;
+    S.npd1 = S.npd + RING_SLOTS + 2;
+    S.isig16 = S.npd1 + RING_SLOTS + 2;
+    S.z = reinterpret_cast<int *>(S.isig16 + R);
+    S.km = S.z + RING;
+    S.i0 = S.km + RING;
+    S.i1 = S.i0 + RING;
+    S.nd = S.i1 + RING;
+    S.np = S.nd + RING;
+    S.label = S.np + kcap;
+    S.np0 = S.label + kcap;
+    return S;
+}
+inline size_t ring_smem_bytes(int R, int kcap)
+{
+    return sizeof(double) * ((size_t)5 * RING + (size_t)RING_SLOTS * RING + 2 * (RING_SLOTS + 2) + R) +
+           sizeof(int) * ((size_t)5 * RING + 3 * (size_t)kcap) + 16;
+}
+
+// asynchronous copies of cells [lo, hi) (both even) into the ring
+__device__ __forceinline__ void ring_issue(const ChainDev &D, const RingSmem &S, int lo, int hi, int nlive)
+{
+    const int ncell = hi - lo;
+    if (ncell <= 0) return;
+    const size_t N = (size_t)D.N;
+    const int nf = nlive + 9;
+    for (int g = threadIdx.x; g < ncell * nf; g += WIN_THREADS) {
+        const int fld = g / ncell, c = lo + (g - fld * ncell);
+        if (c >= D.N) continue;
+        const int ri = c & RMASK;
+        if (fld < nlive) cp_async_8(S.e + (size_t)fld * RING + ri, D.E + (size_t)fld * N + c);
+        else
+            switch (fld - nlive) {
+            case 0: cp_async_8(S.wq + ri, D.wn_q + c); break;
+            case 1: cp_async_8(S.w + ri, D.wn_w + c); break;
+            case 2: cp_async_8(S.qmin + ri, D.qmin + c); break;
+            case 3: cp_async_8(S.ua + ri, D.ua + c); break;
+            case 4: cp_async_4(S.z + ri, D.Zs + c); break;
+            case 5: cp_async_4(S.km + ri, D.kmin + c); break;
+            case 6: cp_async_4(S.i0 + ri, D.icnt + c); break;
+            case 7: cp_async_4(S.i1 + ri, D.icnt + c + 1); break;
+            default: cp_async_4(S.nd + ri, D.nd + c); break;
+            }
+    }
+    for (int g = threadIdx.x; g < ncell / 2; g += WIN_THREADS) {
+        const int c = lo + 2 * g;
+        if (c < D.N) cp_async_16_cg(S.qi + (c & RMASK), D.qnew_i + c);
+    }
+}
+
+// draw of one cell from the ring: draw_cell_fast's arithmetic, weights kept in registers
+template <int KMAX>
+__device__ __forceinline__ int draw_cell_ring(const double *ecol, int nlive, const double *s_npd, const double *s_npd1,
+                                              int zold, double w_new, double ua, double *margin)
+{
+    double w[KMAX];
+    unsigned posm = 0;
+    double run = 0.0;
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) {
+        w[s] = 0.0;
+        if (s < nlive) {
+            const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
+            w[s] = __dmul_rn(nd, ecol[(size_t)s * RING]);
+            run = __dadd_rn(run, w[s]);
+            if (w[s] > 0.0) posm |= 1u << s;
+        }
+    }
+    const double tot = __dadd_rn(run, w_new);
+    const double t = __dmul_rn(ua, tot);
+    // cumulative sums are non-decreasing: those <= t form a prefix of k slots
+    double cum = 0.0, cum_below = 0.0, cum_at = 0.0;
+    int k = 0;
+    bool found = false;
+#pragma unroll
+    for (int s = 0; s < KMAX; s++) {
+        if (s < nlive) {
+            cum = __dadd_rn(cum, w[s]);
+            if (!found) {
+                if (cum > t) {
+                    found = true;
+                    cum_at = cum;
+                } else {
+                    k = s + 1;
+                    cum_below = cum;
+                }
+            }
+        }
+    }
+    int z;
+    double gap;
+    const double below = t - cum_below;
+    if (k < nlive) {
+        z = k;
+        gap = fmin(below, cum_at - t);
+    } else if (w_new > 0.0) {
+        z = nlive;
+        gap = below;
+    } else {
+        z = posm ? 31 - __clz(posm) : -1;
+        gap = 0.0;
+    }
+    *margin = 0.5 * gap - 1e-12 * tot;
+    return z;
+}
+
+// a new cluster (slot b, opened at cell f) is a new candidate for every later cell: this CTA's
+// share of their scores.  Cells are dealt to the warps of the cluster round-robin.
+template <int NCH>
+__device__ __forceinline__ void score_new_column(const ChainDev &D, int f, int b, int rank, int csize,
+                                                 const double *s_isig16, int lane, int warp)
+{
+    const size_t N = (size_t)D.N;
+    const int stride = (WIN_THREADS / 32) * csize;
+    double ur[NCH], x[NCH], xn[NCH];
+    load_row<NCH>(D.U + (size_t)b * D.R, D.R, lane, ur);
+    int cc = f + 1 + rank * (WIN_THREADS / 32) + warp;
+    if (cc < D.N) load_row<NCH>(D.X + (size_t)cc * D.R, D.R, lane, x);
+    for (; cc < D.N; cc += stride) {
+        const int nx = cc + stride;
+        if (nx < D.N) load_row<NCH>(D.X + (size_t)nx * D.R, D.R, lane, xn); // next row in flight
+        const double qm = D.qmin[cc];
+        const long long q = q_regs<NCH>(x, ur, s_isig16, D.R, lane);
+        const double qd = (double)q * Q_SCALE;
+        if (qd < qm) {
+            // the new cluster is this cell's best candidate: it becomes the reference of the
+            // cached exponentials (slots 0..b re-exponentiated, one lane each)
+            for (int s = lane; s <= b; s += 32) {
+                const double qs = (s == b) ? qd : D.Q[(size_t)s * N + cc];
+                D.E[(size_t)s * N + cc] = exp(-0.5 * (qs - qd));
+            }
+            if (lane == 0) {
+                D.Q[(size_t)b * N + cc] = qd;
+                D.qmin[cc] = qd;
+                D.kmin[cc] = b < 255 ? b : 255;
+                D.wn_q[cc] = LLONG_MIN; // the cached new-table weight used the old reference
+            }
+        } else if (lane == 0) {
+            D.Q[(size_t)b * N + cc] = qd;
+            D.E[(size_t)b * N + cc] = exp(-0.5 * (qd - qm)); // cached like the other slots'
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; i++) x[i] = xn[i];
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(WIN_THREADS)
+scan_ring_kernel(ChainDev D, int tt)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+    extern __shared__ __align__(16) unsigned char s_ring_raw[];
+    const RingSmem S = ring_carve(s_ring_raw, D.R, D.kcap);
+    __shared__ int s_nlive, s_kt, s_err, s_block, s_wcnt[WIN_THREADS / 32];
+    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV], s_ev_nd[MAX_EV];
+    __shared__ long long s_scanned, s_events;
+
+    // (uniform over the cluster: the scalars are written back only after the last cluster barrier)
+    const int f0 = D.scal->first_event;
+    if (f0 >= D.N || D.scal->nlive > RING_SLOTS) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) S.isig16[r] = D.isig[r] * 65536.0;
+    volatile int *cmd_cell = &D.scal->open_cell, *cmd_slot = &D.scal->open_slot;
+    if (rank != 0) {
+        // helper CTAs: parked at the cluster barrier until a cluster opens or the walk ends
+        __syncthreads();
+        for (;;) {
+            cluster.sync();
+            const int f = *cmd_cell, b = *cmd_slot;
+            if (f < 0) break;
+            score_new_column<NCH>(D, f, b, rank, csize, S.isig16, lane, warp);
+            cluster.sync();
+        }
+        return;
+    }
+    for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
+        const int n = D.np[s];
+        S.np[s] = n;
+        S.np0[s] = n;
+        S.label[s] = D.slot_label[s];
+        if (s <= RING_SLOTS) {
+            S.npd[s] = n > 0 ? (double)n : 0.0;
+            S.npd1[s] = n > 1 ? (double)(n - 1) : 0.0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        s_nlive = D.scal->nlive;
+        s_kt = D.scal->kt;
+        s_err = 0;
+        s_scanned = 0;
+        s_events = 0;
+    }
+    const size_t N = (size_t)D.N;
+    const int Npad = (D.N + 1) & ~1;
+    int pos = f0, W = WIN_MIN;
+    int head = min(Npad, (pos & ~1) + RING), landed;
+    ring_issue(D, S, pos & ~1, head, D.scal->nlive);
+    cp_async_wait_all();
+    __syncthreads();
+    landed = head;
+    int resume = D.N; // where scan_kernel takes over (N: nowhere)
+    while (pos < D.N) {
+        // ---- every cell of the window is re-drawn exactly against the committed state
+        const int We = min(W, landed - pos);
+        const int c = pos + threadIdx.x;
+        const bool active = threadIdx.x < We && c < D.N;
+        const int ri = c & RMASK;
+        const int nlive = s_nlive;
+        int z = -1, zold = -1;
+        double margin = 0.0; // what this draw tolerates before it has to be redone
+        if (active) {
+            zold = S.z[ri];
+            const long long qi = S.qi[ri];
+            const double q_new = (double)qi * Q_SCALE;
+            const double qmin = S.qmin[ri];
+            const double ua = S.ua[ri];
+            const int km = S.km[ri];
+            // (the conditions under which the cached exponentials are today's: see scan_kernel)
+            bool fast = (km != 255 ? (q_new >= qmin && S.np[km] - (km == zold ? 1 : 0) > 0) : q_new == qmin);
+            if (fast && S.np0[zold] < 2 && S.np[zold] >= 2 && D.Q[(size_t)zold * N + c] < qmin) fast = false;
+            if (fast) {
+                double w_new = S.w[ri];
+                if (S.wq[ri] != qi) { // the proposal was corrected since the weight was cached
+                    w_new = __dmul_rn(D.beta, exp(-0.5 * (q_new - qmin)));
+                    S.wq[ri] = qi;
+                    S.w[ri] = w_new;
+                }
+                const double *ecol = S.e + ri;
+                if (nlive <= 8) z = draw_cell_ring<8>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
+                else if (nlive <= 16) z = draw_cell_ring<16>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
+                else if (nlive <= 24) z = draw_cell_ring<24>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
+                else z = draw_cell_ring<32>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
+            } else {
+                z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, S.np, zold, q_new, qmin, D.beta, ua);
+            }
+        }
+        // ---- the window's event candidates, in cell order (ballot + prefix over the warps)
+        const bool cand = active && z != zold;
+        const unsigned bal = __ballot_sync(CS_FULL, cand);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int jc = __popc(bal & ((1u << lane) - 1u)), ncand = 0; // candidates in front of this cell
+#pragma unroll
+        for (int w = 0; w < WIN_THREADS / 32; w++) {
+            const int cw = s_wcnt[w];
+            if (w < warp) jc += cw;
+            ncand += cw;
+        }
+        if (cand && jc < MAX_EV) {
+            s_ev_f[jc] = c;
+            s_ev_a[jc] = zold;
+            s_ev_b[jc] = z;
+            s_ev_e0[jc] = S.i0[ri];
+            s_ev_e1[jc] = S.i1[ri];
+            s_ev_nd[jc] = S.nd[ri];
+        }
+        if (threadIdx.x == 0) s_block = INT_MAX;
+        __syncthreads();
+        // ---- how many can be committed in this round (scan_kernel's rules; every warp works it
+        // out for itself, one candidate per lane): candidate j is out when it lies at or behind
+        // the nearest dependent of an earlier candidate, or behind one that opens a cluster
+        int K = min(ncand, MAX_EV);
+        {
+            const bool mine = lane < K;
+            const int fj = mine ? s_ev_f[lane] : 0;
+            int lim = mine ? s_ev_nd[lane] : INT_MAX; // -> min over candidates in front of this lane
+            const bool opens = mine && s_ev_b[lane] == nlive;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(CS_FULL, lim, off);
+                if (lane >= off) lim = min(lim, o);
+            }
+            lim = __shfl_up_sync(CS_FULL, lim, 1);
+            if (lane == 0) lim = INT_MAX;
+            const unsigned bad = __ballot_sync(CS_FULL, mine && fj >= lim);
+            const unsigned opn = __ballot_sync(CS_FULL, opens);
+            if (bad) K = min(K, __ffs(bad) - 1);
+            if (opn) K = min(K, __ffs(opn));
+        }
+        // ... or when a cell between the previous candidate and itself (itself included) runs out
+        // of margin: each of the jc events in front of a cell moves its sums and threshold by at
+        // most E[a] + E[b]
+        if (active && jc >= 1 && jc < K) {
+            double m = margin;
+            const double *ecol = S.e + ri;
+            for (int i = 0; i < jc; i++)
+                m -= (ecol[(size_t)s_ev_a[i] * RING] + ecol[(size_t)s_ev_b[i] * RING]) * 1.000000001;
+            if (!(m > 0.0)) atomicMin(&s_block, jc);
+        }
+        __syncthreads();
+        K = min(K, s_block);
+        const int nev = K;
+        const bool opened = nev > 0 && s_ev_b[nev - 1] == nlive;
+        const int lo = nev ? s_ev_f[nev - 1] + 1 : pos;
+        // ---- commit them: counts (order-free integer updates), assignments
+        if (threadIdx.x < nev) {
+            atomicAdd(&S.np[s_ev_a[threadIdx.x]], -1);
+            if (s_ev_b[threadIdx.x] == nlive) S.np[nlive] = 1; // (a slot past the live ones may hold a stale count)
+            else atomicAdd(&S.np[s_ev_b[threadIdx.x]], 1);
+            D.Zs[s_ev_f[threadIdx.x]] = s_ev_b[threadIdx.x];
+        }
+        cp_async_wait_all(); // the copies issued at the end of the previous round
+        __syncthreads();
+        landed = head;
+        if (opened) { // :209-212 the last event opens a cluster with its proposed per-segment states
+            const int f = s_ev_f[nev - 1], b = nlive;
+            if (b >= D.kcap) {
+                if (threadIdx.x == 0) s_err = CS_ERR_KCAP;
+            } else {
+                double *urow = D.U + (size_t)b * D.R;
+                const int *Jrow = D.J + (size_t)f * D.R;
+                const int a_f = s_ev_a[nev - 1]; // (its own assignment was already moved)
+                for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) {
+                    const int j = Jrow[r];
+                    const int zs = (j == f) ? a_f : ((j >= 0) ? D.Zs[j] : 0);
+                    urow[r] = (j >= 0) ? D.U[(size_t)zs * D.R + r] : fresh_state(D, f, r, tt, 0u);
+                }
+                if (threadIdx.x == 0) {
+                    S.label[b] = ++s_kt;
+                    s_nlive = b + 1;
+                }
+            }
+        }
+        if (threadIdx.x <= nlive && threadIdx.x <= RING_SLOTS && threadIdx.x < D.kcap) {
+            const int n = S.np[threadIdx.x];
+            S.npd[threadIdx.x] = n > 0 ? (double)n : 0.0;
+            S.npd1[threadIdx.x] = n > 1 ? (double)(n - 1) : 0.0;
+        }
+        if (threadIdx.x == 0) {
+            s_events += nev;
+            s_scanned += (nev ? lo - pos : min(We, D.N - pos));
+        }
+        __syncthreads();
+        if (s_err) break;
+        // ---- proposals that copied a moved cell's cluster state: correct their distance exactly,
+        // in global memory and, for cells already copied, in the ring
+        {
+            int tot_e = 0;
+            for (int i = 0; i < nev; i++) tot_e += s_ev_e1[i] - s_ev_e0[i];
+            for (int g0 = threadIdx.x; g0 < tot_e; g0 += 2 * WIN_THREADS) {
+                int ev_i[2], rr[2], cc[2];
+                double xv[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int g = g0 + u * WIN_THREADS;
+                    cc[u] = -1;
+                    if (g < tot_e) {
+                        int i = 0, e = g;
+                        while (e >= s_ev_e1[i] - s_ev_e0[i]) {
+                            e -= s_ev_e1[i] - s_ev_e0[i];
+                            i++;
+                        }
+                        e += s_ev_e0[i];
+                        const unsigned cr = D.inv[e];
+                        xv[u] = D.inv_x[e];
+                        ev_i[u] = i;
+                        cc[u] = (int)(cr >> 10);
+                        rr[u] = (int)(cr & 1023u);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    if (cc[u] > -1 && cc[u] > s_ev_f[ev_i[u]] && !cs_isna(xv[u])) {
+                        const int r = rr[u];
+                        const long long d = tint(xv[u], D.U[(size_t)s_ev_b[ev_i[u]] * D.R + r], S.isig16[r]) -
+                                            tint(xv[u], D.U[(size_t)s_ev_a[ev_i[u]] * D.R + r], S.isig16[r]);
+                        if (d) {
+                            atomicAdd(reinterpret_cast<unsigned long long *>(D.qnew_i + cc[u]), (unsigned long long)d);
+                            if (cc[u] < head)
+                                atomicAdd(reinterpret_cast<unsigned long long *>(S.qi + (cc[u] & RMASK)), (unsigned long long)d);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads(); // corrections done (global ones ordered before the copies issued below)
+        const int adv = nev ? lo - pos : We;
+        pos += adv;
+        if (nev == 0) W = min(WIN_CELLS, W * 2);
+        else if (adv < W / 4 && nev < MAX_EV) W = max(WIN_MIN, W / 2);
+        if (opened) {
+            // ---- the new column, scored by the whole cluster; then the ring is filled again
+            const int f = s_ev_f[nev - 1], b = s_ev_b[nev - 1];
+            if (threadIdx.x == 0) {
+                *cmd_cell = f;
+                *cmd_slot = b;
+            }
+            cluster.sync();
+            score_new_column<NCH>(D, f, b, 0, csize, S.isig16, lane, warp);
+            cluster.sync();
+            if (b + 1 > RING_SLOTS) { // a 33rd cluster: the generic walk takes over here
+                resume = pos;
+                break;
+            }
+            ring_issue(D, S, pos & ~1, head, b + 1);
+            cp_async_wait_all();
+            __syncthreads();
+        }
+        // ---- copies for the cells the window will reach after the next round
+        {
+            const int nh = min(Npad, (pos & ~1) + RING);
+            ring_issue(D, S, head, nh, s_nlive);
+            head = max(head, nh);
+        }
+    }
+    cp_async_wait_all();
+    if (threadIdx.x == 0) *cmd_cell = -1;
+    cluster.sync();
+    for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
+        D.np[s] = S.np[s];
+        D.slot_label[s] = S.label[s];
+    }
+    if (threadIdx.x == 0) {
+        D.scal->nlive = s_nlive;
+        D.scal->kt = s_kt;
+        D.scal->cells_scanned += s_scanned;
+        D.scal->n_events += s_events;
+        D.scal->first_event = s_err ? D.N : resume; // what is left for scan_kernel
         if (s_err) D.scal->err = s_err;
     }
 }
@@ -1172,6 +1647,44 @@ __global__ void compact_kernel(ChainDev D, int *__restrict__ rej, int reject_liv
     }
 }
 
+// CTAs in the resident-window walk's cluster (0: the kernel cannot run with this much shared
+// memory): the largest of 16, 8, 4, 2, 1 the device co-schedules.  Worked out once per shape.
+template <int NCH>
+int ring_cluster_size(size_t smem)
+{
+    static size_t known_smem = 0;
+    static int known = -1;
+    if (known >= 0 && known_smem == smem) return known;
+    known_smem = smem;
+    known = 0;
+    if (smem > 227 * 1024) return 0;
+    if (cudaFuncSetAttribute(scan_ring_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(scan_ring_kernel<NCH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    for (int cs = 16; cs >= 1; cs >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(WIN_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = cs;
+        at.val.clusterDim.y = 1;
+        at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, scan_ring_kernel<NCH>, &cfg) == cudaSuccess && n >= 1) {
+            known = cs;
+            break;
+        }
+        (void)cudaGetLastError();
+    }
+    return known;
+}
+
 template <int NCH>
 int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cudaStream_t st, cudaEvent_t *ev)
 {
@@ -1202,6 +1715,25 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
             index_scan_kernel<<<1, 1024, 0, st>>>(D);
             index_fill_kernel<<<nsm * 8, 256, 0, st>>>(D);
             if (ev) CS_CUDA(cudaEventRecord(ev[4], st));
+            // the resident-window walk (sweeps with at most 32 live clusters), then the generic one
+            // for whatever it left (nothing, unless a 33rd cluster opened)
+            const size_t smem_ring = ring_smem_bytes(D.R, D.kcap);
+            const int csize = ring_cluster_size<NCH>(smem_ring);
+            if (csize > 0) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(csize);
+                cfg.blockDim = dim3(WIN_THREADS);
+                cfg.dynamicSmemBytes = smem_ring;
+                cfg.stream = st;
+                cudaLaunchAttribute at;
+                at.id = cudaLaunchAttributeClusterDimension;
+                at.val.clusterDim.x = csize;
+                at.val.clusterDim.y = 1;
+                at.val.clusterDim.z = 1;
+                cfg.attrs = &at;
+                cfg.numAttrs = 1;
+                CS_CUDA(cudaLaunchKernelEx(&cfg, scan_ring_kernel<NCH>, D, tt));
+            }
             scan_kernel<NCH><<<1, WIN_THREADS, smem_scan, st>>>(D, tt);
         }
     }
