@@ -85,7 +85,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_CUDA(c->sig.alloc(R));
     CS_CUDA(c->isig.alloc(R));
     CS_CUDA(c->mean.alloc((size_t)kcap * R));
-    CS_CUDA(c->Zs.alloc(N));
+    CS_CUDA(c->Zs.alloc((size_t)N + 8)); // (+8 here and below: the ring scan copies whole groups of four cells)
     CS_CUDA(c->np.alloc(kcap));
     CS_CUDA(c->slot_label.alloc(kcap));
     CS_CUDA(c->newslot.alloc(kcap));
@@ -96,16 +96,16 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_CUDA(c->pcnt.alloc(ph ? (size_t)nchunks * kcap * R : 16));
     if (ph) {
         CS_CUDA(c->Q.alloc((size_t)N * kcap));
-        CS_CUDA(c->E.alloc((size_t)N * kcap));
-        CS_CUDA(c->qmin.alloc(N));
-        CS_CUDA(c->ua.alloc(N));
-        CS_CUDA(c->qnew_i.alloc((size_t)N + 2)); // (+2: the ring scan copies it in aligned pairs)
-        CS_CUDA(c->wn_q.alloc(N));
-        CS_CUDA(c->wn_w.alloc(N));
-        CS_CUDA(c->kmin.alloc(N));
-        CS_CUDA(c->icnt.alloc((size_t)N + 1));
+        CS_CUDA(c->E.alloc((size_t)N * kcap + 8));
+        CS_CUDA(c->qmin.alloc((size_t)N + 8));
+        CS_CUDA(c->ua.alloc((size_t)N + 8));
+        CS_CUDA(c->qnew_i.alloc((size_t)N + 8));
+        CS_CUDA(c->wn_q.alloc((size_t)N + 8));
+        CS_CUDA(c->wn_w.alloc((size_t)N + 8));
+        CS_CUDA(c->kmin.alloc((size_t)N + 8));
+        CS_CUDA(c->icnt.alloc((size_t)N + 8));
         CS_CUDA(c->icur.alloc(N));
-        CS_CUDA(c->nd.alloc(N));
+        CS_CUDA(c->nd.alloc((size_t)N + 8));
         CS_CUDA(c->inv.alloc(nx));
         CS_CUDA(c->inv_x.alloc(nx));
         CS_CUDA(c->tile_sums.alloc((size_t)N / 1024 + 8));

@@ -39,6 +39,7 @@
 
 #include <cooperative_groups.h>
 #include <limits.h>
+#include <math_constants.h>
 
 namespace cg = cooperative_groups;
 
@@ -776,8 +777,9 @@ scan_kernel(ChainDev D, int tt)
 //   * copies are issued at the end of a round and waited for in the middle of the next one;
 //     a window never reaches past what has landed (RING - WIN_CELLS cells of slack);
 //   * a correction of a proposal distance goes to global memory AND, for cells already
-//     copied, to the ring.  No copy is in flight while corrections are applied, and the
-//     distances are copied past L1 (16-byte .cg), so a later copy sees every correction;
+//     copied, to the ring.  No copy is in flight while corrections are applied, and copies
+//     go past L1 (16 bytes, .cg: cells are copied four at a time), so a later copy sees
+//     every correction;
 //   * opening a cluster rewrites cached columns of all later cells: the other CTAs of the
 //     cluster (parked at the cluster barrier in between) score the new column together with
 //     this one, then the ring is filled again (cluster.sync invalidates L1);
@@ -800,123 +802,159 @@ __device__ __forceinline__ void cp_async_16_cg(void *dst, const void *src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-struct RingSmem {
-    long long *qi, *wq;             // proposal distance (fixed point); the one the cached weight is for
-    double *w, *qmin, *ua, *e;      // cached new-table weight, reference, uniform, exponentials [slot][cell]
-    double *npd, *npd1, *isig16;
-    int *z, *km, *i0, *i1, *nd;     // old slot, cluster at the reference, dependents' range, nearest dependent
-    int *np, *label, *np0;
+constexpr int DEP_STAGE = 2 * WIN_THREADS; // dependents' index entries staged per round
+// fixed part of the kernel's shared memory (compile-time offsets); behind it: np, label, np0
+// (kcap ints each) and isig16 (R doubles)
+struct RingFixed {
+    long long qi[RING], wq[RING];        // proposal distance (fixed point); the one the cached weight is for
+    double w[RING], qmin[RING], ua[RING]; // cached new-table weight, reference, uniform
+    double e[RING_SLOTS * RING];         // cached exponentials [slot][cell]
+    int z[RING], km[RING], i0[RING], nd[RING]; // old slot, cluster at the reference, dependents' offset, nearest dependent
+    double dep_x[DEP_STAGE];             // staged index entries of the round's dependents: X value,
+    unsigned dep_cr[DEP_STAGE];          //   (cell << 10 | segment)
+    double npd[RING_SLOTS + 2], npd1[RING_SLOTS + 2];
 };
-
-__device__ __forceinline__ RingSmem ring_carve(unsigned char *raw, int R, int kcap)
-{
-    RingSmem S;
-    S.qi = reinterpret_cast<long long *>(raw);
-    S.wq = S.qi + RING;
-    S.w = reinterpret_cast<double *>(S.wq + RING);
-    S.qmin = S.w + RING;
-    S.ua = S.qmin + RING;
-    S.e = S.ua + RING;
-    S.npd = S.e + (size_t)RING_SLOTS * RING;
-    S.npd1 = S.npd + RING_SLOTS + 2;
-    S.isig16 = S.npd1 + RING_SLOTS + 2;
-    S.z = reinterpret_cast<int *>(S.isig16 + R);
-    S.km = S.z + RING;
-    S.i0 = S.km + RING;
-    S.i1 = S.i0 + RING;
-    S.nd = S.i1 + RING;
-    S.np = S.nd + RING;
-    S.label = S.np + kcap;
-    S.np0 = S.label + kcap;
-    return S;
-}
 inline size_t ring_smem_bytes(int R, int kcap)
 {
-    return sizeof(double) * ((size_t)5 * RING + (size_t)RING_SLOTS * RING + 2 * (RING_SLOTS + 2) + R) +
-           sizeof(int) * ((size_t)5 * RING + 3 * (size_t)kcap) + 16;
+    return sizeof(RingFixed) + sizeof(int) * 3 * (size_t)kcap + sizeof(double) * ((size_t)R + 1) + 16;
 }
 
-// asynchronous copies of cells [lo, hi) (both even) into the ring
-__device__ __forceinline__ void ring_issue(const ChainDev &D, const RingSmem &S, int lo, int hi, int nlive)
+// asynchronous copies of cells [lo, hi) (multiples of 4) into the ring, 16 bytes at a time: a
+// warp takes a field, its lanes two cells (8-byte fields) or four (4-byte fields) each.  The
+// arrays are padded, so whole groups can be read up to the cell behind the last one (whose
+// dependents' offset closes the last cell's range).
+__device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed &F, int lo, int hi, int nlive)
 {
     const int ncell = hi - lo;
     if (ncell <= 0) return;
     const size_t N = (size_t)D.N;
-    const int nf = nlive + 9;
-    for (int g = threadIdx.x; g < ncell * nf; g += WIN_THREADS) {
-        const int fld = g / ncell, c = lo + (g - fld * ncell);
-        if (c >= D.N) continue;
-        const int ri = c & RMASK;
-        if (fld < nlive) cp_async_8(S.e + (size_t)fld * RING + ri, D.E + (size_t)fld * N + c);
-        else
-            switch (fld - nlive) {
-            case 0: cp_async_8(S.wq + ri, D.wn_q + c); break;
-            case 1: cp_async_8(S.w + ri, D.wn_w + c); break;
-            case 2: cp_async_8(S.qmin + ri, D.qmin + c); break;
-            case 3: cp_async_8(S.ua + ri, D.ua + c); break;
-            case 4: cp_async_4(S.z + ri, D.Zs + c); break;
-            case 5: cp_async_4(S.km + ri, D.kmin + c); break;
-            case 6: cp_async_4(S.i0 + ri, D.icnt + c); break;
-            case 7: cp_async_4(S.i1 + ri, D.icnt + c + 1); break;
-            default: cp_async_4(S.nd + ri, D.nd + c); break;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < nlive + 9; k += WIN_THREADS / 32) {
+        if (k < nlive + 5) {
+            const double *src;
+            double *dst;
+            bool aligned = true;
+            if (k < nlive) {
+                src = D.E + (size_t)k * N;
+                dst = F.e + (size_t)k * RING;
+                aligned = (((size_t)k * N) & 1) == 0; // (odd N: every other column starts at an odd element)
+            } else if (k == nlive) {
+                src = reinterpret_cast<const double *>(D.wn_q);
+                dst = reinterpret_cast<double *>(F.wq);
+            } else if (k == nlive + 1) {
+                src = D.wn_w;
+                dst = F.w;
+            } else if (k == nlive + 2) {
+                src = D.qmin;
+                dst = F.qmin;
+            } else if (k == nlive + 3) {
+                src = D.ua;
+                dst = F.ua;
+            } else {
+                src = reinterpret_cast<const double *>(D.qnew_i);
+                dst = reinterpret_cast<double *>(F.qi);
             }
-    }
-    for (int g = threadIdx.x; g < ncell / 2; g += WIN_THREADS) {
-        const int c = lo + 2 * g;
-        if (c < D.N) cp_async_16_cg(S.qi + (c & RMASK), D.qnew_i + c);
+            for (int p = lane; p < ncell / 2; p += 32) {
+                const int c = lo + 2 * p;
+                if (aligned) {
+                    cp_async_16_cg(dst + (c & RMASK), src + c);
+                } else {
+                    cp_async_8(dst + (c & RMASK), src + c);
+                    cp_async_8(dst + ((c + 1) & RMASK), src + c + 1);
+                }
+            }
+        } else {
+            const int *src;
+            int *dst;
+            if (k == nlive + 5) {
+                src = D.Zs;
+                dst = F.z;
+            } else if (k == nlive + 6) {
+                src = D.kmin;
+                dst = F.km;
+            } else if (k == nlive + 7) {
+                src = D.icnt;
+                dst = F.i0;
+            } else {
+                src = D.nd;
+                dst = F.nd;
+            }
+            for (int q = lane; q < ncell / 4; q += 32) {
+                const int c = lo + 4 * q;
+                cp_async_16_cg(dst + (c & RMASK), src + c);
+            }
+        }
     }
 }
 
-// draw of one cell from the ring: draw_cell_fast's arithmetic, weights kept in registers
-template <int KMAX>
+// draw of one cell from the ring: draw_cell_fast's arithmetic with few registers.  Slots are
+// taken eight at a time with unconditional loads (a slot past the live ones weighs exactly +0,
+// which leaves every sum as it is); the first pass keeps the running sum after each group, the
+// second one re-adds only the group in which the threshold falls — the same additions in the
+// same order, so the same sums.
 __device__ __forceinline__ int draw_cell_ring(const double *ecol, int nlive, const double *s_npd, const double *s_npd1,
                                               int zold, double w_new, double ua, double *margin)
 {
-    double w[KMAX];
-    unsigned posm = 0;
+    constexpr int NG = RING_SLOTS / 8;
+    double cg[NG];
     double run = 0.0;
 #pragma unroll
-    for (int s = 0; s < KMAX; s++) {
-        w[s] = 0.0;
-        if (s < nlive) {
-            const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
-            w[s] = __dmul_rn(nd, ecol[(size_t)s * RING]);
-            run = __dadd_rn(run, w[s]);
-            if (w[s] > 0.0) posm |= 1u << s;
+    for (int g = 0; g < NG; g++) {
+        if (8 * g < nlive) {
+            double e[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) e[i] = ecol[(size_t)(8 * g + i) * RING];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int s = 8 * g + i;
+                const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
+                run = __dadd_rn(run, (s < nlive) ? __dmul_rn(nd, e[i]) : 0.0);
+            }
         }
+        cg[g] = run;
     }
     const double tot = __dadd_rn(run, w_new);
     const double t = __dmul_rn(ua, tot);
-    // cumulative sums are non-decreasing: those <= t form a prefix of k slots
-    double cum = 0.0, cum_below = 0.0, cum_at = 0.0;
-    int k = 0;
-    bool found = false;
+    // cumulative sums are non-decreasing: those <= t form a prefix.  Whole groups first ...
+    int gsel = 0;
+    double start = 0.0;
 #pragma unroll
-    for (int s = 0; s < KMAX; s++) {
-        if (s < nlive) {
-            cum = __dadd_rn(cum, w[s]);
-            if (!found) {
-                if (cum > t) {
-                    found = true;
-                    cum_at = cum;
-                } else {
-                    k = s + 1;
-                    cum_below = cum;
-                }
-            }
+    for (int g = 0; g < NG; g++) {
+        if (8 * g < nlive && !(cg[g] > t)) {
+            gsel = g + 1;
+            start = cg[g];
         }
     }
     int z;
     double gap;
-    const double below = t - cum_below;
-    if (k < nlive) {
-        z = k;
-        gap = fmin(below, cum_at - t);
+    if (8 * gsel < nlive) { // ... then the slots of the group the threshold falls in
+        double cum = start, cum_below = start, cum_at = CUDART_INF;
+        int k = 8 * gsel;
+        const double *eg = ecol + (size_t)(8 * gsel) * RING;
+        double e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) e[i] = eg[(size_t)i * RING];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int s = 8 * gsel + i;
+            const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
+            cum = __dadd_rn(cum, (s < nlive) ? __dmul_rn(nd, e[i]) : 0.0);
+            const bool over = cum > t;
+            cum_below = over ? cum_below : cum;
+            cum_at = over ? fmin(cum_at, cum) : cum_at;
+            k += (!over && s < nlive) ? 1 : 0;
+        }
+        z = k; // (the group's last sum exceeds t, so k < nlive)
+        gap = fmin(t - cum_below, cum_at - t);
     } else if (w_new > 0.0) {
         z = nlive;
-        gap = below;
+        gap = t - start;
     } else {
-        z = posm ? 31 - __clz(posm) : -1;
+        z = -1; // (all weights zero, or the threshold at the very top: the last positive weight)
+        for (int s = 0; s < nlive; s++) {
+            const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
+            if (__dmul_rn(nd, ecol[(size_t)s * RING]) > 0.0) z = s;
+        }
         gap = 0.0;
     }
     *margin = 0.5 * gap - 1e-12 * tot;
@@ -926,7 +964,7 @@ __device__ __forceinline__ int draw_cell_ring(const double *ecol, int nlive, con
 // a new cluster (slot b, opened at cell f) is a new candidate for every later cell: this CTA's
 // share of their scores.  Cells are dealt to the warps of the cluster round-robin.
 template <int NCH>
-__device__ __forceinline__ void score_new_column(const ChainDev &D, int f, int b, int rank, int csize,
+__device__ __noinline__ void score_new_column(const ChainDev &D, int f, int b, int rank, int csize,
                                                  const double *s_isig16, int lane, int warp)
 {
     const size_t N = (size_t)D.N;
@@ -964,22 +1002,26 @@ __device__ __forceinline__ void score_new_column(const ChainDev &D, int f, int b
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(WIN_THREADS)
+__global__ void __launch_bounds__(WIN_THREADS, 1)
 scan_ring_kernel(ChainDev D, int tt)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
     extern __shared__ __align__(16) unsigned char s_ring_raw[];
-    const RingSmem S = ring_carve(s_ring_raw, D.R, D.kcap);
+    RingFixed &F = *reinterpret_cast<RingFixed *>(s_ring_raw);
+    int *s_np = reinterpret_cast<int *>(s_ring_raw + sizeof(RingFixed));
+    int *s_label = s_np + D.kcap, *s_np0 = s_label + D.kcap;
+    double *s_isig16 = reinterpret_cast<double *>(s_ring_raw + sizeof(RingFixed) + sizeof(int) * ((3 * (size_t)D.kcap + 1) & ~(size_t)1));
     __shared__ int s_nlive, s_kt, s_err, s_block, s_wcnt[WIN_THREADS / 32];
     __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV], s_ev_nd[MAX_EV];
+    __shared__ int s_ev_off[MAX_EV + 1]; // dependents in front of each candidate's own (prefix of e1 - e0)
     __shared__ long long s_scanned, s_events;
 
     // (uniform over the cluster: the scalars are written back only after the last cluster barrier)
     const int f0 = D.scal->first_event;
     if (f0 >= D.N || D.scal->nlive > RING_SLOTS) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) S.isig16[r] = D.isig[r] * 65536.0;
+    for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
     volatile int *cmd_cell = &D.scal->open_cell, *cmd_slot = &D.scal->open_slot;
     if (rank != 0) {
         // helper CTAs: parked at the cluster barrier until a cluster opens or the walk ends
@@ -988,19 +1030,19 @@ scan_ring_kernel(ChainDev D, int tt)
             cluster.sync();
             const int f = *cmd_cell, b = *cmd_slot;
             if (f < 0) break;
-            score_new_column<NCH>(D, f, b, rank, csize, S.isig16, lane, warp);
+            score_new_column<NCH>(D, f, b, rank, csize, s_isig16, lane, warp);
             cluster.sync();
         }
         return;
     }
     for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
         const int n = D.np[s];
-        S.np[s] = n;
-        S.np0[s] = n;
-        S.label[s] = D.slot_label[s];
+        s_np[s] = n;
+        s_np0[s] = n;
+        s_label[s] = D.slot_label[s];
         if (s <= RING_SLOTS) {
-            S.npd[s] = n > 0 ? (double)n : 0.0;
-            S.npd1[s] = n > 1 ? (double)(n - 1) : 0.0;
+            F.npd[s] = n > 0 ? (double)n : 0.0;
+            F.npd1[s] = n > 1 ? (double)(n - 1) : 0.0;
         }
     }
     if (threadIdx.x == 0) {
@@ -1011,17 +1053,18 @@ scan_ring_kernel(ChainDev D, int tt)
         s_events = 0;
     }
     const size_t N = (size_t)D.N;
-    const int Npad = (D.N + 1) & ~1;
+    const int Npad = (D.N + 4) & ~3; // cells 0..N, in whole groups of four
     int pos = f0, W = WIN_MIN;
-    int head = min(Npad, (pos & ~1) + RING), landed;
-    ring_issue(D, S, pos & ~1, head, D.scal->nlive);
+    int head = min(Npad, (pos & ~3) + RING), landed;
+    ring_issue(D, F, pos & ~3, head, D.scal->nlive);
     cp_async_wait_all();
     __syncthreads();
     landed = head;
     int resume = D.N; // where scan_kernel takes over (N: nowhere)
     while (pos < D.N) {
         // ---- every cell of the window is re-drawn exactly against the committed state
-        const int We = min(W, landed - pos);
+        // (a cell's range of dependents ends at its successor's offset: one cell short of what has landed)
+        const int We = min(W, landed - 1 - pos);
         const int c = pos + threadIdx.x;
         const bool active = threadIdx.x < We && c < D.N;
         const int ri = c & RMASK;
@@ -1029,29 +1072,26 @@ scan_ring_kernel(ChainDev D, int tt)
         int z = -1, zold = -1;
         double margin = 0.0; // what this draw tolerates before it has to be redone
         if (active) {
-            zold = S.z[ri];
-            const long long qi = S.qi[ri];
+            zold = F.z[ri];
+            const long long qi = F.qi[ri];
             const double q_new = (double)qi * Q_SCALE;
-            const double qmin = S.qmin[ri];
-            const double ua = S.ua[ri];
-            const int km = S.km[ri];
+            const double qmin = F.qmin[ri];
+            const double ua = F.ua[ri];
+            const int km = F.km[ri];
             // (the conditions under which the cached exponentials are today's: see scan_kernel)
-            bool fast = (km != 255 ? (q_new >= qmin && S.np[km] - (km == zold ? 1 : 0) > 0) : q_new == qmin);
-            if (fast && S.np0[zold] < 2 && S.np[zold] >= 2 && D.Q[(size_t)zold * N + c] < qmin) fast = false;
+            bool fast = (km != 255 ? (q_new >= qmin && s_np[km] - (km == zold ? 1 : 0) > 0) : q_new == qmin);
+            if (fast && s_np0[zold] < 2 && s_np[zold] >= 2 && D.Q[(size_t)zold * N + c] < qmin) fast = false;
             if (fast) {
-                double w_new = S.w[ri];
-                if (S.wq[ri] != qi) { // the proposal was corrected since the weight was cached
+                double w_new = F.w[ri];
+                if (F.wq[ri] != qi) { // the proposal was corrected since the weight was cached
                     w_new = __dmul_rn(D.beta, exp(-0.5 * (q_new - qmin)));
-                    S.wq[ri] = qi;
-                    S.w[ri] = w_new;
+                    F.wq[ri] = qi;
+                    F.w[ri] = w_new;
                 }
-                const double *ecol = S.e + ri;
-                if (nlive <= 8) z = draw_cell_ring<8>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
-                else if (nlive <= 16) z = draw_cell_ring<16>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
-                else if (nlive <= 24) z = draw_cell_ring<24>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
-                else z = draw_cell_ring<32>(ecol, nlive, S.npd, S.npd1, zold, w_new, ua, &margin);
+                const double *ecol = F.e + ri;
+                z = draw_cell_ring(ecol, nlive, F.npd, F.npd1, zold, w_new, ua, &margin);
             } else {
-                z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, S.np, zold, q_new, qmin, D.beta, ua);
+                z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, s_np, zold, q_new, qmin, D.beta, ua);
             }
         }
         // ---- the window's event candidates, in cell order (ballot + prefix over the warps)
@@ -1070,9 +1110,9 @@ scan_ring_kernel(ChainDev D, int tt)
             s_ev_f[jc] = c;
             s_ev_a[jc] = zold;
             s_ev_b[jc] = z;
-            s_ev_e0[jc] = S.i0[ri];
-            s_ev_e1[jc] = S.i1[ri];
-            s_ev_nd[jc] = S.nd[ri];
+            s_ev_e0[jc] = F.i0[ri];
+            s_ev_e1[jc] = F.i0[(c + 1) & RMASK];
+            s_ev_nd[jc] = F.nd[ri];
         }
         if (threadIdx.x == 0) s_block = INT_MAX;
         __syncthreads();
@@ -1096,13 +1136,23 @@ scan_ring_kernel(ChainDev D, int tt)
             const unsigned opn = __ballot_sync(CS_FULL, opens);
             if (bad) K = min(K, __ffs(bad) - 1);
             if (opn) K = min(K, __ffs(opn));
+            if (warp == 0) { // where each candidate's dependents start in the round's flattened list
+                int len = lane < K ? s_ev_e1[lane] - s_ev_e0[lane] : 0, inc = len;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int o = __shfl_up_sync(CS_FULL, inc, off);
+                    if (lane >= off) inc += o;
+                }
+                s_ev_off[lane] = inc - len;
+                if (lane == 31) s_ev_off[32] = inc;
+            }
         }
         // ... or when a cell between the previous candidate and itself (itself included) runs out
         // of margin: each of the jc events in front of a cell moves its sums and threshold by at
         // most E[a] + E[b]
         if (active && jc >= 1 && jc < K) {
             double m = margin;
-            const double *ecol = S.e + ri;
+            const double *ecol = F.e + ri;
             for (int i = 0; i < jc; i++)
                 m -= (ecol[(size_t)s_ev_a[i] * RING] + ecol[(size_t)s_ev_b[i] * RING]) * 1.000000001;
             if (!(m > 0.0)) atomicMin(&s_block, jc);
@@ -1112,11 +1162,27 @@ scan_ring_kernel(ChainDev D, int tt)
         const int nev = K;
         const bool opened = nev > 0 && s_ev_b[nev - 1] == nlive;
         const int lo = nev ? s_ev_f[nev - 1] + 1 : pos;
+        // ---- the index entries of the committed events' dependents are staged now (asynchronous
+        // copies, two per thread); they are read after the commit, when their latency has passed
+        const int tot_e = s_ev_off[nev];
+        int dep_i[2] = {-1, -1};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int g = threadIdx.x + u * WIN_THREADS;
+            if (g < tot_e) {
+                int i = 0;
+                for (int j = 1; j < nev; j++) i += (s_ev_off[j] <= g) ? 1 : 0;
+                const int e = s_ev_e0[i] + (g - s_ev_off[i]);
+                cp_async_4(&F.dep_cr[g], D.inv + e);
+                cp_async_8(&F.dep_x[g], D.inv_x + e);
+                dep_i[u] = i;
+            }
+        }
         // ---- commit them: counts (order-free integer updates), assignments
         if (threadIdx.x < nev) {
-            atomicAdd(&S.np[s_ev_a[threadIdx.x]], -1);
-            if (s_ev_b[threadIdx.x] == nlive) S.np[nlive] = 1; // (a slot past the live ones may hold a stale count)
-            else atomicAdd(&S.np[s_ev_b[threadIdx.x]], 1);
+            atomicAdd(&s_np[s_ev_a[threadIdx.x]], -1);
+            if (s_ev_b[threadIdx.x] == nlive) s_np[nlive] = 1; // (a slot past the live ones may hold a stale count)
+            else atomicAdd(&s_np[s_ev_b[threadIdx.x]], 1);
             D.Zs[s_ev_f[threadIdx.x]] = s_ev_b[threadIdx.x];
         }
         cp_async_wait_all(); // the copies issued at the end of the previous round
@@ -1136,15 +1202,15 @@ scan_ring_kernel(ChainDev D, int tt)
                     urow[r] = (j >= 0) ? D.U[(size_t)zs * D.R + r] : fresh_state(D, f, r, tt, 0u);
                 }
                 if (threadIdx.x == 0) {
-                    S.label[b] = ++s_kt;
+                    s_label[b] = ++s_kt;
                     s_nlive = b + 1;
                 }
             }
         }
         if (threadIdx.x <= nlive && threadIdx.x <= RING_SLOTS && threadIdx.x < D.kcap) {
-            const int n = S.np[threadIdx.x];
-            S.npd[threadIdx.x] = n > 0 ? (double)n : 0.0;
-            S.npd1[threadIdx.x] = n > 1 ? (double)(n - 1) : 0.0;
+            const int n = s_np[threadIdx.x];
+            F.npd[threadIdx.x] = n > 0 ? (double)n : 0.0;
+            F.npd1[threadIdx.x] = n > 1 ? (double)(n - 1) : 0.0;
         }
         if (threadIdx.x == 0) {
             s_events += nev;
@@ -1155,42 +1221,29 @@ scan_ring_kernel(ChainDev D, int tt)
         // ---- proposals that copied a moved cell's cluster state: correct their distance exactly,
         // in global memory and, for cells already copied, in the ring
         {
-            int tot_e = 0;
-            for (int i = 0; i < nev; i++) tot_e += s_ev_e1[i] - s_ev_e0[i];
-            for (int g0 = threadIdx.x; g0 < tot_e; g0 += 2 * WIN_THREADS) {
-                int ev_i[2], rr[2], cc[2];
-                double xv[2];
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int g = g0 + u * WIN_THREADS;
-                    cc[u] = -1;
-                    if (g < tot_e) {
-                        int i = 0, e = g;
-                        while (e >= s_ev_e1[i] - s_ev_e0[i]) {
-                            e -= s_ev_e1[i] - s_ev_e0[i];
-                            i++;
-                        }
-                        e += s_ev_e0[i];
-                        const unsigned cr = D.inv[e];
-                        xv[u] = D.inv_x[e];
-                        ev_i[u] = i;
-                        cc[u] = (int)(cr >> 10);
-                        rr[u] = (int)(cr & 1023u);
+            auto correct = [&](int i, int cc, int r, double xv) {
+                if (cc > s_ev_f[i] && !cs_isna(xv)) {
+                    const long long d = tint(xv, D.U[(size_t)s_ev_b[i] * D.R + r], s_isig16[r]) -
+                                        tint(xv, D.U[(size_t)s_ev_a[i] * D.R + r], s_isig16[r]);
+                    if (d) {
+                        atomicAdd(reinterpret_cast<unsigned long long *>(D.qnew_i + cc), (unsigned long long)d);
+                        if (cc < head)
+                            atomicAdd(reinterpret_cast<unsigned long long *>(F.qi + (cc & RMASK)), (unsigned long long)d);
                     }
                 }
+            };
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    if (cc[u] > -1 && cc[u] > s_ev_f[ev_i[u]] && !cs_isna(xv[u])) {
-                        const int r = rr[u];
-                        const long long d = tint(xv[u], D.U[(size_t)s_ev_b[ev_i[u]] * D.R + r], S.isig16[r]) -
-                                            tint(xv[u], D.U[(size_t)s_ev_a[ev_i[u]] * D.R + r], S.isig16[r]);
-                        if (d) {
-                            atomicAdd(reinterpret_cast<unsigned long long *>(D.qnew_i + cc[u]), (unsigned long long)d);
-                            if (cc[u] < head)
-                                atomicAdd(reinterpret_cast<unsigned long long *>(S.qi + (cc[u] & RMASK)), (unsigned long long)d);
-                        }
-                    }
+            for (int u = 0; u < 2; u++)
+                if (dep_i[u] >= 0) {
+                    const unsigned cr = F.dep_cr[threadIdx.x + u * WIN_THREADS];
+                    correct(dep_i[u], (int)(cr >> 10), (int)(cr & 1023u), F.dep_x[threadIdx.x + u * WIN_THREADS]);
                 }
+            for (int g = threadIdx.x + 2 * WIN_THREADS; g < tot_e; g += WIN_THREADS) { // (rarely: long lists)
+                int i = 0;
+                for (int j = 1; j < nev; j++) i += (s_ev_off[j] <= g) ? 1 : 0;
+                const int e = s_ev_e0[i] + (g - s_ev_off[i]);
+                const unsigned cr = D.inv[e];
+                correct(i, (int)(cr >> 10), (int)(cr & 1023u), D.inv_x[e]);
             }
         }
         __syncthreads(); // corrections done (global ones ordered before the copies issued below)
@@ -1206,20 +1259,20 @@ scan_ring_kernel(ChainDev D, int tt)
                 *cmd_slot = b;
             }
             cluster.sync();
-            score_new_column<NCH>(D, f, b, 0, csize, S.isig16, lane, warp);
+            score_new_column<NCH>(D, f, b, 0, csize, s_isig16, lane, warp);
             cluster.sync();
             if (b + 1 > RING_SLOTS) { // a 33rd cluster: the generic walk takes over here
                 resume = pos;
                 break;
             }
-            ring_issue(D, S, pos & ~1, head, b + 1);
+            ring_issue(D, F, pos & ~3, head, b + 1);
             cp_async_wait_all();
             __syncthreads();
         }
         // ---- copies for the cells the window will reach after the next round
         {
-            const int nh = min(Npad, (pos & ~1) + RING);
-            ring_issue(D, S, head, nh, s_nlive);
+            const int nh = min(Npad, (pos & ~3) + RING);
+            ring_issue(D, F, head, nh, s_nlive);
             head = max(head, nh);
         }
     }
@@ -1227,8 +1280,8 @@ scan_ring_kernel(ChainDev D, int tt)
     if (threadIdx.x == 0) *cmd_cell = -1;
     cluster.sync();
     for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
-        D.np[s] = S.np[s];
-        D.slot_label[s] = S.label[s];
+        D.np[s] = s_np[s];
+        D.slot_label[s] = s_label[s];
     }
     if (threadIdx.x == 0) {
         D.scal->nlive = s_nlive;
