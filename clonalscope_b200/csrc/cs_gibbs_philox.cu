@@ -1411,7 +1411,7 @@ seq_scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
 
 // ---------------------------------------------------------------- end of sweep
 // per-chunk per-cluster sums of X and non-NA counts (R/BayesNonparCluster.R:223)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 stats_partial_kernel(ChainDev D, int smem_doubles)
 {
     extern __shared__ double s_dyn[];
@@ -1464,17 +1464,17 @@ __global__ void stats_final_kernel(ChainDev D, int nchunks)
     if (e >= nlive * D.R) return;
     double s = 0.0;
     long long c = 0;
-    for (int ch = 0; ch < nchunks; ch += 8) { // chunks in order, 8 loads in flight
-        double ps[8];
-        int pc[8];
+    for (int ch = 0; ch < nchunks; ch += 16) { // chunks in order, 16 loads in flight
+        double ps[16];
+        int pc[16];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 16; k++) {
             const size_t o = (size_t)(ch + k) * nlive * D.R + e;
             ps[k] = (ch + k < nchunks) ? D.psum[o] : 0.0;
             pc[k] = (ch + k < nchunks) ? D.pcnt[o] : 0;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 16; k++) {
             s += ps[k];
             c += pc[k];
         }
@@ -1519,7 +1519,7 @@ redraw_kernel(ChainDev D, int tt, int last)
 }
 
 // per-chunk per-segment squared residuals (R/BayesNonparCluster.R:234)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 sigma_partial_kernel(ChainDev D)
 {
     const int i0 = blockIdx.x * D.chunk, i1 = min(D.N, i0 + D.chunk);
@@ -1550,41 +1550,34 @@ sigma_partial_kernel(ChainDev D)
 // sigma_r = sqrt(S_r / c_r) with S_r the squared residuals and c_r the non-NA count of segment
 // r (:234).  The total log-likelihood at the state just recorded (:245) follows from the same
 // sums: sum_i sum_r dnorm(x; u, sigma_r, log) = -sum_r [c_r (ln sqrt(2 pi) + ln sigma_r) +
-// S_r / (2 sigma_r^2)] — no second pass over the data.  One CTA; fixed summation order.
-__global__ void __launch_bounds__(256) sigma_final_kernel(ChainDev D, int nchunks, int tt)
+// S_r / (2 sigma_r^2)] — no second pass over the data.  A thread per segment (chunks in
+// order); the per-segment terms go to D.mean[0..R) (free once the means are redrawn) and are
+// summed in segment order by record_kernel.
+__global__ void __launch_bounds__(64) sigma_final_kernel(ChainDev D, int nchunks, int tt)
 {
-    __shared__ double s_ll[256];
-    double ll = 0.0;
-    for (int r = threadIdx.x; r < D.R; r += 256) {
-        double s = 0.0;
-        long long c = 0;
-        for (int ch = 0; ch < nchunks; ch += 8) { // chunks in order, 8 loads in flight
-            double ps[8];
-            int pc[8];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= D.R) return;
+    double s = 0.0;
+    long long c = 0;
+    for (int ch = 0; ch < nchunks; ch += 16) { // chunks in order, 16 loads in flight
+        double ps[16];
+        int pc[16];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                ps[k] = (ch + k < nchunks) ? D.psum[(size_t)(ch + k) * D.R + r] : 0.0;
-                pc[k] = (ch + k < nchunks) ? D.pcnt[(size_t)(ch + k) * D.R + r] : 0;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                s += ps[k];
-                c += pc[k];
-            }
+        for (int k = 0; k < 16; k++) {
+            ps[k] = (ch + k < nchunks) ? D.psum[(size_t)(ch + k) * D.R + r] : 0.0;
+            pc[k] = (ch + k < nchunks) ? D.pcnt[(size_t)(ch + k) * D.R + r] : 0;
         }
-        const double sg = sqrt((1.0 / (double)c) * s);
-        D.sig[r] = sg;
-        D.isig[r] = 1.0 / sg;
-        D.sigma_all[(size_t)tt * D.R + r] = sg;
-        if (c > 0) ll -= (double)c * (CS_LN_SQRT_2PI + log(sg)) + 0.5 * s / (sg * sg);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            s += ps[k];
+            c += pc[k];
+        }
     }
-    s_ll[threadIdx.x] = ll;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < 256; i++) t += s_ll[i];
-        D.LL[tt] = t;
-    }
+    const double sg = sqrt((1.0 / (double)c) * s);
+    D.sig[r] = sg;
+    D.isig[r] = 1.0 / sg;
+    D.sigma_all[(size_t)tt * D.R + r] = sg;
+    D.mean[r] = (c > 0) ? (double)c * (CS_LN_SQRT_2PI + log(sg)) + 0.5 * s / (sg * sg) : 0.0;
 }
 
 // total fixed-state log-likelihood (R/BayesNonparCluster.R:133,245): per-chunk partials
@@ -1645,6 +1638,17 @@ record_kernel(ChainDev D, int tt)
         D.u_off[tt + 1] = s_off + k;
         if (s_off + k > D.urec_cap) D.scal->err = CS_ERR_UCAP;
         D.scal->u_used = s_off + k;
+    }
+    if (threadIdx.x == 32) { // total log-likelihood: sigma_final_kernel's per-segment terms, in segment order
+        double ll = 0.0;
+        for (int r0 = 0; r0 < D.R; r0 += 16) {
+            double t[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) t[k] = (r0 + k < D.R) ? D.mean[r0 + k] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) ll -= t[k];
+        }
+        D.LL[tt] = ll;
     }
     __syncthreads();
     const bool fits = s_off + s_nocc <= D.urec_cap;
@@ -1816,13 +1820,15 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
     }
     if (rc) return rc;
     const int nchunks = (D.N + D.chunk - 1) / D.chunk;
-    const int stat_smem = 160 * 1024;
+    // (a thread per segment; 72 KB of accumulators = 20 clusters of 300 segments per pass, three CTAs per SM)
+    const int stat_smem = 72 * 1024;
+    const int seg_threads = D.R >= 1024 ? 1024 : (D.R < 64 ? 64 : ((D.R + 31) / 32) * 32);
     CS_CUDA(cudaFuncSetAttribute(stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stat_smem));
-    stats_partial_kernel<<<nchunks, 256, stat_smem, st>>>(D, stat_smem / 8);
+    stats_partial_kernel<<<nchunks, seg_threads, stat_smem, st>>>(D, stat_smem / 8);
     stats_final_kernel<<<(D.kcap * D.R + 255) / 256, 256, 0, st>>>(D, nchunks);
     redraw_kernel<<<D.kcap, 128, 0, st>>>(D, tt, last);
-    sigma_partial_kernel<<<nchunks, 256, 0, st>>>(D);
-    sigma_final_kernel<<<1, 256, 0, st>>>(D, nchunks, tt);
+    sigma_partial_kernel<<<nchunks, seg_threads, 0, st>>>(D);
+    sigma_final_kernel<<<(D.R + 63) / 64, 64, 0, st>>>(D, nchunks, tt);
     record_kernel<<<1, 256, 0, st>>>(D, tt);
     relabel_kernel<<<(D.N + 255) / 256, 256, 0, st>>>(D, tt);
     compact_kernel<<<1, 256, 0, st>>>(D, rej, D.single && tt == 0);
