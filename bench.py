@@ -35,8 +35,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "nCRP Gibbs cell-updates/sec at 100k cells x 300 segs; bin-count GB/s vs HBM"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-# captures (profiles/r1_scan_full.txt: sweep 12 of the bench workload; profiles/r1_prepare_full.txt)
-SCAN_TRAFFIC_BYTES = 24_330_752
+# captures (profiles/r1_scan_ring_full.txt: sweep 3 of the bench workload; profiles/r1_prepare_full.txt)
+SCAN_TRAFFIC_BYTES = 34_788_352
 PREPARE_TRAFFIC_BYTES = 350_580_480
 
 
@@ -289,6 +289,38 @@ def run_ours(a):
                h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h))
     L.cs_chain_destroy(chain)
 
+    # ---------------- independent chains run concurrently on the GPU (supplementary: a chain's
+    # sequential walk occupies one cluster of SMs, other chains' all-SM kernels fill the rest)
+    conc = None
+    if a.chains > 1:
+        chs = []
+        for k in range(a.chains):
+            ch = C.c_void_p()
+            assert L.cs_chain_create(N, R, 0, niter, _lib.RNG_PHILOX, C.byref(ch)) == 0, L.cs_last_error()
+            chs.append(ch)
+
+        def chains_step():
+            for k, ch in enumerate(chs):
+                rc = L.cs_chain_init(ch, dp(X, C.c_double), 2, dp(U0, C.c_double), dp(Z0, C.c_int), dp(sig0, C.c_double),
+                                     C.c_double(2.0), C.c_double(2.0), C.c_uint32(seed + 1000 * (k + 1)), 0)
+                assert rc == 0, L.cs_last_error()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for t in range(niter):  # sweeps enqueued round-robin: no chain's launches wait behind another's
+                for ch in chs:
+                    assert L.cs_chain_run(ch, 1, int(t == niter - 1), 0) == 0, L.cs_last_error()
+            for ch in chs:
+                assert L.cs_chain_sync(ch) == 0, L.cs_last_error()
+            return (time.perf_counter() - t0) * 1e3
+
+        chains_step()
+        cms = max_over_ranks(chains_step())
+        conc = dict(chains=a.chains, ms=cms, value=world * a.chains * N * niter / (cms * 1e-3), unit="cell-updates/s",
+                    note="aggregate over independent chains sharing one GPU (host wall clock around "
+                         "enqueue + sync); the headline `value` is ONE chain")
+        for ch in chs:
+            L.cs_chain_destroy(ch)
+
     # ---------------- gene -> bin aggregation (cells sharded across ranks, no collective)
     G, NB = a.genes, a.bin_cells
     bins, genes = synth.geometry(G=G)
@@ -385,10 +417,11 @@ def run_ours(a):
                         step="one full chain of niter sweeps", l2="per-sweep working set (X 240 MB + Q + J) exceeds the 126 MB L2",
                         binning=f"{NB} cells x {G} genes -> {B} bins per GPU"),
             e2e=e2e, gpu_launches=int(a.steps * niter * 14),
-            roofline=dict(bound="hbm", kernel="scan_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
+            roofline=dict(bound="hbm", kernel="scan_ring_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
                           frac=ach / hbm_peak, traffic=SCAN_TRAFFIC_BYTES, peak_source=peak_src,
-                          note="latency-bound sequential commit (one CTA by contract of the sweep order): "
-                               "algorithmic bytes are N*S*8 per launch, the kernel itself touches far less",
+                          note="latency-bound sequential commit (one CTA walks the cells in the sweep's order; "
+                               "15 more CTAs of its cluster only help when a cluster opens): algorithmic bytes "
+                               "are N*S*8 per launch, the kernel itself touches far less",
                           ms_per_launch=scan_ms, share_of_step=prof[3] / max(prof[0], 1e-9),
                           prepare_kernel=dict(ms_per_launch=prof[1] / niter,
                                               achieved=alg_bytes / (prof[1] / niter * 1e-3) / 1e9,
@@ -397,6 +430,8 @@ def run_ours(a):
             sweep_split_ms=dict(run=prof[0], prepare=prof[1], index=prof[2], scan=prof[3], end_of_sweep=prof[4]),
             scan=dict(cells_scanned=int(sc.value), events=int(ev.value)),
             binning=binning, clocks=clocks)
+        if conc:
+            line["concurrent_chains"] = conc
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -413,6 +448,7 @@ def main():
     ap.add_argument("--cells", type=int, default=100000)
     ap.add_argument("--segs", type=int, default=300)
     ap.add_argument("--niter", type=int, default=200)
+    ap.add_argument("--chains", type=int, default=8, help="independent chains run concurrently (supplementary; 1 = skip)")
     ap.add_argument("--genes", type=int, default=30000)
     ap.add_argument("--bin-cells", type=int, default=100000)
     ap.add_argument("--e2e-bin-cells", type=int, default=20000)
