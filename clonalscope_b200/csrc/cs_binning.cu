@@ -13,10 +13,13 @@
 //                              stream of sorted intervals and one warp counts it with a
 //                              prefix-max scan — no shared memory, 64 warps per SM
 //   scan    exclusive scan of the per-column counts -> out_colptr
-//   pass 2  bin_fill_kernel    128-bit loads of rowidx/x, gene->bin lookup through a
-//                              packed per-gene word (first_bin | nhits<<20), shared
-//                              memory integer accumulators (ATOMS.ADD), bitmap
-//                              compaction with a warp-shuffle scan, coalesced stores
+//   pass 2  bin_fill_kernel    128-bit loads of rowidx/x (first group fetched one column
+//                              ahead), gene->bin lookup through a packed per-gene word
+//                              (first_bin | nhits<<20), shared memory integer accumulators
+//                              for all bins — one ATOMS.ADD per hit and nothing else; the
+//                              touched bins are recovered from the accumulators themselves
+//                              (conflict-free rotated scan into one 32-bin mask per
+//                              register), block scan, staged u16 ranks, coalesced stores
 //
 // Integer counts carried in doubles are summed exactly in int32 accumulators; every
 // value is checked for integrality / range and every column for overflow, and any

@@ -16,13 +16,18 @@
 //   index kernels (all SMs; skipped when the sweep has no event)
 //       inverse source index: for every cell f the (cell, segment) pairs whose proposal
 //       copies f's cluster state — what an event at f invalidates.
-//   scan_kernel (one CTA, thread per cell)
-//       resumes at the first event and walks the rest of the sweep in windows of 1024 cells:
-//       each thread re-draws its cell against the committed state from the cached
+//   scan_ring_kernel / scan_kernel (one CTA walks, thread per cell)
+//       resumes at the first event and walks the rest of the sweep in windows of 128-256
+//       cells: each thread re-draws its cell against the committed state from the cached
 //       exponentials (no exp, no gathers: counts are the only thing an event changes for
-//       almost every cell), the window is cut at its first event, that event is committed,
-//       its dependents' proposal distances are corrected in place (fixed-point, so the
-//       correction is exact), and the walk continues behind it.
+//       almost every cell) and keeps a margin — how far its sums may move before the draw
+//       could change; the window's events are committed in order for as long as every draw
+//       in front of the next one provably still holds, their dependents' proposal
+//       distances are corrected in place (fixed-point, so the correction is exact), and
+//       the walk continues behind the last one.  scan_ring_kernel (<= 32 live clusters)
+//       keeps what a re-draw needs in a shared-memory ring filled by asynchronous copies
+//       and runs as a cluster of CTAs whose other members score the column of a newly
+//       opened cluster; scan_kernel is the generic walk against global memory.
 //   seq_scan_kernel (one CTA, warp per cell): the plain sequential evaluation, used for the
 //       first sweep of a single-cluster start (rejection loop live, :174) and as the
 //       test hook that proves the speculative path draws the same chain.
