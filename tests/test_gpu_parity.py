@@ -303,6 +303,23 @@ def test_sampler_philox_vs_oracle_synthetic(cs, oracle, N, R, na, niter):
     assert np.array_equal(cs.BayesNonparCluster(s["X"], U0=s["U0"], sigmas0=s["sigmas0"], niter=1)["priors"]["Z0"], Z0)
 
 
+@pytest.mark.parametrize("N,R,K,noise,alpha", [(1200, 12, 45, 0.08, 8.0), (1500, 6, 48, 0.05, 2.0)])
+def test_sampler_philox_more_clusters_than_the_resident_walk_holds(cs, oracle, N, R, K, noise, alpha):
+    """The resident-window walk keeps 32 clusters in shared memory; when a 33rd opens in the middle
+    of a sweep it hands the walk to the generic kernel at that cell, and sweeps that start with more
+    run on the generic kernel alone.  Many well separated planted clusters force both."""
+    rng = np.random.default_rng(5)
+    prof = rng.choice([0.4, 0.9, 1.4, 1.9, 2.4], size=(K, R))
+    z = rng.integers(0, K, size=N)
+    X = np.clip(prof[z] + noise * rng.standard_normal((N, R)), 0.05, 3.0)
+    U0 = np.vstack([np.ones(R), prof[0]])
+    sig0 = np.full(R, 0.15)
+    Z0 = oracle.loglik_matrix(X, U0, sig0).argmax(axis=1).astype(np.int32) + 1
+    got, want = _philox_pair(cs, oracle, X, U0, Z0, sig0, 8, alpha=alpha)
+    assert max(want["kt"]) > 32
+    _assert_same_chain(got, want, 8)
+
+
 @pytest.mark.parametrize("name,niter", [("P5931", 40), ("BC_ductal2", 6), ("P5847_tumor", 8)])
 def test_sampler_philox_vs_oracle_on_reference_data(cs, oracle, name, niter):
     """Real fixtures are event-dense (8-25 % of the cells move per sweep, kt keeps growing) and
