@@ -28,6 +28,7 @@
 // as Matrix(sparse=TRUE) does; that rare case triggers a compaction pass.
 #include "cs_common.cuh"
 
+#include <limits.h>
 #include <vector>
 
 namespace {
@@ -37,7 +38,7 @@ constexpr int FILL_THREADS = 512;
 constexpr int LIST_CAP = 6144; // ranks staged per output round (u16 each)
 constexpr int COUNT_THREADS = 128;
 
-enum { FLAG_INEXACT = 0, FLAG_SHRUNK = 1, FLAG_CAP = 2, NFLAGS = 4 };
+enum { FLAG_INEXACT = 0, FLAG_SHRUNK = 1, FLAG_CAP = 2, FLAG_IRREG = 3, NFLAGS = 4 };
 
 // ---- pass 1 ---------------------------------------------------------------
 __global__ void __launch_bounds__(COUNT_THREADS)
@@ -455,6 +456,261 @@ bin_count_stream_kernel(int N, const int64_t *__restrict__ colptr, const int32_t
     }
 }
 
+// ---- streaming fill (regular maps, sorted columns) -----------------------------
+// With contiguous hits whose first bin is non-decreasing along the column (see
+// bin_count_stream_kernel) the RANK of every bin a column touches follows from two prefix
+// scans over its entries, M = max end of the intervals in front of an entry and C = number
+// of distinct bins they cover:
+//     bin b of interval [f, f+nh) is new when b >= M: rank C + (b - max(f, M));
+//     otherwise it lies in [f, M), which is covered without gaps: rank C - (M - b).
+// So the sums are accumulated directly in RANK space — a dense array of the column's output
+// length — and neither a bin-indexed accumulator nor its compaction exists.  One CTA per
+// column, one warp per tile of 256 entries (eight consecutive entries per lane, 128-bit
+// loads); tiles are chained through shared memory in super-steps of 16 tiles: tile maxima
+// -> barrier -> new-bin counts -> barrier -> scatter (one ATOMS.ADD per hit; the bin id of
+// a new bin is stored straight to the output).  Values are int32-exact as in
+// bin_fill_kernel (same guard, same FP64 re-run by the caller).  A column whose row indices
+// are not ascending raises FLAG_IRREG and the caller falls back to the generic kernels.
+#ifndef SF_THREADS_N
+#define SF_THREADS_N 256
+#endif
+#ifndef SF_CAP_N
+#define SF_CAP_N 8192
+#endif
+constexpr int SF_THREADS = SF_THREADS_N;
+constexpr int SF_WARPS = SF_THREADS / 32;
+constexpr int SF_CAP = SF_CAP_N;      // ranks accumulated per pass over a column (longer columns take more passes)
+constexpr int SF_EPL = 8;             // consecutive entries per lane (two 128-bit groups)
+constexpr int SF_TILE = 32 * SF_EPL;  // entries per warp tile
+
+__global__ void __launch_bounds__(SF_THREADS, 1024 / SF_THREADS)
+bin_fill_stream_kernel(int N, int B, const int64_t *__restrict__ colptr,
+                       const int32_t *__restrict__ rowidx, const double *__restrict__ x,
+                       const uint32_t *__restrict__ gmap, const int64_t *__restrict__ out_colptr,
+                       int32_t *__restrict__ out_rowidx, double *__restrict__ out_x, int64_t out_cap,
+                       int *__restrict__ counts_actual, int *__restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    int *s_acc = reinterpret_cast<int *>(s_raw); // rank-indexed sums: a window of SF_CAP ranks
+    __shared__ int s_tmax[32], s_tnew[32], s_glast[32];
+    __shared__ unsigned long long s_mag[SF_WARPS];
+    __shared__ int s_nz[SF_WARPS];
+
+    if (out_colptr[N] > out_cap) { // caller's buffers too small: report, write nothing
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[FLAG_CAP] = 1;
+        return;
+    }
+    for (int b = threadIdx.x; b < SF_CAP; b += SF_THREADS) s_acc[b] = 0;
+    if (threadIdx.x < 32) { // (entries past the warps of the CTA stay neutral)
+        s_tmax[threadIdx.x] = 0;
+        s_tnew[threadIdx.x] = 0;
+        s_glast[threadIdx.x] = -1;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool before_me = lane < wid; // lanes that stand for the tiles in front of this warp's
+
+    for (int c = blockIdx.x; c < N; c += gridDim.x) {
+        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+        const int64_t o = out_colptr[c];
+        const int expect = (int)(out_colptr[c + 1] - o);
+        int32_t *__restrict__ ocol_i = out_rowidx + o;
+        double *__restrict__ ocol_x = out_x + o;
+        const int64_t tb = e0 & ~(int64_t)3;
+        const int ntiles = (int)((e1 - tb + SF_TILE - 1) / SF_TILE);
+        bool inexact = false, irregular = false;
+        unsigned long long magsum = 0;
+        int nz = 0;
+        // (a column with more than SF_CAP distinct bins is streamed once per window of ranks)
+        for (int rb = 0; rb == 0 || rb < expect; rb += SF_CAP) {
+        int carryM = 0, carryC = 0, prev_glast = -1;
+        if (rb) magsum = 0;
+        for (int t0 = 0; t0 < ntiles; t0 += SF_WARPS) {
+            // ---- this warp's tile: SF_EPL consecutive entries per lane (warps without one only
+            // keep the barriers company)
+            const int64_t tile0 = tb + (int64_t)(t0 + wid) * SF_TILE;
+            const bool has = tile0 < e1;
+            const int64_t base = tile0 + SF_EPL * lane;
+            uint32_t w[SF_EPL];
+            int iv[SF_EPL];
+            int incl = 0, tfirst = INT_MAX, mbase = 0, cinc = 0, lnew = 0;
+            if (has) {
+                int g[SF_EPL];
+                double v[SF_EPL];
+#pragma unroll
+                for (int q = 0; q < SF_EPL; q += 4) {
+                    const int64_t b4 = base + q;
+                    g[q] = g[q + 1] = g[q + 2] = g[q + 3] = -1;
+                    v[q] = v[q + 1] = v[q + 2] = v[q + 3] = 0.0;
+                    if (b4 >= e0 && b4 + 4 <= e1) {
+                        const int4 g4 = __ldcs(reinterpret_cast<const int4 *>(rowidx + b4));
+                        const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(x + b4));
+                        const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(x + b4 + 2));
+                        g[q] = g4.x, g[q + 1] = g4.y, g[q + 2] = g4.z, g[q + 3] = g4.w;
+                        v[q] = v01.x, v[q + 1] = v01.y, v[q + 2] = v23.x, v[q + 3] = v23.y;
+                    } else if (b4 + 4 > e0 && b4 < e1) { // the column's ragged ends
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if (b4 + i >= e0 && b4 + i < e1) {
+                                g[q + i] = rowidx[b4 + i];
+                                v[q + i] = x[b4 + i];
+                            }
+                    }
+                }
+                int lmax = 0, gfirst = INT_MAX, glast = -1;
+                unsigned magl = 0; // sum of |v| x min(hits, 2) over this lane's entries (16 x 2^24 fits)
+#pragma unroll
+                for (int i = 0; i < SF_EPL; i++) {
+                    w[i] = (g[i] >= 0) ? __ldg(gmap + g[i]) : 0u;
+                    const int f = (int)(w[i] & 0xFFFFF), nh = (int)(w[i] >> 20);
+                    lmax = max(lmax, nh ? f + nh : 0);
+                    iv[i] = 0;
+                    if (g[i] >= 0) {
+                        // (integral and below 2^24 in magnitude, or the FP64 path takes the matrix)
+                        iv[i] = __double2int_rz(v[i]);
+                        if (!(__int2double_rn(iv[i]) == v[i] && (unsigned)(iv[i] + (1 << 24)) < (1u << 25))) inexact = true;
+                        magl += (unsigned)abs(iv[i]) << (nh >= 2 ? 1 : 0);
+                        if (g[i] < glast) irregular = true; // (row indices must ascend)
+                        gfirst = min(gfirst, g[i]);
+                        glast = g[i];
+                    }
+                }
+                magsum += magl;
+                // ascending across lanes (interior lanes are all valid: the neighbour's last entry is enough)
+                const int before = __shfl_up_sync(CS_FULL, glast, 1);
+                if (lane > 0 && gfirst < before) irregular = true;
+                incl = warp_incl_max(lmax, lane);
+                tfirst = __reduce_min_sync(CS_FULL, gfirst);
+                const int tlast = __reduce_max_sync(CS_FULL, glast);
+                if (lane == 31) {
+                    s_tmax[wid] = incl;
+                    s_glast[wid] = tlast;
+                }
+            } else if (lane == 31) {
+                s_tmax[wid] = 0;
+                s_glast[wid] = -1;
+                s_tnew[wid] = 0;
+            }
+            __syncthreads();
+            // ---- prefix max of the interval ends in front of this lane's entries (lane l reads tile l's)
+            const int tm = s_tmax[lane], tl = s_glast[lane];
+            const int step_max = max(carryM, __reduce_max_sync(CS_FULL, tm));
+            const int gall = max(prev_glast, __reduce_max_sync(CS_FULL, tl));
+            if (has) {
+                const int m_in = max(carryM, __reduce_max_sync(CS_FULL, before_me ? tm : 0));
+                const int gl = max(prev_glast, __reduce_max_sync(CS_FULL, before_me ? tl : -1));
+                if (tfirst < gl) irregular = true;
+                int excl = __shfl_up_sync(CS_FULL, incl, 1);
+                if (lane == 0) excl = 0;
+                mbase = max(m_in, excl);
+                int m = mbase;
+#pragma unroll
+                for (int i = 0; i < SF_EPL; i++) {
+                    const int f = (int)(w[i] & 0xFFFFF), nh = (int)(w[i] >> 20);
+                    if (nh) {
+                        lnew += max(0, f + nh - max(f, m));
+                        m = max(m, f + nh);
+                    }
+                }
+                cinc = lnew;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int tprev = __shfl_up_sync(CS_FULL, cinc, off);
+                    if (lane >= off) cinc += tprev;
+                }
+                if (lane == 31) s_tnew[wid] = cinc;
+            }
+            __syncthreads();
+            const int tn = s_tnew[lane];
+            const int step_new = (int)__reduce_add_sync(CS_FULL, (unsigned)tn);
+            if (has) {
+                const int c_in = carryC + (int)__reduce_add_sync(CS_FULL, before_me ? (unsigned)tn : 0u);
+                // ---- scatter in rank space: bin b goes to b + (b < m ? C - m : C - max(f, m))
+                int cr = c_in + cinc - lnew, m = mbase;
+#pragma unroll
+                for (int i = 0; i < SF_EPL; i++) {
+                    const int f = (int)(w[i] & 0xFFFFF), nh = (int)(w[i] >> 20);
+                    const int off_old = cr - m, off_new = cr - max(f, m), m0 = m;
+                    if (nh) {
+                        {
+                            const bool isnew = f >= m0;
+                            const int rank = f + (isnew ? off_new : off_old);
+                            if ((unsigned)(rank - rb) < (unsigned)SF_CAP && rank < expect) {
+                                atomicAdd(&s_acc[rank - rb], iv[i]);
+                                if (isnew) ocol_i[rank] = f;
+                            } else if ((unsigned)rank >= (unsigned)expect) {
+                                irregular = true;
+                            }
+                        }
+                        if (nh >= 2) {
+                            const int b = f + 1;
+                            const bool isnew = b >= m0;
+                            const int rank = b + (isnew ? off_new : off_old);
+                            if ((unsigned)(rank - rb) < (unsigned)SF_CAP && rank < expect) {
+                                atomicAdd(&s_acc[rank - rb], iv[i]);
+                                if (isnew) ocol_i[rank] = b;
+                            } else if ((unsigned)rank >= (unsigned)expect) {
+                                irregular = true;
+                            }
+                        }
+                        cr += max(0, f + nh - max(f, m0));
+                        m = max(m0, f + nh);
+                    }
+                    if (nh >= 3) { // genes over three bins or more (2 % of them)
+                        magsum += (unsigned long long)(unsigned)abs(iv[i]) * (unsigned)(nh - 2);
+#pragma unroll 1
+                        for (int k = 2; k < nh; k++) {
+                            const int b = f + k;
+                            const bool isnew = b >= m0;
+                            const int rank = b + (isnew ? off_new : off_old);
+                            if ((unsigned)(rank - rb) < (unsigned)SF_CAP && rank < expect) {
+                                atomicAdd(&s_acc[rank - rb], iv[i]);
+                                if (isnew) ocol_i[rank] = b;
+                            } else if ((unsigned)rank >= (unsigned)expect) {
+                                irregular = true;
+                            }
+                        }
+                    }
+                }
+            }
+            carryM = step_max;
+            carryC += step_new;
+            prev_glast = gall;
+            if (t0 + SF_WARPS < ntiles) __syncthreads(); // (the tile slots are rewritten by the next super-step)
+        }
+        // exactness guard: every value integral and the column cannot overflow int32
+        for (int off = 16; off >= 1; off >>= 1) magsum += __shfl_xor_sync(CS_FULL, magsum, off);
+        if (lane == 0) s_mag[wid] = magsum;
+        if (inexact) flags[FLAG_INEXACT] = 1;
+        if (irregular || carryC != expect) flags[FLAG_IRREG] = 1;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long mm = (lane < SF_WARPS) ? s_mag[lane] : 0ull;
+            for (int off = 16; off >= 1; off >>= 1) mm += __shfl_xor_sync(CS_FULL, mm, off);
+            if (lane == 0 && mm >= 2147483647ull) flags[FLAG_INEXACT] = 1;
+        }
+        // ---- the sums, in rank order; zero sums are kept here and closed up by the caller
+        const int total = min(min(carryC, expect) - rb, SF_CAP);
+        for (int r = threadIdx.x; r < total; r += SF_THREADS) {
+            const int sv = s_acc[r];
+            s_acc[r] = 0;
+            __stcs(ocol_x + rb + r, (double)sv);
+            nz += (sv != 0) ? 1 : 0;
+        }
+        if (rb + SF_CAP < expect) __syncthreads(); // (the window is refilled by the next pass)
+        } // rank windows
+        nz = (int)__reduce_add_sync(CS_FULL, (unsigned)nz);
+        if (lane == 0) s_nz[wid] = nz;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tnz = 0;
+            for (int w2 = 0; w2 < SF_WARPS; w2++) tnz += s_nz[w2];
+            counts_actual[c] = tnz;
+            if (tnz != expect) flags[FLAG_SHRUNK] = 1;
+        }
+    }
+}
+
 // closes the gaps left by dropped zero sums: column c's first nwritten entries (all of its
 // padded range when nwritten == NULL) are copied, zeros skipped, to the compact offsets
 __global__ void compact_columns_kernel(int N, const int64_t *__restrict__ old_colptr,
@@ -491,6 +747,7 @@ __global__ void compact_columns_kernel(int N, const int64_t *__restrict__ old_co
 struct cs_bin_plan {
     int G = 0, B = 0;
     bool regular = false; // contiguous hits with non-decreasing first bin: streaming kernels apply
+    bool stream_fill = true; // (cleared for good when a matrix with unsorted columns shows up)
     DevBuf<uint32_t> gmap;
     DevBuf<int32_t> map_ptr, map_bin;
     DevBuf<int> counts, counts2, flags;
@@ -664,8 +921,22 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         return CS_OK;
     }
     CS_REQUIRE(d_out_x != nullptr, "cs_bin_counts_dev: d_out_x is NULL");
-    rc = launch_fill<int>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
-    if (rc) return rc;
+    const bool streamed = p->regular && p->stream_fill;
+    if (streamed) {
+        const size_t smem = (size_t)SF_CAP * sizeof(int);
+        CS_CUDA(cudaFuncSetAttribute(bin_fill_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bin_fill_stream_kernel, SF_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        int grid = cs_num_sms() * per_sm;
+        if (grid > N) grid = N;
+        bin_fill_stream_kernel<<<grid, SF_THREADS, smem, st>>>(N, p->B, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr,
+                                                              d_out_rowidx, d_out_x, out_cap, p->counts2.p, p->flags.p);
+        CS_CUDA(cudaGetLastError());
+    } else {
+        rc = launch_fill<int>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
+        if (rc) return rc;
+    }
     CS_CUDA(cudaEventRecord(p->ev[3], st));
     p->timed = true;
     CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -677,7 +948,18 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
                      (long long)*h_nnz);
         return CS_ERR_UCAP;
     }
+    if (p->h_pinned[FLAG_IRREG]) {
+        // row indices of some column do not ascend (the streaming count presumed they do, so the
+        // offsets are void as well): the generic kernels from now on.  CS_ERR_UCAP from here means
+        // the caller sized the output from a streaming count; *nnz_out holds what is needed.
+        p->stream_fill = false;
+        p->regular = false;
+        return cs_bin_counts_dev(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, nnz_out,
+                                 stream);
+    }
+    bool zeros_inline = streamed; // the streaming fill leaves zero sums in place, the generic one drops them
     if (p->h_pinned[FLAG_INEXACT]) { // non-integer / huge values: exact-order-free FP64 accumulators
+        zeros_inline = false;
         CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
         rc = launch_fill<double>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
         if (rc) return rc;
@@ -691,7 +973,7 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         CS_CUDA(p->tmp_x.reserve((size_t)padded));
         rc = run_scan(p, N, p->counts2.p, p->colptr2.p, st);
         if (rc) return rc;
-        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, p->counts2.p,
+        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, zeros_inline ? nullptr : p->counts2.p,
                                                                  p->colptr2.p, d_out_rowidx, d_out_x, p->tmp_i.p,
                                                                  p->tmp_x.p);
         CS_CUDA(cudaGetLastError());
@@ -762,6 +1044,14 @@ extern "C" int cs_bin_counts_begin(int G, int N, int B, const int32_t *colptr, c
     CS_CUDA(job->out_x.alloc((size_t)need));
     rc = cs_bin_counts_dev(plan, N, d_colptr.p, d_rowidx.p, d_x.p, job->out_colptr.p, job->out_rowidx.p,
                            job->out_x.p, need, &job->nnz, nullptr);
+    if (rc == CS_ERR_UCAP && job->nnz > need) { // (columns with unsorted rows: the first count was void)
+        need = job->nnz;
+        CS_REQUIRE(need <= 2147483647LL, "cs_bin_counts_begin: result has %lld nonzeros, more than a dgCMatrix holds", (long long)need);
+        CS_CUDA(job->out_rowidx.alloc((size_t)need));
+        CS_CUDA(job->out_x.alloc((size_t)need));
+        rc = cs_bin_counts_dev(plan, N, d_colptr.p, d_rowidx.p, d_x.p, job->out_colptr.p, job->out_rowidx.p,
+                               job->out_x.p, need, &job->nnz, nullptr);
+    }
     if (rc) return rc;
     *nnz_out = job->nnz;
     *job_out = job;

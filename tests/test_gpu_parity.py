@@ -184,6 +184,13 @@ def test_binning_streaming_path_edge_cases(cs, oracle):
     x3[5] = 2.5e9
     _check_bins(cs, oracle, G, N, B, colptr, rowidx, x3, map_ptr, map_bin)
     _check_bins(cs, oracle, G, N, B, colptr, rowidx, x + 0.5, map_ptr, map_bin, exact=False)
+    # row indices that do not ascend within a column (not a valid dgCMatrix, but the C ABI takes any
+    # CSC): the streaming fill notices and the generic kernels take over
+    r4, x4 = rowidx.copy(), x.copy()
+    perm = rng.permutation(colptr[14] - colptr[13])
+    r4[colptr[13]:colptr[14]] = r4[colptr[13]:colptr[14]][perm]
+    x4[colptr[13]:colptr[14]] = x4[colptr[13]:colptr[14]][perm]
+    _check_bins(cs, oracle, G, N, B, colptr, r4, x4, map_ptr, map_bin)
 
 
 def test_binning_permutation_invariance(cs):
