@@ -13,7 +13,10 @@
 //                              stream of sorted intervals and one warp counts it with a
 //                              prefix-max scan — no shared memory, 64 warps per SM
 //   scan    exclusive scan of the per-column counts -> out_colptr
-//   pass 2  bin_fill_kernel    128-bit loads of rowidx/x (first group fetched one column
+//   pass 2  bin_fill_stream_kernel (regular maps): sums accumulated in RANK space — the rank
+//                              of every bin follows from two prefix scans over the column
+//                              (see the kernel) — no bin-indexed accumulator, no compaction
+//           bin_fill_kernel    (any map) 128-bit loads of rowidx/x (first group fetched one column
 //                              ahead), gene->bin lookup through a packed per-gene word
 //                              (first_bin | nhits<<20), shared memory integer accumulators
 //                              for all bins — one ATOMS.ADD per hit and nothing else; the
@@ -404,9 +407,7 @@ bin_fill_kernel(int N, int B, const int64_t *__restrict__ colptr,
 // the reference's 200-kb tiles give), a CSC column is a stream of intervals [b0, b0+nh)
 // sorted by b0, and the number of distinct bins it touches is the length of their union:
 // an interval adds the bins no earlier interval covered (prefix max of the interval ends).
-// One warp counts one column with shuffles only.  (Warp-cooperative and lane-per-column
-// streaming FILL kernels built on the same idea were measured at 2.7-11 ms per 100k cells
-// against 3.2 ms for bin_fill_kernel and dropped; see DESIGN.md "Binning: what was tried".)
+// One warp counts one column with shuffles only.
 constexpr int STREAM_THREADS = 512;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 
@@ -510,10 +511,20 @@ bin_fill_stream_kernel(int N, int B, const int64_t *__restrict__ colptr,
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool before_me = lane < wid; // lanes that stand for the tiles in front of this warp's
 
+    // (the offsets of the next column are fetched while the current one is processed)
+    int64_t ne0 = 0, ne1 = 0, no0 = 0, no1 = 0;
+    if ((int)blockIdx.x < N) {
+        ne0 = colptr[blockIdx.x], ne1 = colptr[blockIdx.x + 1];
+        no0 = out_colptr[blockIdx.x], no1 = out_colptr[blockIdx.x + 1];
+    }
     for (int c = blockIdx.x; c < N; c += gridDim.x) {
-        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
-        const int64_t o = out_colptr[c];
-        const int expect = (int)(out_colptr[c + 1] - o);
+        const int64_t e0 = ne0, e1 = ne1;
+        const int64_t o = no0;
+        const int expect = (int)(no1 - o);
+        if (c + (int)gridDim.x < N) {
+            ne0 = colptr[c + gridDim.x], ne1 = colptr[c + gridDim.x + 1];
+            no0 = out_colptr[c + gridDim.x], no1 = out_colptr[c + gridDim.x + 1];
+        }
         int32_t *__restrict__ ocol_i = out_rowidx + o;
         double *__restrict__ ocol_x = out_x + o;
         const int64_t tb = e0 & ~(int64_t)3;
