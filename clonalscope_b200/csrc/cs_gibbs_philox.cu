@@ -44,6 +44,7 @@
 
 #include <cooperative_groups.h>
 #include <limits.h>
+#include <stdlib.h>
 #include <math_constants.h>
 
 namespace cg = cooperative_groups;
@@ -1725,7 +1726,12 @@ int ring_cluster_size(size_t smem)
         (void)cudaGetLastError();
         return 0;
     }
+    // (CS_RING_CLUSTER caps the cluster: smaller clusters co-schedule more easily when several
+    //  chains share the GPU; the helpers only matter in sweeps that open clusters)
+    int cap = 16;
+    if (const char *e = getenv("CS_RING_CLUSTER")) cap = atoi(e) < 1 ? 1 : atoi(e);
     for (int cs = 16; cs >= 1; cs >>= 1) {
+        if (cs > cap) continue;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs);
         cfg.blockDim = dim3(WIN_THREADS);
@@ -1752,10 +1758,15 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
 {
     const size_t smem_prep = sizeof(double) * D.R + sizeof(int) * D.kcap;
     const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap + 64 * WIN_CELLS) + sizeof(int) * 3 * D.kcap + 16;
-    CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
-    if (smem_scan > 48 * 1024) {
-        CS_CUDA(cudaFuncSetAttribute(prepare_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
-        CS_CUDA(cudaFuncSetAttribute(seq_scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+    static size_t attr_scan = 0, attr_prep = 0; // (function attributes are set when the sizes change, not every sweep)
+    if (attr_scan != smem_scan || attr_prep != smem_prep) {
+        CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+        if (smem_scan > 48 * 1024) {
+            CS_CUDA(cudaFuncSetAttribute(prepare_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+            CS_CUDA(cudaFuncSetAttribute(seq_scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+        }
+        attr_scan = smem_scan;
+        attr_prep = smem_prep;
     }
     const bool reject_live = D.single && tt == 0;
     if (ev) CS_CUDA(cudaEventRecord(ev[0], st));
@@ -1828,7 +1839,11 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
     // (a thread per segment; 72 KB of accumulators = 20 clusters of 300 segments per pass, three CTAs per SM)
     const int stat_smem = 72 * 1024;
     const int seg_threads = D.R >= 1024 ? 1024 : (D.R < 64 ? 64 : ((D.R + 31) / 32) * 32);
-    CS_CUDA(cudaFuncSetAttribute(stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stat_smem));
+    static bool attr_stats = false;
+    if (!attr_stats) {
+        CS_CUDA(cudaFuncSetAttribute(stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stat_smem));
+        attr_stats = true;
+    }
     stats_partial_kernel<<<nchunks, seg_threads, stat_smem, st>>>(D, stat_smem / 8);
     stats_final_kernel<<<(D.kcap * D.R + 255) / 256, 256, 0, st>>>(D, nchunks);
     redraw_kernel<<<D.kcap, 128, 0, st>>>(D, tt, last);
