@@ -16,6 +16,15 @@ struct ChainScal {
     long long cells_scanned, n_events, n_reject, u_used;
 };
 
+// one entry of the inverse source index: a (cell, segment) whose proposal copies the source
+// cell's cluster state, with the value the correction needs riding along (one 16-byte record:
+// one store when the index is built, one 16-byte copy when it is read)
+struct __align__(16) InvEntry {
+    unsigned cr;      // cell << 10 | segment
+    unsigned pad;
+    double x;         // X[cell][segment]
+};
+
 struct ChainDev {
     int N, R, kcap;
     int chunk;        // cells per end-of-sweep reduction chunk
@@ -44,8 +53,7 @@ struct ChainDev {
     int *qcols;       // N          (sequential kernel) valid columns of Q
     int *icnt;        // N+1        inverse source index: offsets (after the scan)
     int *icur;        // N          fill cursors
-    unsigned *inv;    // N x R      (cell << 10 | segment) entries grouped by source cell
-    double *inv_x;    // N x R      X[cell][segment] of the same entries
+    InvEntry *inv;    // N x R      inverse source index, entries grouped by source cell
     int *nd;          // N          nearest later cell whose proposal copies this cell
     long long *tile_sums; // scan scratch
     double *mean;     // kcap x R cluster means

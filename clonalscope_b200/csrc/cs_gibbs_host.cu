@@ -22,11 +22,11 @@ struct cs_chain {
     bool inited = false;
     cudaStream_t st = nullptr;
     ChainDev D{};
-    DevBuf<double> X, Xc, Ua, Ub, sig, isig, Q, E, qmin, ua, inv_x, mean, psum, sigma_all, LL, u_rows, L0;
+    DevBuf<double> X, Xc, Ua, Ub, sig, isig, Q, E, qmin, ua, mean, psum, sigma_all, LL, u_rows, L0;
     DevBuf<long long> qnew_i, tile_sums, wn_q;
     DevBuf<double> wn_w;
     DevBuf<int> kmin, icnt, icur, nd;
-    DevBuf<unsigned> inv;
+    DevBuf<InvEntry> inv;
     DevBuf<int> Zs, np, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
     DevBuf<long long> u_off;
     DevBuf<uint32_t> mt;
@@ -107,7 +107,6 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
         CS_CUDA(c->icur.alloc(N));
         CS_CUDA(c->nd.alloc((size_t)N + 8));
         CS_CUDA(c->inv.alloc(nx));
-        CS_CUDA(c->inv_x.alloc(nx));
         CS_CUDA(c->tile_sums.alloc((size_t)N / 1024 + 8));
         CS_CUDA(c->J.alloc(nx));
         CS_CUDA(c->zspec.alloc(N));
@@ -127,7 +126,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     D.slot_label = c->slot_label.p; D.sig = c->sig.p; D.isig = c->isig.p; D.Q = c->Q.p; D.J = c->J.p;
     D.E = c->E.p; D.qmin = c->qmin.p; D.ua = c->ua.p; D.qnew_i = c->qnew_i.p; D.icnt = c->icnt.p;
     D.wn_q = c->wn_q.p; D.wn_w = c->wn_w.p; D.kmin = c->kmin.p;
-    D.icur = c->icur.p; D.inv = c->inv.p; D.inv_x = c->inv_x.p; D.nd = c->nd.p; D.tile_sums = c->tile_sums.p;
+    D.icur = c->icur.p; D.inv = c->inv.p; D.nd = c->nd.p; D.tile_sums = c->tile_sums.p;
     D.zspec = c->zspec.p; D.qcols = c->qcols.p; D.mean = c->mean.p; D.psum = c->psum.p; D.pcnt = c->pcnt.p;
     D.newslot = c->newslot.p; D.mt = c->mt.p; D.scal = c->scal.p;
     D.Zall = c->Zall.p; D.sigma_all = c->sigma_all.p; D.LL = c->LL.p; D.kt_all = c->kt_all.p;

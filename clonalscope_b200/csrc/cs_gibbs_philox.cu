@@ -380,7 +380,7 @@ __device__ __forceinline__ int draw_cell_fast(const double *Ec, size_t stride, i
 
 // ---------------------------------------------------------------- prepare (all SMs)
 template <int NCH>
-__global__ void __launch_bounds__(PREP_THREADS)
+__global__ void __launch_bounds__(PREP_THREADS, 4)
 prepare_kernel(ChainDev D, int tt, int *__restrict__ rej)
 {
     extern __shared__ double s_dyn[];
@@ -519,9 +519,12 @@ __global__ void index_fill_kernel(ChainDev D)
         const int cc = (int)(e / (size_t)D.R);
         if (j >= 0 && cc > j) {
             const int p = atomicAdd(&D.icur[j], 1);
-            D.inv[p] = ((unsigned)cc << 10) | (unsigned)(e % (size_t)D.R);
+            InvEntry en; // (the value the correction needs rides along: one dependent load less)
+            en.cr = ((unsigned)cc << 10) | (unsigned)(e % (size_t)D.R);
+            en.pad = 0u;
+            en.x = D.X[e];
+            *reinterpret_cast<int4 *>(D.inv + p) = *reinterpret_cast<const int4 *>(&en);
             atomicMin(&D.nd[j], cc); // nearest later cell whose proposal copies cell j
-            D.inv_x[p] = D.X[e];     // the value the correction needs rides along: one dependent load less
         }
     }
 }
@@ -715,8 +718,8 @@ scan_kernel(ChainDev D, int tt)
                 }
                 e += s_ev_e0[i];
                 const int f = s_ev_f[i];
-                const unsigned cr = D.inv[e];
-                const double xv = D.inv_x[e];
+                const unsigned cr = D.inv[e].cr;
+                const double xv = D.inv[e].x;
                 const int cc = (int)(cr >> 10), r = (int)(cr & 1023u);
                 if (cc > f && !cs_isna(xv)) {
                     const long long d = tint(xv, D.U[(size_t)s_ev_b[i] * D.R + r], s_isig16[r]) -
@@ -794,10 +797,6 @@ constexpr int RING = 512;
 constexpr int RMASK = RING - 1;
 constexpr int RING_SLOTS = 32;
 
-__device__ __forceinline__ void cp_async_4(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async_8(void *dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -816,8 +815,7 @@ struct RingFixed {
     double w[RING], qmin[RING], ua[RING]; // cached new-table weight, reference, uniform
     double e[RING_SLOTS * RING];         // cached exponentials [slot][cell]
     int z[RING], km[RING], i0[RING], nd[RING]; // old slot, cluster at the reference, dependents' offset, nearest dependent
-    double dep_x[DEP_STAGE];             // staged index entries of the round's dependents: X value,
-    unsigned dep_cr[DEP_STAGE];          //   (cell << 10 | segment)
+    InvEntry dep[DEP_STAGE];             // staged index entries of the round's dependents
     double npd[RING_SLOTS + 2], npd1[RING_SLOTS + 2];
 };
 inline size_t ring_smem_bytes(int R, int kcap)
@@ -1179,8 +1177,7 @@ scan_ring_kernel(ChainDev D, int tt)
                 int i = 0;
                 for (int j = 1; j < nev; j++) i += (s_ev_off[j] <= g) ? 1 : 0;
                 const int e = s_ev_e0[i] + (g - s_ev_off[i]);
-                cp_async_4(&F.dep_cr[g], D.inv + e);
-                cp_async_8(&F.dep_x[g], D.inv_x + e);
+                cp_async_16_cg(&F.dep[g], D.inv + e);
                 dep_i[u] = i;
             }
         }
@@ -1241,15 +1238,15 @@ scan_ring_kernel(ChainDev D, int tt)
 #pragma unroll
             for (int u = 0; u < 2; u++)
                 if (dep_i[u] >= 0) {
-                    const unsigned cr = F.dep_cr[threadIdx.x + u * WIN_THREADS];
-                    correct(dep_i[u], (int)(cr >> 10), (int)(cr & 1023u), F.dep_x[threadIdx.x + u * WIN_THREADS]);
+                    const unsigned cr = F.dep[threadIdx.x + u * WIN_THREADS].cr;
+                    correct(dep_i[u], (int)(cr >> 10), (int)(cr & 1023u), F.dep[threadIdx.x + u * WIN_THREADS].x);
                 }
             for (int g = threadIdx.x + 2 * WIN_THREADS; g < tot_e; g += WIN_THREADS) { // (rarely: long lists)
                 int i = 0;
                 for (int j = 1; j < nev; j++) i += (s_ev_off[j] <= g) ? 1 : 0;
                 const int e = s_ev_e0[i] + (g - s_ev_off[i]);
-                const unsigned cr = D.inv[e];
-                correct(i, (int)(cr >> 10), (int)(cr & 1023u), D.inv_x[e]);
+                const unsigned cr = D.inv[e].cr;
+                correct(i, (int)(cr >> 10), (int)(cr & 1023u), D.inv[e].x);
             }
         }
         __syncthreads(); // corrections done (global ones ordered before the copies issued below)
