@@ -1460,29 +1460,48 @@ stats_partial_kernel(ChainDev D, int smem_doubles)
     }
 }
 
-__global__ void stats_final_kernel(ChainDev D, int nchunks)
+// (the chunk partials of an element are summed by FIN_PARTS threads, each over a contiguous
+// quarter of the chunks in order, and the quarters are added in order: a fixed order again,
+// at a quarter of the latency)
+constexpr int FIN_ELEMS = 64, FIN_PARTS = 4;
+__global__ void __launch_bounds__(FIN_ELEMS * FIN_PARTS) stats_final_kernel(ChainDev D, int nchunks)
 {
+    __shared__ double s_s[FIN_PARTS][FIN_ELEMS];
+    __shared__ long long s_c[FIN_PARTS][FIN_ELEMS];
     const int nlive = D.scal->nlive;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nlive * D.R) return;
+    const int le = threadIdx.x % FIN_ELEMS, part = threadIdx.x / FIN_ELEMS;
+    const int e = blockIdx.x * FIN_ELEMS + le;
+    const int per = (nchunks + FIN_PARTS - 1) / FIN_PARTS;
+    const int c0 = part * per, c1 = min(nchunks, c0 + per);
     double s = 0.0;
     long long c = 0;
-    for (int ch = 0; ch < nchunks; ch += 16) { // chunks in order, 16 loads in flight
-        double ps[16];
-        int pc[16];
+    if (e < nlive * D.R) {
+        for (int ch = c0; ch < c1; ch += 16) { // chunks in order, 16 loads in flight
+            double ps[16];
+            int pc[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const size_t o = (size_t)(ch + k) * nlive * D.R + e;
-            ps[k] = (ch + k < nchunks) ? D.psum[o] : 0.0;
-            pc[k] = (ch + k < nchunks) ? D.pcnt[o] : 0;
-        }
+            for (int k = 0; k < 16; k++) {
+                const size_t o = (size_t)(ch + k) * nlive * D.R + e;
+                ps[k] = (ch + k < c1) ? D.psum[o] : 0.0;
+                pc[k] = (ch + k < c1) ? D.pcnt[o] : 0;
+            }
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            s += ps[k];
-            c += pc[k];
+            for (int k = 0; k < 16; k++) {
+                s += ps[k];
+                c += pc[k];
+            }
         }
     }
-    D.mean[e] = c ? s / (double)c : 0.0;
+    s_s[part][le] = s;
+    s_c[part][le] = c;
+    __syncthreads();
+    if (part == 0 && e < nlive * D.R) {
+        for (int p2 = 1; p2 < FIN_PARTS; p2++) {
+            s += s_s[p2][le];
+            c += s_c[p2][le];
+        }
+        D.mean[e] = c ? s / (double)c : 0.0;
+    }
 }
 
 // redraw of the cluster means (R/BayesNonparCluster.R:221-232; :260-266 on the last sweep)
@@ -1556,25 +1575,39 @@ sigma_partial_kernel(ChainDev D)
 // S_r / (2 sigma_r^2)] — no second pass over the data.  A thread per segment (chunks in
 // order); the per-segment terms go to D.mean[0..R) (free once the means are redrawn) and are
 // summed in segment order by record_kernel.
-__global__ void __launch_bounds__(64) sigma_final_kernel(ChainDev D, int nchunks, int tt)
+__global__ void __launch_bounds__(FIN_ELEMS * FIN_PARTS) sigma_final_kernel(ChainDev D, int nchunks, int tt)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= D.R) return;
+    __shared__ double s_s[FIN_PARTS][FIN_ELEMS];
+    __shared__ long long s_c[FIN_PARTS][FIN_ELEMS];
+    const int le = threadIdx.x % FIN_ELEMS, part = threadIdx.x / FIN_ELEMS;
+    const int r = blockIdx.x * FIN_ELEMS + le;
+    const int per = (nchunks + FIN_PARTS - 1) / FIN_PARTS;
+    const int c0 = part * per, c1 = min(nchunks, c0 + per);
     double s = 0.0;
     long long c = 0;
-    for (int ch = 0; ch < nchunks; ch += 16) { // chunks in order, 16 loads in flight
-        double ps[16];
-        int pc[16];
+    if (r < D.R) {
+        for (int ch = c0; ch < c1; ch += 16) { // chunks in order, 16 loads in flight
+            double ps[16];
+            int pc[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            ps[k] = (ch + k < nchunks) ? D.psum[(size_t)(ch + k) * D.R + r] : 0.0;
-            pc[k] = (ch + k < nchunks) ? D.pcnt[(size_t)(ch + k) * D.R + r] : 0;
-        }
+            for (int k = 0; k < 16; k++) {
+                ps[k] = (ch + k < c1) ? D.psum[(size_t)(ch + k) * D.R + r] : 0.0;
+                pc[k] = (ch + k < c1) ? D.pcnt[(size_t)(ch + k) * D.R + r] : 0;
+            }
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            s += ps[k];
-            c += pc[k];
+            for (int k = 0; k < 16; k++) {
+                s += ps[k];
+                c += pc[k];
+            }
         }
+    }
+    s_s[part][le] = s;
+    s_c[part][le] = c;
+    __syncthreads();
+    if (part != 0 || r >= D.R) return;
+    for (int p2 = 1; p2 < FIN_PARTS; p2++) {
+        s += s_s[p2][le];
+        c += s_c[p2][le];
     }
     const double sg = sqrt((1.0 / (double)c) * s);
     D.sig[r] = sg;
@@ -1842,10 +1875,10 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
         attr_stats = true;
     }
     stats_partial_kernel<<<nchunks, seg_threads, stat_smem, st>>>(D, stat_smem / 8);
-    stats_final_kernel<<<(D.kcap * D.R + 255) / 256, 256, 0, st>>>(D, nchunks);
+    stats_final_kernel<<<(D.kcap * D.R + FIN_ELEMS - 1) / FIN_ELEMS, FIN_ELEMS * FIN_PARTS, 0, st>>>(D, nchunks);
     redraw_kernel<<<D.kcap, 128, 0, st>>>(D, tt, last);
     sigma_partial_kernel<<<nchunks, seg_threads, 0, st>>>(D);
-    sigma_final_kernel<<<(D.R + 63) / 64, 64, 0, st>>>(D, nchunks, tt);
+    sigma_final_kernel<<<(D.R + FIN_ELEMS - 1) / FIN_ELEMS, FIN_ELEMS * FIN_PARTS, 0, st>>>(D, nchunks, tt);
     record_kernel<<<1, 256, 0, st>>>(D, tt);
     relabel_kernel<<<(D.N + 255) / 256, 256, 0, st>>>(D, tt);
     compact_kernel<<<1, 256, 0, st>>>(D, rej, D.single && tt == 0);
