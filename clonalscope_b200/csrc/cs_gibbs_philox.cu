@@ -1431,18 +1431,18 @@ stats_partial_kernel(ChainDev D, int smem_doubles)
             cnt[e] = 0;
         }
         __syncthreads();
-        // a thread owns segment r: cells in order (fixed summation order), 8 loads in flight
+        // a thread owns segment r: cells in order (fixed summation order), 16 loads in flight
         for (int r = threadIdx.x; r < R; r += blockDim.x) {
-            for (int i = i0; i < i1; i += 8) {
-                int sl[8];
-                double v[8];
+            for (int i = i0; i < i1; i += 16) {
+                int sl[16];
+                double v[16];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < 16; u++) {
                     sl[u] = (i + u < i1) ? D.Zs[i + u] - t0 : -1;
                     v[u] = (i + u < i1) ? D.X[(size_t)(i + u) * R + r] : 0.0;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < 16; u++) {
                     if (sl[u] >= 0 && sl[u] < ns && !cs_isna(v[u])) {
                         acc[sl[u] * R + r] += v[u];
                         cnt[sl[u] * R + r] += 1;
@@ -1548,16 +1548,16 @@ sigma_partial_kernel(ChainDev D)
     for (int r = threadIdx.x; r < D.R; r += blockDim.x) {
         double s = 0.0;
         int c = 0;
-        for (int i = i0; i < i1; i += 8) { // cells in order, 8 (x, u) pairs in flight
-            double x[8], u[8];
+        for (int i = i0; i < i1; i += 16) { // cells in order, 16 (x, u) pairs in flight
+            double x[16], u[16];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < 16; k++) {
                 const bool ok = i + k < i1;
                 x[k] = ok ? D.X[(size_t)(i + k) * D.R + r] : NAN;
                 u[k] = ok ? D.U[(size_t)D.Zs[i + k] * D.R + r] : 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < 16; k++) {
                 if (cs_isna(x[k])) continue;
                 c++;
                 const double d = x[k] - u[k];
