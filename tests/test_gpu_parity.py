@@ -455,3 +455,92 @@ def test_device_stats_match_numpy(cs):
         d = X - U[Z - 1]
         sig = np.sqrt(np.nansum(d * d, axis=0) / (~np.isnan(X)).sum(axis=0))
         np.testing.assert_allclose(out["sigma"].cpu().numpy(), sig, rtol=1e-11)
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes, through properties
+def test_full_size_binning_properties(cs):
+    """100k cells x 30k genes -> 14,385 bins (the bench workload), through the device entry point.
+    Size-independent properties: every column's sum equals sum_g x_g * (bins of g) (integer
+    exact), row indices strictly ascend within a column, no stored zero, the column pointer is
+    the running count, and a second pass over the same buffers gives byte-identical output."""
+    import ctypes as C
+    import torch
+    import bench
+    from clonalscope_b200 import synth
+    dev = torch.device("cuda", 0)
+    L = cs.lib()
+    N, G = 100000, 30000
+    bins, genes = synth.geometry(G=G)
+    mp, mb = synth.geometry_map(bins, genes)
+    B = len(bins["chr"])
+    colptr, rowidx, x = bench.synth_counts_gpu(torch, dev, N, G, seed=4242)
+    dp = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    plan = C.c_void_p()
+    assert L.cs_bin_plan_create(G, B, dp(mp, C.c_int32), dp(mb, C.c_int32), C.byref(plan)) == 0
+    try:
+        ocp = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        nnz = C.c_int64()
+        assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp), None, None, 0, C.byref(nnz), None) == 0
+        cap = nnz.value
+        ori = torch.empty(cap, dtype=torch.int32, device=dev)
+        ox = torch.empty(cap, dtype=torch.float64, device=dev)
+        assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp), vp(ori), vp(ox), cap, C.byref(nnz), None) == 0, L.cs_last_error()
+        assert nnz.value == cap == int(ocp[-1])
+        assert bool((ocp[1:] >= ocp[:-1]).all()) and int(ocp[0]) == 0
+        assert bool((ox != 0).all()) and bool((ox == ox.round()).all())
+        assert int(ori.min()) >= 0 and int(ori.max()) < B
+        # strictly ascending bins within each column
+        col_of_out = torch.repeat_interleave(torch.arange(N, device=dev), (ocp[1:] - ocp[:-1]))
+        same_col = col_of_out[1:] == col_of_out[:-1]
+        assert bool((ori[1:][same_col] > ori[:-1][same_col]).all())
+        # per-column sums: sum of outputs == sum_g x_g * nh_g (all values are small integers: exact in FP64)
+        nh = torch.from_numpy(np.diff(mp).astype(np.float64)).to(dev)
+        col_of_in = torch.repeat_interleave(torch.arange(N, device=dev), (colptr[1:] - colptr[:-1]))
+        want = torch.zeros(N, dtype=torch.float64, device=dev).index_add_(0, col_of_in, x * nh[rowidx.long()])
+        got = torch.zeros(N, dtype=torch.float64, device=dev).index_add_(0, col_of_out, ox)
+        assert bool((want == got).all())
+        # per-bin totals over all cells (a checksum of checksums across the other axis)
+        first = torch.from_numpy(mb[mp[:-1].clip(max=len(mb) - 1)].astype(np.int64)).to(dev)
+        hits_g = torch.zeros(G, dtype=torch.float64, device=dev).index_add_(0, rowidx.long(), x)
+        want_bins = torch.zeros(B + 32, dtype=torch.float64, device=dev)
+        for k in range(int(np.diff(mp).max())):
+            sel = torch.from_numpy((np.diff(mp) > k)).to(dev)
+            want_bins.index_add_(0, (first + k)[sel], hits_g[sel])
+        got_bins = torch.zeros(B + 32, dtype=torch.float64, device=dev).index_add_(0, ori.long(), ox)
+        assert bool((want_bins == got_bins).all())
+        # idempotence: the same call again gives the same bytes
+        ori2, ox2, ocp2 = torch.empty_like(ori), torch.empty_like(ox), torch.zeros_like(ocp)
+        assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp2), vp(ori2), vp(ox2), cap, C.byref(nnz), None) == 0
+        assert torch.equal(ocp, ocp2) and torch.equal(ori, ori2) and torch.equal(ox, ox2)
+    finally:
+        L.cs_bin_plan_destroy(plan)
+
+
+def test_full_size_sampler_properties(cs):
+    """100k cells x 300 segments (the bench workload), a few event-dense sweeps: the speculative
+    walk (resident window, cluster helpers) and the plainly sequential kernel give the SAME chain,
+    and the chain's book-keeping is consistent."""
+    from clonalscope_b200 import synth
+    N, R, niter = 100000, 300, 5
+    s = synth.sampler_input(N, R=R)
+    kw = dict(alpha=2.0, beta=2.0, niter=niter, sigmas0=s["sigmas0"], U0=s["U0"], seed=200, rng="philox")
+    a = cs.BayesNonparCluster(s["X"], **kw)
+    b = cs.BayesNonparCluster(s["X"], _flags=1, **kw)
+    Za, Zb = a["results"]["Zall"], b["results"]["Zall"]
+    assert np.array_equal(Za, Zb)
+    assert np.array_equal(a["results"]["Likelihood"], b["results"]["Likelihood"])
+    for ua, ub in zip(a["results"]["Uall"], b["results"]["Uall"]):
+        assert np.array_equal(ua, ub, equal_nan=True)
+    kt = [u.shape[0] for u in a["results"]["Uall"]]
+    assert all(k2 >= k1 for k1, k2 in zip(kt, kt[1:]))                # labels are never renumbered
+    for t in range(niter):
+        z = Za[t]
+        assert z.min() >= 1 and z.max() <= kt[t]
+        live = np.nonzero(~np.isnan(a["results"]["Uall"][t][:, 0]))[0] + 1
+        assert set(np.unique(z)) == set(live)                          # occupied clusters == non-NA rows
+        assert np.isfinite(a["results"]["Likelihood"][t])
+        sg = np.asarray(a["results"]["sigma_all"][t])
+        assert np.all(np.isfinite(sg)) and np.all(sg > 0)
+    moved = sum(int((Za[t] != Za[t - 1]).sum()) for t in range(1, niter))
+    assert moved > 30000                                               # the sweeps really are event-dense
