@@ -7,6 +7,7 @@ fallback: every entry point raises if the library or a CUDA device is missing.
 """
 from .api import (  # noqa: F401
     Gen_bin_cell_rna_filtered,
+    EstRegionCov,
     PrepCovMatrix,
     BayesNonparCluster,
     BayesNonparAlleleCluster,
@@ -18,7 +19,7 @@ from .api import (  # noqa: F401
 from ._lib import lib, build_library, library_path  # noqa: F401
 
 __all__ = [
-    "Gen_bin_cell_rna_filtered", "PrepCovMatrix", "BayesNonparCluster", "BayesNonparAlleleCluster",
+    "Gen_bin_cell_rna_filtered", "EstRegionCov", "PrepCovMatrix", "BayesNonparCluster", "BayesNonparAlleleCluster",
     "MCMCtrim", "majority_vote", "loglik_matrix", "ClonalscopeError", "lib", "build_library",
     "library_path",
 ]

@@ -22,7 +22,7 @@ SYMBOLS = [
     "cs_chain_sweeps_done", "cs_chain_timing", "cs_chain_stats", "cs_chain_fetch", "cs_chain_destroy",
     "cs_ncrp_gibbs_allele",
     "cs_majority_vote", "cs_majority_vote_dev",
-    "cs_cluster_stats_dev", "cs_sigma_stats_dev",
+    "cs_cluster_stats_dev", "cs_sigma_stats_dev", "cs_gene_moments",
 ]
 
 

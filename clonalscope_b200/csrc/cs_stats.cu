@@ -71,7 +71,48 @@ sigma_stats_kernel(int N, int R, int K, const double *__restrict__ X, const int 
     }
 }
 
+// per-gene sums and sums of squares over the cells of a CSC (gene x cell) matrix — the inputs
+// of the variance filter of EstRegionCov (R/EstRegionCov.R:42-48) without densifying the matrix.
+// Integer counts give exact, order-free FP64 sums (below 2^53).
+__global__ void gene_moments_kernel(int64_t nnz, const int32_t *__restrict__ rowidx, const double *__restrict__ x,
+                                    double *__restrict__ sum, double *__restrict__ sumsq)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[e];
+        const int g = rowidx[e];
+        atomicAdd(sum + g, v);
+        atomicAdd(sumsq + g, v * v);
+    }
+}
+
 } // namespace
+
+// host (R layout) form: the dgCMatrix slots @i @x of a G x N matrix with nnz entries
+extern "C" int cs_gene_moments(int G, int64_t nnz, const int32_t *rowidx, const double *x, double *sum, double *sumsq)
+{
+    CS_REQUIRE(G >= 0 && nnz >= 0 && sum && sumsq && (nnz == 0 || (rowidx && x)), "cs_gene_moments: bad arguments");
+    for (int64_t e = 0; e < nnz; e++)
+        CS_REQUIRE(rowidx[e] >= 0 && rowidx[e] < G, "cs_gene_moments: rowidx[%lld]=%d outside [0,%d)", (long long)e, rowidx[e], G);
+    DevBuf<int32_t> d_i;
+    DevBuf<double> d_x, d_s, d_q;
+    CS_CUDA(d_i.alloc((size_t)nnz));
+    CS_CUDA(d_x.alloc((size_t)nnz));
+    CS_CUDA(d_s.alloc((size_t)G));
+    CS_CUDA(d_q.alloc((size_t)G));
+    CS_CUDA(cudaMemset(d_s.p, 0, sizeof(double) * (size_t)(G > 0 ? G : 1)));
+    CS_CUDA(cudaMemset(d_q.p, 0, sizeof(double) * (size_t)(G > 0 ? G : 1)));
+    if (nnz) {
+        CS_CUDA(cudaMemcpy(d_i.p, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CS_CUDA(cudaMemcpy(d_x.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+        gene_moments_kernel<<<cs_num_sms() * 8, 256>>>(nnz, d_i.p, d_x.p, d_s.p, d_q.p);
+        CS_CUDA(cudaGetLastError());
+    }
+    if (G) {
+        CS_CUDA(cudaMemcpy(sum, d_s.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost));
+        CS_CUDA(cudaMemcpy(sumsq, d_q.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost));
+    }
+    return CS_OK;
+}
 
 extern "C" int cs_cluster_stats_dev(int N, int R, int K, const double *d_X, const int *d_Z, double *d_sum_x,
                                     double *d_cnt_x, double *d_nk, void *stream)

@@ -201,6 +201,14 @@ int cs_cluster_stats_dev(int N, int R, int K, const double *d_X, const int *d_Z,
 int cs_sigma_stats_dev(int N, int R, int K, const double *d_X, const int *d_Z,
                        const double *d_U, double *d_sq, double *d_cnt, void *stream);
 
+/* ------------------------------------------------------------------------
+ * per-gene sums and sums of squares over the cells of a G x N dgCMatrix (slots @i @x, nnz
+ * entries) — what the variance filter of EstRegionCov needs (replaces the dense
+ * `apply(mtx, 1, var)` / `rowSums` of R/EstRegionCov.R:42-43; the per-segment and library-size
+ * column sums of :88-159 go through cs_bin_counts_* with a gene -> segment map).
+ * ---------------------------------------------------------------------- */
+int cs_gene_moments(int G, int64_t nnz, const int32_t *rowidx, const double *x, double *sum, double *sumsq);
+
 #ifdef __cplusplus
 }
 #endif

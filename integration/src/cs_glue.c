@@ -101,11 +101,26 @@ SEXP cs_R_majority_vote(SEXP Zall)
     return z;
 }
 
+/* .Call("cs_R_gene_moments", i, x, G): list(sum, sumsq), one entry per gene (EstRegionCov :42-43) */
+SEXP cs_R_gene_moments(SEXP i, SEXP x, SEXP G)
+{
+    const int g = Rf_asInteger(G);
+    SEXP s = PROTECT(Rf_allocVector(REALSXP, g)), q = PROTECT(Rf_allocVector(REALSXP, g));
+    int rc = cs_gene_moments(g, (int64_t)XLENGTH(x), INTEGER(i), REAL(x), REAL(s), REAL(q));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, s);
+    SET_VECTOR_ELT(out, 1, q);
+    UNPROTECT(3);
+    check(rc);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
     {"cs_R_loglik_matrix", (DL_FUNC)&cs_R_loglik_matrix, 3},
     {"cs_R_bin_counts", (DL_FUNC)&cs_R_bin_counts, 7},
     {"cs_R_ncrp_gibbs", (DL_FUNC)&cs_R_ncrp_gibbs, 10},
     {"cs_R_majority_vote", (DL_FUNC)&cs_R_majority_vote, 1},
+    {"cs_R_gene_moments", (DL_FUNC)&cs_R_gene_moments, 3},
     {NULL, NULL, 0}};
 
 void R_init_Clonalscope(DllInfo *dll)

@@ -238,3 +238,108 @@ def bin_counts_dense(G, N, B, colptr, rowidx, x, map_ptr, map_bin):
                                _p(x, C.c_double), _p(map_ptr, C.c_int32), _p(map_bin, C.c_int32),
                                _p(out, C.c_double))
     return out.T  # B x N
+
+
+def _r_num_str(v):
+    """as.character() of a numeric scalar the way paste0() prints it (0.99 -> '0.99', 1 -> '1')."""
+    f = float(v)
+    return str(int(f)) if f == int(f) else repr(f)
+
+
+def est_region_cov(mtx, barcodes, features, bed, celltype0=None, var_pt=0.99, var_pt_ctrl=0.99, ngene_filter=0,
+                   include="tumor", alpha_source="all", ctrl_region=None, seg_table=None, size=None):
+    """Restatement of EstRegionCov (reference R/EstRegionCov.R:24-209), dense and line by line;
+    test infrastructure only.  `mtx`: G x N array; `bed`: list of 4 columns (chr, start, end, gene id);
+    `celltype0`: (barcodes, types) or None; `seg_table`: dict(chr, start, end, chrr) or None with
+    `size` = (chromosome names, lengths).  Column sums are accumulated in long double like R's
+    colSums.  Returns dict(deltas_all=[(name, cell names, values)], ngenes, sel, alpha, barcodes_normal)."""
+    mtx = np.asarray(mtx, dtype=np.float64)
+    barcodes = [str(b) for b in barcodes]
+    features = [str(f) for f in features]
+    bchr = [str(c) for c in bed[0]]
+    if "chr" not in bchr[0]:                                            # :28-30
+        bchr = ["chr" + c for c in bchr]
+    bstart = np.asarray(bed[1], dtype=np.float64)
+    bend = np.asarray(bed[2], dtype=np.float64)
+    bgene = [str(g) for g in bed[3]]
+    if celltype0 is None:                                               # :32-34
+        celltype0 = (list(barcodes), ["normal"] * len(barcodes))
+    ct_bar = [str(b) for b in celltype0[0]]
+    ct_type = np.asarray([str(t) for t in celltype0[1]])
+    col_of = {b: i for i, b in reversed(list(enumerate(barcodes)))}     # match(): first occurrence
+    mtx = mtx[:, [col_of[b] for b in ct_bar]]                           # :40
+    N = mtx.shape[1]
+    mean = mtx.astype(np.longdouble).sum(axis=1) / N                    # :42 var(): two passes, long double
+    rna_var = np.asarray((((mtx.astype(np.longdouble) - mean[:, None]) ** 2).sum(axis=1) / (N - 1)), dtype=np.float64)
+    ngenes_row = np.asarray(mtx.astype(np.longdouble).sum(axis=1), dtype=np.float64)
+    q = np.quantile(rna_var, var_pt)                                    # :47 type 7
+    qc = np.quantile(rna_var, var_pt_ctrl)
+    keep = np.nonzero((rna_var < q) & (rna_var != 0) & (ngenes_row > ngene_filter))[0]
+    keep_c = np.nonzero((rna_var < qc) & (rna_var != 0) & (ngenes_row > ngene_filter))[0]
+    rna, rna_control = mtx[keep], mtx[keep_c]
+    first = {}
+    for i, g in enumerate(bgene):
+        first.setdefault(g, i)
+    sub_chr, sub_s, sub_e = [], [], []
+    for k in keep:                                                      # :51-52 (unmatched genes: all-zero row)
+        j = first.get(features[k])
+        sub_chr.append(bchr[j] if j is not None else "0")
+        sub_s.append(bstart[j] if j is not None else 0.0)
+        sub_e.append(bend[j] if j is not None else 0.0)
+    sub_chr = np.asarray(sub_chr)
+    sub_s, sub_e = np.asarray(sub_s), np.asarray(sub_e)
+    est_name = f"pt{_r_num_str(var_pt)}_{include}_alpha{alpha_source}"  # :60
+    if seg_table is None:                                               # :63-67
+        names = [str(s) for s in size[0]][:22]
+        seg_table = dict(chr=[n.replace("chr", "") for n in names], start=[0.0] * len(names),
+                         end=[float(v) for v in list(size[1])[:22]], chrr=names)
+    seg_chr = [str(c) for c in seg_table["chr"]]
+    seg_s = np.asarray(seg_table["start"], dtype=np.float64)
+    seg_e = np.asarray(seg_table["end"], dtype=np.float64)
+    seg_name = [str(c) for c in seg_table["chrr"]]
+    out, ngenes, sel = [], [], []
+    alphas = None
+    barcodes_normal = None
+    for chrr in seg_name:                                               # :80
+        gene_ind = []
+        for r in [i for i, n in enumerate(seg_name) if n == chrr]:      # findOverlaps, type "any"
+            hit = np.nonzero((sub_chr == "chr" + seg_chr[r]) & (sub_s <= seg_e[r]) & (sub_e >= seg_s[r]) & (sub_s <= sub_e))[0]
+            gene_ind.extend(hit.tolist())
+        rna_sub = rna[gene_ind]
+        colsum = np.asarray(rna_sub.astype(np.longdouble).sum(axis=0), dtype=np.float64)
+        sel_cell = np.nonzero(colsum > 0)[0]                            # :93
+        if len(sel_cell) == 0:
+            continue
+        sel.append(chrr)
+        rna_sub = rna_sub[:, sel_cell]
+        types = ct_type[sel_cell]
+        normal = np.nonzero(types == "normal")[0]
+        tumor = np.nonzero(types == "tumor")[0]
+        barcodes_normal = [ct_bar[i] for i in sel_cell[normal]]
+        control = rna_sub[:, normal]
+        if include == "tumor":
+            tsel = tumor
+        elif include == "control":
+            tsel = normal
+        elif include == "all":
+            tsel = np.arange(len(sel_cell))
+        else:
+            raise ValueError("include variable is not valid!")
+        test = rna_sub[:, tsel]
+        if alpha_source == "all":                                       # :131-133
+            alphas = np.asarray(rna_control[:, sel_cell].astype(np.longdouble).sum(axis=0), dtype=np.float64)
+        elif alpha_source == "control":
+            rows = np.nonzero(np.isin(sub_chr, list(ctrl_region)))[0]
+            alphas = np.asarray(rna[rows][:, sel_cell].astype(np.longdouble).sum(axis=0), dtype=np.float64)
+        else:
+            raise ValueError("alpha_source is not valid!")
+        med = np.median(alphas)
+        a_ctrl = alphas[normal] / med                                   # :141
+        a_test = alphas[tsel] / med
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tsum = np.asarray((test / a_test[None, :]).astype(np.longdouble).sum(axis=0), dtype=np.float64)
+            csum = np.asarray((control / a_ctrl[None, :]).astype(np.longdouble).sum(axis=0), dtype=np.float64)
+            deltas = tsum / (np.median(csum) if len(csum) else np.nan)  # :159
+        out.append((est_name + chrr, [ct_bar[i] for i in sel_cell[tsel]], deltas))
+        ngenes.append((est_name + chrr, len(gene_ind)))
+    return dict(deltas_all=out, ngenes=ngenes, sel=sel, alpha=alphas, barcodes_normal=barcodes_normal)

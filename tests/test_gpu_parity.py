@@ -544,3 +544,83 @@ def test_full_size_sampler_properties(cs):
         assert np.all(np.isfinite(sg)) and np.all(sg > 0)
     moved = sum(int((Za[t] != Za[t - 1]).sum()) for t in range(1, niter))
     assert moved > 30000                                               # the sweeps really are event-dense
+
+
+# ------------------------------------------------------------------ a7: EstRegionCov
+def _region_cov_case(seed, G=500, N=320, nseg=9):
+    rng = np.random.default_rng(seed)
+    lam = rng.lognormal(-1.0, 1.0, size=G)
+    mtx = rng.poisson(lam[:, None] * rng.lognormal(0, 0.3, size=N)[None, :]).astype(np.float64)
+    mtx[rng.choice(G, 12, replace=False)] = 0.0                  # genes without a single read
+    mtx[:, rng.choice(N, 3, replace=False)] *= 0                 # empty cells
+    barcodes = [f"AAAC{i:05d}-1" for i in range(N)]
+    features = [f"ENSG{i:08d}" for i in range(G)]
+    chrom = np.sort(rng.integers(1, 5, size=G))
+    start = np.zeros(G, dtype=np.int64)
+    for c in range(1, 5):
+        sel = chrom == c
+        start[sel] = np.sort(rng.integers(1000, 2_000_000, size=int(sel.sum())))
+    end = start + rng.integers(500, 60_000, size=G)
+    order = rng.permutation(G)                                   # the bed file is not in matrix order
+    bed = np.empty((G - 7, 4), dtype=object)                     # ... and misses a few genes
+    o2 = order[:G - 7]
+    bed[:, 0], bed[:, 1], bed[:, 2], bed[:, 3] = [str(c) for c in chrom[o2]], start[o2], end[o2], [features[i] for i in o2]
+    perm = rng.permutation(N)
+    celltype0 = np.empty((N - 5, 2), dtype=object)               # a subset of the cells, shuffled
+    celltype0[:, 0] = [barcodes[i] for i in perm[:N - 5]]
+    celltype0[:, 1] = rng.choice(["tumor", "normal"], size=N - 5, p=[0.7, 0.3])
+    seg = dict(chr=[], start=[], end=[], chrr=[], states=[])
+    for c in range(1, 5):
+        cuts = np.sort(rng.choice(np.arange(50_000, 1_950_000, 10_000), size=nseg // 4, replace=False))
+        edges = [0] + list(cuts) + [2_100_000]
+        for a, b_ in zip(edges[:-1], edges[1:]):
+            seg["chr"].append(str(c)), seg["start"].append(float(a)), seg["end"].append(float(b_))
+            seg["chrr"].append(f"chr{c}_{a}_{b_}"), seg["states"].append(int(rng.integers(0, 3)))
+    seg["chr"].append("7"), seg["start"].append(0.0), seg["end"].append(1e6), seg["chrr"].append("chr7_0_1e6"), seg["states"].append(1)
+    return mtx, barcodes, features, bed, celltype0, seg
+
+
+@pytest.mark.parametrize("include,alpha_source,seed", [("tumor", "all", 1), ("all", "control", 2), ("control", "all", 3)])
+def test_est_region_cov_vs_oracle(cs, oracle, include, alpha_source, seed):
+    """Device moments + segment aggregation vs the dense, line-by-line restatement: the same genes
+    pass the filter, the same cells are selected per segment, deltas agree to 1e-12 (the reference
+    divides every count by its cell's alpha before summing, here the integer sum is divided)."""
+    import scipy.sparse as sp
+    from clonalscope_b200.api import EstRegionCov
+    mtx, barcodes, features, bed, celltype0, seg = _region_cov_case(seed)
+    kw = dict(var_pt=0.97, var_pt_ctrl=0.95, ngene_filter=1, include=include, alpha_source=alpha_source,
+              ctrl_region=["chr1", "chr3"])
+    got = EstRegionCov(mtx=sp.csc_matrix(mtx), barcodes=np.asarray(barcodes, dtype=object).reshape(-1, 1),
+                       features=np.asarray(features, dtype=object).reshape(-1, 1), bed=bed, celltype0=celltype0,
+                       seg_table_filtered=seg, **kw)
+    want = oracle.est_region_cov(mtx, barcodes, features, [bed[:, 0], bed[:, 1], bed[:, 2], bed[:, 3]],
+                                 (list(celltype0[:, 0]), list(celltype0[:, 1])), seg_table=seg, **kw)
+    assert list(got["deltas_all"].keys()) == [n for n, _, _ in want["deltas_all"]]
+    assert len(want["deltas_all"]) >= 8
+    for name, cells, vals in want["deltas_all"]:
+        gc, gv = got["deltas_all"][name]
+        assert gc == cells
+        np.testing.assert_allclose(gv, vals, rtol=1e-12, equal_nan=True)
+    assert list(got["ngenes"].items()) == want["ngenes"]
+    assert got["seg_table_filtered"]["chrr"] == want["sel"] and "chr7_0_1e6" not in want["sel"]
+    assert got["barcodes_normal"] == want["barcodes_normal"]
+    np.testing.assert_allclose(got["alpha"], want["alpha"], rtol=0, atol=0)
+
+
+def test_est_region_cov_default_segments_and_errors(cs, oracle):
+    import scipy.sparse as sp
+    from clonalscope_b200.api import EstRegionCov
+    mtx, barcodes, features, bed, celltype0, _ = _region_cov_case(5)
+    size = np.empty((24, 2), dtype=object)
+    size[:, 0] = [f"chr{c}" for c in range(1, 25)]
+    size[:, 1] = [2_100_000] * 24
+    got = EstRegionCov(mtx=sp.csc_matrix(mtx), barcodes=barcodes, features=features, bed=bed, celltype0=None, size=size)
+    want = oracle.est_region_cov(mtx, barcodes, features, [bed[:, 0], bed[:, 1], bed[:, 2], bed[:, 3]], None,
+                                 size=(list(size[:, 0]), list(size[:, 1])))
+    assert list(got["deltas_all"].keys()) == [n for n, _, _ in want["deltas_all"]] == \
+        [f"pt0.99_tumor_alphaallchr{c}" for c in range(1, 5)]
+    for name, cells, vals in want["deltas_all"]:
+        assert got["deltas_all"][name][0] == cells == []           # no tumor cell without a celltype table
+    assert got["ngenes"] == dict(want["ngenes"])
+    with pytest.raises(ValueError):
+        EstRegionCov(mtx=sp.csc_matrix(mtx), barcodes=barcodes, features=features, bed=bed, size=size, include="both")

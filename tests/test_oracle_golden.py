@@ -103,3 +103,25 @@ def test_r_rng_known_answers(oracle):
     z = oracle.mt_rnorm(42, [0.0, 0.0], [1.0, 1.0])
     np.testing.assert_allclose(z, [1.37095845, -0.56469817], atol=5e-8)
     assert oracle.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+def test_est_region_cov_restatement_small_case(oracle):
+    """EstRegionCov restatement (R/EstRegionCov.R:24-209) against the formula written out by hand
+    on a case small enough to follow: one segment, no gene filtered by variance."""
+    mtx = np.array([[1, 0, 2, 3], [0, 1, 1, 0], [2, 2, 0, 1], [5, 0, 0, 0.]])
+    barcodes, features = ["a", "b", "c", "d"], ["g1", "g2", "g3", "g4"]
+    bed = [["chr1", "chr1", "chr1", "chr2"], [10, 200, 500, 10], [100, 300, 600, 90], features]
+    ct = (["d", "c", "b", "a"], ["tumor", "normal", "normal", "tumor"])          # reorders the cells
+    res = oracle.est_region_cov(mtx, barcodes, features, bed, ct, var_pt=1.0, var_pt_ctrl=1.0,
+                                seg_table=dict(chr=["1"], start=[0.0], end=[250.0], chrr=["chr1_0_250"]))
+    # var < quantile(var, 1) drops the most variable gene (g4: var of (0,0,0,5)); g1, g2 overlap [0, 250]
+    m = mtx[:3][:, [3, 2, 1, 0]]
+    seg = m[:2].sum(axis=0)                  # cells d, c, b, a -> 3, 3, 1, 1
+    alphas = m.sum(axis=0)                   # library size over the kept genes
+    med = np.median(alphas)
+    ctrl = seg[[1, 2]] / (alphas[[1, 2]] / med)
+    want = (seg[[0, 3]] / (alphas[[0, 3]] / med)) / np.median(ctrl)
+    (name, cells, vals), = res["deltas_all"]
+    assert name == "pt1_tumor_alphaallchr1_0_250" and cells == ["d", "a"]
+    np.testing.assert_allclose(vals, want, rtol=1e-15)
+    assert res["ngenes"] == [(name, 2)] and res["barcodes_normal"] == ["c", "b"]
