@@ -385,6 +385,46 @@ def run_ours(a):
                           h2d_bytes=int(cp_h.nbytes + ri_h.nbytes + x_h.nbytes), d2h_bytes=int(ocp.nbytes + ori.nbytes + ox.nbytes))
     L.cs_bin_plan_destroy(plan)
 
+    # ---------------- EstRegionCov (a7) end to end with host buffers on the same count matrix
+    region = None
+    if rank == 0 and world == 1 and not a.no_region:
+        import scipy.sparse as sp
+        from clonalscope_b200.api import EstRegionCov
+        rng = np.random.default_rng(77)
+        mtx = sp.csc_matrix((x_h, ri_h, cp_h), shape=(G, nb2))
+        feats = [f"g{i}" for i in range(G)]
+        bars = [f"c{i}" for i in range(nb2)]
+        bed = np.empty((G, 4), dtype=object)
+        bed[:, 0], bed[:, 1], bed[:, 2], bed[:, 3] = [str(int(c)) for c in genes["chr"]], genes["start"], genes["end"], feats
+        ct = np.empty((nb2, 2), dtype=object)
+        ct[:, 0], ct[:, 1] = bars, rng.choice(["tumor", "normal"], size=nb2, p=[0.7, 0.3])
+        seg = dict(chr=[], start=[], end=[], chrr=[])
+        for c, size_c in enumerate(synth.CHR_SIZES):
+            nseg = 14 if c < 14 else 13          # 300 segments in all
+            edges = np.linspace(0, size_c, nseg + 1)
+            for lo_, hi_ in zip(edges[:-1], edges[1:]):
+                seg["chr"].append(str(c + 1)), seg["start"].append(float(lo_)), seg["end"].append(float(hi_))
+                seg["chrr"].append(f"chr{c + 1}_{int(lo_)}_{int(hi_)}")
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            EstRegionCov(mtx, bars, feats, bed, ct, seg_table_filtered=seg)
+            t0 = time.perf_counter()
+            out_rc = EstRegionCov(mtx, bars, feats, bed, ct, seg_table_filtered=seg)
+            rdt = time.perf_counter() - t0
+        region = dict(cells=nb2, genes=G, segments=len(out_rc["deltas_all"]), ms=rdt * 1e3,
+                      cells_per_s=nb2 / rdt, note="EstRegionCov through the host API (scipy CSC in, per-segment deltas out)")
+        if not a.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as O2
+            ncpu = min(nb2, 100)
+            dense = np.asarray(mtx[:, :ncpu].todense())
+            t0 = time.perf_counter()
+            O2.est_region_cov(dense, bars[:ncpu], feats, [bed[:, 0], bed[:, 1], bed[:, 2], bed[:, 3]],
+                              (bars[:ncpu], list(ct[:ncpu, 1])), seg_table=seg)
+            cdt = time.perf_counter() - t0
+            region["cpu_cells_per_s"] = ncpu / cdt
+            region["cpu_sample"] = f"dense restatement of the reference, {ncpu} cells, 1 core"
+
     # ---------------- CPU baseline on the box's host cores (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -432,6 +472,8 @@ def run_ours(a):
             binning=binning, clocks=clocks)
         if conc:
             line["concurrent_chains"] = conc
+        if region:
+            line["region_cov"] = region
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -448,6 +490,7 @@ def main():
     ap.add_argument("--cells", type=int, default=100000)
     ap.add_argument("--segs", type=int, default=300)
     ap.add_argument("--niter", type=int, default=200)
+    ap.add_argument("--no-region", action="store_true", help="skip the EstRegionCov leg")
     ap.add_argument("--chains", type=int, default=8, help="independent chains run concurrently (supplementary; 1 = skip)")
     ap.add_argument("--genes", type=int, default=30000)
     ap.add_argument("--bin-cells", type=int, default=100000)
