@@ -1743,12 +1743,27 @@ __global__ void compact_kernel(ChainDev D, int *__restrict__ rej, int reject_liv
 
 // CTAs in the resident-window walk's cluster (0: the kernel cannot run with this much shared
 // memory): the largest of 16, 8, 4, 2, 1 the device co-schedules.  Worked out once per shape.
+// (function attributes and what a device co-schedules are per device: the caches below are
+//  indexed by the current device; host threads may race to fill an entry with the same value)
+constexpr int MAX_DEVICES = 64;
+inline int current_device()
+{
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+    return d;
+}
+
 template <int NCH>
 int ring_cluster_size(size_t smem)
 {
-    static size_t known_smem = 0;
-    static int known = -1;
-    if (known >= 0 && known_smem == smem) return known;
+    static size_t known_smem_d[MAX_DEVICES] = {};
+    static int known_d[MAX_DEVICES] = {};
+    static bool have_d[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (have_d[dev] && known_smem_d[dev] == smem) return known_d[dev];
+    size_t &known_smem = known_smem_d[dev];
+    int &known = known_d[dev];
+    have_d[dev] = true;
     known_smem = smem;
     known = 0;
     if (smem > 227 * 1024) return 0;
@@ -1789,7 +1804,9 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
 {
     const size_t smem_prep = sizeof(double) * D.R + sizeof(int) * D.kcap;
     const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap + 64 * WIN_CELLS) + sizeof(int) * 3 * D.kcap + 16;
-    static size_t attr_scan = 0, attr_prep = 0; // (function attributes are set when the sizes change, not every sweep)
+    // (function attributes are set when the sizes change, not every sweep)
+    static size_t attr_scan_d[MAX_DEVICES] = {}, attr_prep_d[MAX_DEVICES] = {};
+    size_t &attr_scan = attr_scan_d[current_device()], &attr_prep = attr_prep_d[current_device()];
     if (attr_scan != smem_scan || attr_prep != smem_prep) {
         CS_CUDA(cudaFuncSetAttribute(scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         if (smem_scan > 48 * 1024) {
@@ -1870,7 +1887,8 @@ int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej
     // (a thread per segment; 72 KB of accumulators = 20 clusters of 300 segments per pass, three CTAs per SM)
     const int stat_smem = 72 * 1024;
     const int seg_threads = D.R >= 1024 ? 1024 : (D.R < 64 ? 64 : ((D.R + 31) / 32) * 32);
-    static bool attr_stats = false;
+    static bool attr_stats_d[MAX_DEVICES] = {};
+    bool &attr_stats = attr_stats_d[current_device()];
     if (!attr_stats) {
         CS_CUDA(cudaFuncSetAttribute(stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stat_smem));
         attr_stats = true;

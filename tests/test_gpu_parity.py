@@ -624,3 +624,19 @@ def test_est_region_cov_default_segments_and_errors(cs, oracle):
     assert got["ngenes"] == dict(want["ngenes"])
     with pytest.raises(ValueError):
         EstRegionCov(mtx=sp.csc_matrix(mtx), barcodes=barcodes, features=features, bed=bed, size=size, include="both")
+
+
+def test_chains_on_two_devices_from_one_process(cs):
+    """`device=` selects the GPU per call; per-device kernel attributes must follow (needs 2 GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(3000, R=300, seed=9, K_true=6)
+    kw = dict(alpha=2.0, beta=2.0, niter=6, sigmas0=s["sigmas0"], U0=s["U0"], seed=11, rng="philox")
+    a = cs.BayesNonparCluster(s["X"], device=0, **kw)
+    b = cs.BayesNonparCluster(s["X"], device=1, **kw)
+    c = cs.BayesNonparCluster(s["X"], device=0, **kw)
+    assert np.array_equal(a["results"]["Zall"], b["results"]["Zall"])
+    assert np.array_equal(a["results"]["Zall"], c["results"]["Zall"])
+    assert np.array_equal(a["results"]["Likelihood"], b["results"]["Likelihood"])
