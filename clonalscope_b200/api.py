@@ -283,8 +283,13 @@ def PrepCovMatrix(deltas_all=None, ngene_filter=200, ncell_filter=None, prep_mod
     chr/start/end).  Returns dict(df=NamedMatrix N x R, ngene_filter, ncell_filter,
     seg_table_filtered).
     """
-    df = list(deltas_all["deltas_all"])
-    ngenes = np.asarray(deltas_all["ngenes"])
+    df, ngenes = deltas_all["deltas_all"], deltas_all["ngenes"]
+    if isinstance(df, dict):            # EstRegionCov's named list: one (names, values) pair per segment
+        df = list(df.values())
+    if isinstance(ngenes, dict):
+        ngenes = list(ngenes.values())
+    df = list(df)
+    ngenes = np.asarray(ngenes)
     seg = {k: np.asarray(v) for k, v in deltas_all["seg_table_filtered"].items()}
     if ncell_filter is None:
         ncells = np.array([len(n) for n, _ in df], dtype=np.float64)

@@ -640,3 +640,37 @@ def test_chains_on_two_devices_from_one_process(cs):
     assert np.array_equal(a["results"]["Zall"], b["results"]["Zall"])
     assert np.array_equal(a["results"]["Zall"], c["results"]["Zall"])
     assert np.array_equal(a["results"]["Likelihood"], b["results"]["Likelihood"])
+
+
+def test_region_cov_feeds_prep_and_the_sampler(cs):
+    """a7 -> a2 -> a3 on one synthetic sample: EstRegionCov's output is what PrepCovMatrix takes, and
+    the coverage matrix it builds separates a planted gain when clustered."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(12)
+    G, N = 1200, 600
+    chrom = np.sort(rng.integers(1, 4, size=G))
+    start = np.concatenate([np.sort(rng.integers(1, 3_000_000, size=int((chrom == c).sum()))) for c in (1, 2, 3)])
+    lam = rng.lognormal(0.3, 0.6, size=G)
+    tumor = np.arange(N) >= 200
+    gain = (chrom == 2)[:, None] & (tumor & (np.arange(N) % 2 == 0))[None, :]      # half of the tumor cells gain chr2
+    mtx = rng.poisson(lam[:, None] * np.where(gain, 1.6, 1.0) * rng.lognormal(0, 0.2, size=N)[None, :]).astype(np.float64)
+    feats = [f"g{i}" for i in range(G)]
+    bars = [f"c{i}" for i in range(N)]
+    bed = np.empty((G, 4), dtype=object)
+    bed[:, 0], bed[:, 1], bed[:, 2], bed[:, 3] = [str(c) for c in chrom], start, start + 5000, feats
+    ct = np.empty((N, 2), dtype=object)
+    ct[:, 0], ct[:, 1] = bars, np.where(tumor, "tumor", "normal")
+    seg = dict(chr=["1", "2", "3"], start=[0.0, 0.0, 0.0], end=[4e6, 4e6, 4e6], chrr=["chr1", "chr2", "chr3"],
+               states=[1, 1.5, 1])
+    est = cs.EstRegionCov(sp.csc_matrix(mtx), bars, feats, bed, ct, seg_table_filtered=seg)
+    prep = cs.PrepCovMatrix(est, ngene_filter=50)
+    X = prep["df"]
+    assert X.values.shape == (400, 3) and X.colnames == ["chr1-0-4e+06", "chr2-0-4e+06", "chr3-0-4e+06"]
+    out = cs.BayesNonparCluster(X.values, cna_states_WGS=np.array([1, 1.5, 1.0]), niter=40, rng="philox", seed=3)
+    z = cs.majority_vote(cs.MCMCtrim(out)["results"]["Zall"])
+    planted = (np.arange(200, 600) % 2 == 0).astype(int)
+    ratio = np.nanmean(X.values[planted == 1, 1]) / np.nanmean(X.values[planted == 0, 1])
+    assert 1.25 < ratio < 1.5      # the planted 1.6x gain of chr2, diluted by its own share of the library size (1.6 / 1.2)
+    purity = sum(max(int(((z == k) & (planted == 1)).sum()), int(((z == k) & (planted == 0)).sum()))
+                 for k in np.unique(z)) / len(z)
+    assert purity > 0.9                                                    # clusters do not mix the two groups
