@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     BayesNonparCluster,
     BayesNonparAlleleCluster,
     MCMCtrim,
+    AssignCluster,
     majority_vote,
     loglik_matrix,
     ClonalscopeError,
@@ -20,6 +21,6 @@ from ._lib import lib, build_library, library_path  # noqa: F401
 
 __all__ = [
     "Gen_bin_cell_rna_filtered", "EstRegionCov", "PrepCovMatrix", "BayesNonparCluster", "BayesNonparAlleleCluster",
-    "MCMCtrim", "majority_vote", "loglik_matrix", "ClonalscopeError", "lib", "build_library",
+    "MCMCtrim", "AssignCluster", "majority_vote", "loglik_matrix", "ClonalscopeError", "lib", "build_library",
     "library_path",
 ]

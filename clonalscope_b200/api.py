@@ -618,3 +618,107 @@ def majority_vote(Zall):
     out = np.zeros(N, dtype=np.int32)
     _check(_lib.lib().cs_majority_vote(T, N, _ptr(Z, C.c_int), _ptr(out, C.c_int)))
     return out
+
+
+# --------------------------------------------------------------------------- AssignCluster
+def _label_stats(Xd, z, K, U=None):
+    """Per-cluster sums / non-NA counts (cs_cluster_stats_dev) and, given U, per-segment squared
+    residuals (cs_sigma_stats_dev) of device-resident data; labels outside 1..K are skipped."""
+    import torch
+    L = _lib.lib()
+    N, R = Xd.shape
+    zd = torch.as_tensor(np.ascontiguousarray(z, dtype=np.int32), device=Xd.device)
+    sum_x = torch.zeros((K, R), dtype=torch.float64, device=Xd.device)
+    cnt_x, nk = torch.zeros_like(sum_x), torch.zeros(K, dtype=torch.float64, device=Xd.device)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if U is None:
+        _check(L.cs_cluster_stats_dev(N, R, K, vp(Xd), vp(zd), vp(sum_x), vp(cnt_x), vp(nk), st))
+        torch.cuda.synchronize()
+        return sum_x.cpu().numpy(), cnt_x.cpu().numpy()
+    Ud = torch.as_tensor(np.ascontiguousarray(U, dtype=np.float64), device=Xd.device)
+    sq, cnt = torch.zeros(R, dtype=torch.float64, device=Xd.device), torch.zeros(R, dtype=torch.float64, device=Xd.device)
+    _check(L.cs_sigma_stats_dev(N, R, K, vp(Xd), vp(zd), vp(Ud), vp(sq), vp(cnt), st))
+    torch.cuda.synchronize()
+    return sq.cpu().numpy()
+
+
+def AssignCluster(cluster_obj=None, mincell=20, cutoff=0.2, allele=False, cna_states_WGS=None, rm_extreme=False,
+                  cap_corr=1.5):
+    """Assign a subclone to every cell (reference R/AssignCluster.R:20-208, coverage branch):
+    majority vote over the kept sweeps, clusters of at most `mincell` cells dissolved and their
+    cells re-drawn among the remaining ones under R's own random stream (`set.seed(100)`, :36,63),
+    final means / sigmas, malignancy index and T/N annotation per cluster.
+
+    Device: the tally, the per-cluster sums and squared residuals, the orphans' log-likelihoods.
+    Host: counting, R's stream (one uniform per orphan), the K x R index arithmetic of :106-150.
+    `allele=TRUE` (:210-) and `cutoff='km'` (k-means on R's stream, :191-194) are not built."""
+    import torch
+    if allele:
+        raise ClonalscopeError("AssignCluster(allele=TRUE) is not built in this path")
+    if isinstance(cutoff, str):
+        raise ClonalscopeError("AssignCluster(cutoff='km') is not built in this path")
+    if rm_extreme:
+        raise ClonalscopeError("rm_extreme=TRUE returns NULL indices in the reference (:139-144); not supported")
+    from .rrng import RStream, sample_int_prob_one
+    res, priors = cluster_obj["results"], cluster_obj["priors"]
+    Xobj = cluster_obj["data"]
+    Xv, _, colnames = _values(Xobj)
+    X = np.ascontiguousarray(Xv, dtype=np.float64)
+    N, R = X.shape
+    Zall = np.asarray(res["Zall"], dtype=np.int32)
+    kt = int(np.asarray(res["Uall"][-1]).shape[0])
+    stream = RStream(100)                                                # :36
+    zmaj = majority_vote(Zall)                                           # :37
+    labs, cnts = np.unique(zmaj, return_counts=True)
+    ind_clusters = labs[cnts > mincell].astype(np.int64)                 # :41
+    orphan = ~np.isin(zmaj, ind_clusters)                                # :42
+    ind_cell = np.nonzero(orphan)[0]
+    if len(ind_clusters) == 0:
+        raise ClonalscopeError("no cluster has more than mincell cells")
+    Xd = torch.as_tensor(X, device="cuda")
+    z = np.where(orphan, 0, zmaj).astype(np.int32)
+
+    def means(zz):                                                       # :46-51 colMeans(na.rm = T), NA -> 0
+        s, c = _label_stats(Xd, zz, kt)
+        U = np.full((kt, R), np.nan)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            m = np.where(c > 0, s / np.maximum(c, 1), 0.0)
+        U[ind_clusters - 1] = m[ind_clusters - 1]
+        return U
+
+    Usub = means(z)
+    Ufill = np.where(np.isnan(Usub), 0.0, Usub)
+    sig = np.sqrt(1.0 / (N - len(ind_cell)) * _label_stats(Xd, z, kt, Ufill))   # :53
+    if len(ind_cell):                                                    # :56-64
+        LLo = loglik_matrix(X[ind_cell], Usub[ind_clusters - 1], sig)
+        for row, ii in zip(LLo, ind_cell):
+            P = np.full(kt, np.nan)
+            P[ind_clusters - 1] = row - np.nanmax(row)
+            P[np.isnan(P)] = np.nanmin(P) - 100
+            z[ii] = sample_int_prob_one(stream, np.exp(P))
+    Usub = means(z)                                                      # :67-72
+    sigmas = np.sqrt(1.0 / N * _label_stats(Xd, z, kt, np.where(np.isnan(Usub), 0.0, Usub)))   # :77
+    pri = priors.get("cna_states_WGS") if cna_states_WGS is None else cna_states_WGS    # :80-84
+    pri = np.asarray(pri, dtype=np.float64).ravel()
+    if np.all(pri == 1):                                                 # :85-88
+        pri = np.full(R, 1.5)
+    U2 = np.maximum(np.minimum(Usub, cap_corr), 0.5)                     # :106-107
+    corrs = np.zeros(kt)
+    for k in range(kt):                                                  # :127-152
+        x = U2[k]
+        if np.any(np.isnan(x)):
+            continue
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tmp = ((x - 1) * (pri - 1)) / (np.sqrt(np.sum((x - 1) ** 2)) * np.sqrt(np.sum((pri - 1) ** 2)))
+        tmp = np.sort(tmp[~np.isnan(tmp)])
+        corrs[k] = float(np.sum(tmp.astype(np.longdouble))) if len(tmp) else 0.0
+    if corrs.max() < 0.5:                                                # :154-156
+        import warnings
+        warnings.warn("WGS and scRNA do not match well. annot might not be accurate!")
+    annot = np.where(corrs > cutoff, "T", "N")                           # :196-197
+    print("Succeed!")
+    Uest = NamedMatrix(Usub, [f"Cluster{k + 1}" for k in range(kt)], colnames) if colnames is not None else Usub
+    return dict(Zest=z.astype(np.int32), corrs=corrs[z - 1], annot=annot[z - 1], Uest=Uest, sigmas_est=sigmas,
+                Zmaj=zmaj, cutoff=cutoff, U0=priors.get("U0"), mincell=mincell, wU0=priors.get("wU0"))
+

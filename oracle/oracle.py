@@ -343,3 +343,69 @@ def est_region_cov(mtx, barcodes, features, bed, celltype0=None, var_pt=0.99, va
         out.append((est_name + chrr, [ct_bar[i] for i in sel_cell[tsel]], deltas))
         ngenes.append((est_name + chrr, len(gene_ind)))
     return dict(deltas_all=out, ngenes=ngenes, sel=sel, alpha=alphas, barcodes_normal=barcodes_normal)
+
+
+def assign_cluster(Zall, kt_last, X, cna_states_WGS, mincell=20, cutoff=0.2, cap_corr=1.5):
+    """Restatement of AssignCluster, coverage branch (reference R/AssignCluster.R:22-208); test
+    infrastructure only.  `Zall`: T x N trimmed labels; `kt_last` = nrow(Uall[[T]]); `X`: N x R.
+    Returns dict(Zest, corrs, annot, Uest, sigmas_est, Zmaj, cutoff)."""
+    L = lib()
+    Zall = np.asarray(Zall)
+    X = np.asarray(X, dtype=np.float64)
+    N, R = X.shape
+    g = MT()
+    L.cso_set_seed(C.byref(g), C.c_uint32(100))                          # :36
+    zmaj = majority_vote(Zall)                                           # :37
+    Zest = zmaj.astype(np.float64)
+    labs, cnts = np.unique(zmaj, return_counts=True)
+    ind_clusters = labs[cnts > mincell]                                  # :41
+    ind_cell = np.nonzero(~np.isin(zmaj, ind_clusters))[0]               # :42
+    Zest[ind_cell] = np.nan
+
+    def means():
+        U = np.full((kt_last, R), np.nan)
+        for kk in ind_clusters:                                          # :46-51 colMeans(na.rm=T), long double
+            rows = X[Zest == kk].astype(np.longdouble)
+            ok = ~np.isnan(rows)
+            cnt = ok.sum(axis=0)
+            s = np.where(ok, rows, 0).sum(axis=0)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                m = np.asarray(s / cnt, dtype=np.float64)
+            m[cnt == 0] = 0.0
+            U[kk - 1] = m
+        return U
+
+    Usub = means()
+    kept = np.setdiff1d(np.arange(N), ind_cell)
+    d = (X[kept] - Usub[Zest[kept].astype(int) - 1]).astype(np.longdouble) ** 2   # :53
+    sig = np.sqrt(1.0 / (N - len(ind_cell)) * np.asarray(np.where(np.isnan(d), 0, d).sum(axis=0), dtype=np.float64))
+    for ii in ind_cell:                                                  # :56-64
+        P = np.full(kt_last, np.nan)
+        for kk in ind_clusters:
+            P[kk - 1] = total_loglik(X[ii:ii + 1], Usub[kk - 1:kk], np.array([1], dtype=np.int32), sig)
+        P[ind_clusters - 1] -= np.nanmax(P[ind_clusters - 1])
+        P[np.isnan(P)] = np.nanmin(P) - 100
+        P = np.exp(P)
+        perm = np.zeros(kt_last, dtype=np.int32)
+        p = np.ascontiguousarray(P, dtype=np.float64)
+        Zest[ii] = L.cso_sample_int_prob(C.byref(g), kt_last, _p(p, C.c_double), _p(perm, C.c_int))
+    Usub = means()                                                       # :67-72
+    z = Zest.astype(int)
+    d = (X - Usub[z - 1]).astype(np.longdouble) ** 2
+    sig = np.sqrt(1.0 / N * np.asarray(np.where(np.isnan(d), 0, d).sum(axis=0), dtype=np.float64))   # :77
+    priors = np.asarray(cna_states_WGS, dtype=np.float64)
+    if np.all(priors == 1):                                              # :85-88
+        priors = np.full(R, 1.5)
+    U2 = np.maximum(np.minimum(Usub, cap_corr), 0.5)                     # :106-107
+    corrs = np.zeros(kt_last)
+    for k in range(kt_last):                                             # :127-150
+        x = U2[k]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tmp = ((x - 1) * (priors - 1)) / (np.sqrt(np.sum((x - 1) ** 2)) * np.sqrt(np.sum((priors - 1) ** 2)))
+        tmp = np.sort(tmp[~np.isnan(tmp)])                               # sort() drops NA
+        s = 0.0
+        for v in tmp:                                                    # sum() of the sorted terms (long double)
+            s = np.longdouble(s) + v
+        corrs[k] = float(s) if len(tmp) and not np.any(np.isnan(x)) else 0.0
+    annot = np.where(corrs > cutoff, "T", "N")
+    return dict(Zest=z, corrs=corrs[z - 1], annot=annot[z - 1], Uest=Usub, sigmas_est=sig, Zmaj=zmaj, cutoff=cutoff)

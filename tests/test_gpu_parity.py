@@ -674,3 +674,53 @@ def test_region_cov_feeds_prep_and_the_sampler(cs):
     purity = sum(max(int(((z == k) & (planted == 1)).sum()), int(((z == k) & (planted == 0)).sum()))
                  for k in np.unique(z)) / len(z)
     assert purity > 0.9                                                    # clusters do not mix the two groups
+
+
+# ------------------------------------------------------------------ AssignCluster
+@pytest.mark.parametrize("name,mincell", [("P5931", 20), ("P5931", 100), ("P5847_tumor", 20)])
+def test_assign_cluster_vs_oracle(cs, oracle, name, mincell):
+    """The posterior step on a chain that reproduces the reference's own (R-compatible mode, the
+    fixture's seed): same tally, the same orphans re-drawn to the same clusters under set.seed(100),
+    means / sigmas / malignancy index to 1e-10."""
+    g = load_golden(f"sampler_{name}.npz")
+    niter = 40
+    out = cs.BayesNonparCluster(g["X"], cna_states_WGS=g["cna_states_WGS"], alpha=float(g["alpha"]),
+                                beta=float(g["beta"]), niter=niter, sigmas0=g["sigmas0"], U0=g["U0"], Z0=g["Z0"],
+                                seed=int(g["seed"]), rng="r")
+    assert np.array_equal(out["results"]["Zall"], g["Zall"][:niter])
+    trimmed = cs.MCMCtrim(out)
+    got = cs.AssignCluster(trimmed, mincell=mincell)
+    want = oracle.assign_cluster(trimmed["results"]["Zall"], trimmed["results"]["Uall"][-1].shape[0], g["X"],
+                                 g["cna_states_WGS"], mincell=mincell)
+    assert np.array_equal(got["Zmaj"], want["Zmaj"])
+    assert (got["Zest"] != got["Zmaj"]).sum() > 0                   # some cells really were re-drawn
+    assert np.array_equal(got["Zest"], want["Zest"])
+    U = got["Uest"].values if hasattr(got["Uest"], "values") else got["Uest"]
+    np.testing.assert_allclose(U, want["Uest"], rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(got["sigmas_est"], want["sigmas_est"], rtol=1e-10)
+    np.testing.assert_allclose(got["corrs"], want["corrs"], rtol=1e-10, atol=1e-12)
+    assert np.array_equal(got["annot"], want["annot"])
+
+
+@pytest.mark.parametrize("name,mincell,labels", [
+    ("P5931", 13, {1, 2, 4, 53, 62, 73, 100, 192}),
+    ("BC_ductal2", 40, {1, 7, 9, 13, 19, 25, 26, 27, 37, 49, 141, 146, 150, 160, 201}),
+    ("P5847_tumor", 50, {1, 2}),
+    ("P5847_allcells", 50, {1, 3, 5, 6, 9, 36, 39, 80, 125})])
+def test_assign_cluster_on_the_reference_chains(cs, name, mincell, labels):
+    """On the reference's own stored chains (burn-in 100) the final assignment keeps exactly the
+    published subclones and gives every cell one of them."""
+    g = load_golden(f"sampler_{name}.npz")
+    R = g["X"].shape[1]
+    obj = dict(results=dict(Zall=g["Zall"][100:].astype(np.int32), Uall=[np.zeros((int(g["kt"][-1]), R))]),
+               priors=dict(U0=g["U0"], cna_states_WGS=g["cna_states_WGS"], wU0=True), data=g["X"])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = cs.AssignCluster(obj, mincell=mincell)
+    lab, cnt = np.unique(out["Zest"], return_counts=True)
+    assert set(int(l) for l in lab) == labels
+    zl, zc = np.unique(out["Zmaj"], return_counts=True)
+    before = {int(l): int(c) for l, c in zip(zl, zc)}
+    assert all(c >= before[int(l)] for l, c in zip(lab, cnt)) and cnt.sum() == g["X"].shape[0]
+    assert set(np.unique(out["annot"])) <= {"T", "N"} and np.all(np.isfinite(out["sigmas_est"]))

@@ -175,3 +175,27 @@ def test_no_gpu_means_loud_failure(cs):
         cs.loglik_matrix(np.ones((4, 2)), np.ones((1, 2)), 0.25)
     with pytest.raises(cs.ClonalscopeError):
         cs.majority_vote(np.ones((3, 4), dtype=np.int32))
+
+
+def test_host_r_stream_matches_the_oracle(oracle):
+    """clonalscope_b200.rrng (the product's host copy of R's stream, used by AssignCluster) against the
+    oracle's C restatement: uniforms after set.seed, and sample.int(n, 1, prob=) draws incl. ties."""
+    import ctypes as C
+    from clonalscope_b200.rrng import RStream, sample_int_prob_one
+    for seed in (100, 42, 200):
+        r = RStream(seed)
+        assert np.array_equal(np.array([r.unif_rand() for _ in range(1300)]), oracle.mt_uniforms(seed, 1300))
+    L = oracle.lib()
+    gm = oracle.MT()
+    L.cso_set_seed(C.byref(gm), C.c_uint32(100))
+    r = RStream(100)
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        n = int(rng.integers(1, 40))
+        P = np.exp(rng.normal(0, 3, size=n))
+        if t % 5 == 0:
+            P[rng.integers(0, n, size=3)] = P.min()
+        p, perm = P.copy(), np.zeros(n, dtype=np.int32)
+        a = L.cso_sample_int_prob(C.byref(gm), n, p.ctypes.data_as(C.POINTER(C.c_double)),
+                                  perm.ctypes.data_as(C.POINTER(C.c_int)))
+        assert a == sample_int_prob_one(r, P)
