@@ -299,7 +299,7 @@ def _assert_same_chain(got, want, niter, tol=1e-9):
 
 
 @pytest.mark.parametrize("N,R,na,niter", [(1500, 40, 0.0, 12), (1200, 300, 0.0, 8), (900, 70, 0.02, 10),
-                                          (333, 4, 0.0, 25), (64, 1, 0.0, 10)])
+                                          (333, 4, 0.0, 25), (64, 1, 0.0, 10), (501, 700, 0.01, 6), (6, 33, 0.0, 5)])
 def test_sampler_philox_vs_oracle_synthetic(cs, oracle, N, R, na, niter):
     from clonalscope_b200 import synth
     s = synth.sampler_input(N, R=R, seed=1003 + R, K_true=6, na_frac=na)
