@@ -36,6 +36,7 @@ struct ChainDev {
     double *U;        // kcap x R rows
     double *Unext;    // compaction target (Philox)
     int *np;          // kcap counts
+    int *np0;         // kcap counts at the start of the sweep (Philox; written by prepare_kernel)
     int *slot_label;  // kcap (Philox)
     double *sig;      // R
     double *isig;     // R : 1/sig

@@ -27,7 +27,7 @@ struct cs_chain {
     DevBuf<double> wn_w;
     DevBuf<int> kmin, icnt, icur, nd;
     DevBuf<InvEntry> inv;
-    DevBuf<int> Zs, np, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
+    DevBuf<int> Zs, np, np0, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
     DevBuf<long long> u_off;
     DevBuf<uint32_t> mt;
     DevBuf<ChainScal> scal;
@@ -87,6 +87,8 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_CUDA(c->mean.alloc((size_t)kcap * R));
     CS_CUDA(c->Zs.alloc((size_t)N + 8)); // (+8 here and below: the ring scan copies whole groups of four cells)
     CS_CUDA(c->np.alloc(kcap));
+    CS_CUDA(c->np0.alloc(kcap));
+    CS_CUDA(cudaMemset(c->np0.p, 0, sizeof(int) * (size_t)kcap));
     CS_CUDA(c->slot_label.alloc(kcap));
     CS_CUDA(c->newslot.alloc(kcap));
     CS_CUDA(c->scal.alloc(1));
@@ -122,7 +124,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     CS_CUDA(c->u_rows.alloc((size_t)urec_cap * R));
     ChainDev &D = c->D;
     D.N = N; D.R = R; D.kcap = kcap; D.chunk = chunk;
-    D.X = c->X.p; D.Zs = c->Zs.p; D.U = c->Ua.p; D.Unext = c->Ub.p; D.np = c->np.p;
+    D.X = c->X.p; D.Zs = c->Zs.p; D.U = c->Ua.p; D.Unext = c->Ub.p; D.np = c->np.p; D.np0 = c->np0.p;
     D.slot_label = c->slot_label.p; D.sig = c->sig.p; D.isig = c->isig.p; D.Q = c->Q.p; D.J = c->J.p;
     D.E = c->E.p; D.qmin = c->qmin.p; D.ua = c->ua.p; D.qnew_i = c->qnew_i.p; D.icnt = c->icnt.p;
     D.wn_q = c->wn_q.p; D.wn_w = c->wn_w.p; D.kmin = c->kmin.p;

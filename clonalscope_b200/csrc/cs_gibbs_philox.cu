@@ -390,6 +390,8 @@ prepare_kernel(ChainDev D, int tt, int *__restrict__ rej)
     const int nlive = D.scal->nlive;
     for (int r = threadIdx.x; r < D.R; r += PREP_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
     for (int s = threadIdx.x; s < nlive; s += PREP_THREADS) s_np[s] = D.np[s];
+    if (blockIdx.x == 0) // the counts the speculative draws were made against (the walks consult them)
+        for (int s = threadIdx.x; s < D.kcap; s += PREP_THREADS) D.np0[s] = s < nlive ? D.np[s] : 0;
     __syncthreads();
     const bool reject_live = D.single && tt == 0;
     const int lane = threadIdx.x & 31;
@@ -559,7 +561,7 @@ scan_kernel(ChainDev D, int tt)
         s_np[s] = n;
         s_npd[s] = n > 0 ? (double)n : 0.0;
         s_npd1[s] = n > 1 ? (double)(n - 1) : 0.0;
-        s_np0[s] = n;
+        s_np0[s] = D.np0[s];
         s_label[s] = D.slot_label[s];
     }
     if (threadIdx.x == 0) {
@@ -794,9 +796,13 @@ scan_kernel(ChainDev D, int tt)
 //     cluster (parked at the cluster barrier in between) score the new column together with
 //     this one, then the ring is filled again (cluster.sync invalidates L1);
 //   * when a 33rd cluster opens the walk is handed to scan_kernel at that cell.
-constexpr int RING = 512;
-constexpr int RMASK = RING - 1;
-constexpr int RING_SLOTS = 32;
+// two shapes of the resident window: cells in the ring x live clusters it holds x widest window
+template <int RING_, int SLOTS_, int WINC_>
+struct RingCfg {
+    static constexpr int RING = RING_, RMASK = RING_ - 1, SLOTS = SLOTS_, WINC = WINC_;
+};
+using RingWide = RingCfg<1024, 12, 512>; // few clusters (the later, sparser sweeps): 512-cell windows, half the rounds
+using RingDeep = RingCfg<512, 32, 256>;  // up to 32 clusters
 
 __device__ __forceinline__ void cp_async_8(void *dst, const void *src)
 {
@@ -811,24 +817,27 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr int DEP_STAGE = 2 * WIN_THREADS; // dependents' index entries staged per round
 // fixed part of the kernel's shared memory (compile-time offsets); behind it: np, label, np0
 // (kcap ints each) and isig16 (R doubles)
+template <typename Cfg>
 struct RingFixed {
-    long long qi[RING], wq[RING];        // proposal distance (fixed point); the one the cached weight is for
-    double w[RING], qmin[RING], ua[RING]; // cached new-table weight, reference, uniform
-    double e[RING_SLOTS * RING];         // cached exponentials [slot][cell]
-    int z[RING], km[RING], i0[RING], nd[RING]; // old slot, cluster at the reference, dependents' offset, nearest dependent
+    long long qi[Cfg::RING], wq[Cfg::RING];        // proposal distance (fixed point); the one the cached weight is for
+    double w[Cfg::RING], qmin[Cfg::RING], ua[Cfg::RING]; // cached new-table weight, reference, uniform
+    double e[Cfg::SLOTS * Cfg::RING];         // cached exponentials [slot][cell]
+    int z[Cfg::RING], km[Cfg::RING], i0[Cfg::RING], nd[Cfg::RING]; // old slot, cluster at the reference, dependents' offset, nearest dependent
     InvEntry dep[DEP_STAGE];             // staged index entries of the round's dependents
-    double npd[RING_SLOTS + 2], npd1[RING_SLOTS + 2];
+    double npd[Cfg::SLOTS + 2], npd1[Cfg::SLOTS + 2];
 };
+template <typename Cfg>
 inline size_t ring_smem_bytes(int R, int kcap)
 {
-    return sizeof(RingFixed) + sizeof(int) * 3 * (size_t)kcap + sizeof(double) * ((size_t)R + 1) + 16;
+    return sizeof(RingFixed<Cfg>) + sizeof(int) * 3 * (size_t)kcap + sizeof(double) * ((size_t)R + 1) + 16;
 }
 
 // asynchronous copies of cells [lo, hi) (multiples of 4) into the ring, 16 bytes at a time: a
 // warp takes a field, its lanes two cells (8-byte fields) or four (4-byte fields) each.  The
 // arrays are padded, so whole groups can be read up to the cell behind the last one (whose
 // dependents' offset closes the last cell's range).
-__device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed &F, int lo, int hi, int nlive)
+template <typename Cfg>
+__device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed<Cfg> &F, int lo, int hi, int nlive)
 {
     const int ncell = hi - lo;
     if (ncell <= 0) return;
@@ -841,7 +850,7 @@ __device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed &F, int 
             bool aligned = true;
             if (k < nlive) {
                 src = D.E + (size_t)k * N;
-                dst = F.e + (size_t)k * RING;
+                dst = F.e + (size_t)k * Cfg::RING;
                 aligned = (((size_t)k * N) & 1) == 0; // (odd N: every other column starts at an odd element)
             } else if (k == nlive) {
                 src = reinterpret_cast<const double *>(D.wn_q);
@@ -862,10 +871,10 @@ __device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed &F, int 
             for (int p = lane; p < ncell / 2; p += 32) {
                 const int c = lo + 2 * p;
                 if (aligned) {
-                    cp_async_16_cg(dst + (c & RMASK), src + c);
+                    cp_async_16_cg(dst + (c & Cfg::RMASK), src + c);
                 } else {
-                    cp_async_8(dst + (c & RMASK), src + c);
-                    cp_async_8(dst + ((c + 1) & RMASK), src + c + 1);
+                    cp_async_8(dst + (c & Cfg::RMASK), src + c);
+                    cp_async_8(dst + ((c + 1) & Cfg::RMASK), src + c + 1);
                 }
             }
         } else {
@@ -886,7 +895,7 @@ __device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed &F, int 
             }
             for (int q = lane; q < ncell / 4; q += 32) {
                 const int c = lo + 4 * q;
-                cp_async_16_cg(dst + (c & RMASK), src + c);
+                cp_async_16_cg(dst + (c & Cfg::RMASK), src + c);
             }
         }
     }
@@ -897,10 +906,11 @@ __device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed &F, int 
 // which leaves every sum as it is); the first pass keeps the running sum after each group, the
 // second one re-adds only the group in which the threshold falls — the same additions in the
 // same order, so the same sums.
+template <typename Cfg>
 __device__ __forceinline__ int draw_cell_ring(const double *ecol, int nlive, const double *s_npd, const double *s_npd1,
                                               int zold, double w_new, double ua, double *margin)
 {
-    constexpr int NG = RING_SLOTS / 8;
+    constexpr int NG = (Cfg::SLOTS + 7) / 8;
     double cg[NG];
     double run = 0.0;
 #pragma unroll
@@ -908,7 +918,7 @@ __device__ __forceinline__ int draw_cell_ring(const double *ecol, int nlive, con
         if (8 * g < nlive) {
             double e[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) e[i] = ecol[(size_t)(8 * g + i) * RING];
+            for (int i = 0; i < 8; i++) e[i] = (8 * g + i < Cfg::SLOTS) ? ecol[(size_t)(8 * g + i) * Cfg::RING] : 0.0;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int s = 8 * g + i;
@@ -935,10 +945,10 @@ __device__ __forceinline__ int draw_cell_ring(const double *ecol, int nlive, con
     if (8 * gsel < nlive) { // ... then the slots of the group the threshold falls in
         double cum = start, cum_below = start, cum_at = CUDART_INF;
         int k = 8 * gsel;
-        const double *eg = ecol + (size_t)(8 * gsel) * RING;
+        const double *eg = ecol + (size_t)(8 * gsel) * Cfg::RING;
         double e[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) e[i] = eg[(size_t)i * RING];
+        for (int i = 0; i < 8; i++) e[i] = (8 * gsel + i < Cfg::SLOTS) ? eg[(size_t)i * Cfg::RING] : 0.0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int s = 8 * gsel + i;
@@ -958,7 +968,7 @@ __device__ __forceinline__ int draw_cell_ring(const double *ecol, int nlive, con
         z = -1; // (all weights zero, or the threshold at the very top: the last positive weight)
         for (int s = 0; s < nlive; s++) {
             const double nd = (s == zold) ? s_npd1[s] : s_npd[s];
-            if (__dmul_rn(nd, ecol[(size_t)s * RING]) > 0.0) z = s;
+            if (__dmul_rn(nd, ecol[(size_t)s * Cfg::RING]) > 0.0) z = s;
         }
         gap = 0.0;
     }
@@ -1006,17 +1016,17 @@ __device__ __noinline__ void score_new_column(const ChainDev &D, int f, int b, i
     }
 }
 
-template <int NCH>
+template <int NCH, typename Cfg>
 __global__ void __launch_bounds__(WIN_THREADS, 1)
 scan_ring_kernel(ChainDev D, int tt)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
     extern __shared__ __align__(16) unsigned char s_ring_raw[];
-    RingFixed &F = *reinterpret_cast<RingFixed *>(s_ring_raw);
-    int *s_np = reinterpret_cast<int *>(s_ring_raw + sizeof(RingFixed));
+    RingFixed<Cfg> &F = *reinterpret_cast<RingFixed<Cfg> *>(s_ring_raw);
+    int *s_np = reinterpret_cast<int *>(s_ring_raw + sizeof(RingFixed<Cfg>));
     int *s_label = s_np + D.kcap, *s_np0 = s_label + D.kcap;
-    double *s_isig16 = reinterpret_cast<double *>(s_ring_raw + sizeof(RingFixed) + sizeof(int) * ((3 * (size_t)D.kcap + 1) & ~(size_t)1));
+    double *s_isig16 = reinterpret_cast<double *>(s_ring_raw + sizeof(RingFixed<Cfg>) + sizeof(int) * ((3 * (size_t)D.kcap + 1) & ~(size_t)1));
     __shared__ int s_nlive, s_kt, s_err, s_block, s_wcnt[WIN_THREADS / 32];
     __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV], s_ev_nd[MAX_EV];
     __shared__ int s_ev_off[MAX_EV + 1]; // dependents in front of each candidate's own (prefix of e1 - e0)
@@ -1024,7 +1034,7 @@ scan_ring_kernel(ChainDev D, int tt)
 
     // (uniform over the cluster: the scalars are written back only after the last cluster barrier)
     const int f0 = D.scal->first_event;
-    if (f0 >= D.N || D.scal->nlive > RING_SLOTS) return;
+    if (f0 >= D.N || D.scal->nlive > Cfg::SLOTS) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
     volatile int *cmd_cell = &D.scal->open_cell, *cmd_slot = &D.scal->open_slot;
@@ -1043,9 +1053,9 @@ scan_ring_kernel(ChainDev D, int tt)
     for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
         const int n = D.np[s];
         s_np[s] = n;
-        s_np0[s] = n;
+        s_np0[s] = D.np0[s];
         s_label[s] = D.slot_label[s];
-        if (s <= RING_SLOTS) {
+        if (s <= Cfg::SLOTS) {
             F.npd[s] = n > 0 ? (double)n : 0.0;
             F.npd1[s] = n > 1 ? (double)(n - 1) : 0.0;
         }
@@ -1060,8 +1070,8 @@ scan_ring_kernel(ChainDev D, int tt)
     const size_t N = (size_t)D.N;
     const int Npad = (D.N + 4) & ~3; // cells 0..N, in whole groups of four
     int pos = f0, W = WIN_MIN;
-    int head = min(Npad, (pos & ~3) + RING), landed;
-    ring_issue(D, F, pos & ~3, head, D.scal->nlive);
+    int head = min(Npad, (pos & ~3) + Cfg::RING), landed;
+    ring_issue<Cfg>(D, F, pos & ~3, head, D.scal->nlive);
     cp_async_wait_all();
     __syncthreads();
     landed = head;
@@ -1072,7 +1082,7 @@ scan_ring_kernel(ChainDev D, int tt)
         const int We = min(W, landed - 1 - pos);
         const int c = pos + threadIdx.x;
         const bool active = threadIdx.x < We && c < D.N;
-        const int ri = c & RMASK;
+        const int ri = c & Cfg::RMASK;
         const int nlive = s_nlive;
         int z = -1, zold = -1;
         double margin = 0.0; // what this draw tolerates before it has to be redone
@@ -1094,7 +1104,7 @@ scan_ring_kernel(ChainDev D, int tt)
                     F.w[ri] = w_new;
                 }
                 const double *ecol = F.e + ri;
-                z = draw_cell_ring(ecol, nlive, F.npd, F.npd1, zold, w_new, ua, &margin);
+                z = draw_cell_ring<Cfg>(ecol, nlive, F.npd, F.npd1, zold, w_new, ua, &margin);
             } else {
                 z = draw_cell_thread(D.Q + c, D.E + c, N, nlive, nlive, s_np, zold, q_new, qmin, D.beta, ua);
             }
@@ -1116,7 +1126,7 @@ scan_ring_kernel(ChainDev D, int tt)
             s_ev_a[jc] = zold;
             s_ev_b[jc] = z;
             s_ev_e0[jc] = F.i0[ri];
-            s_ev_e1[jc] = F.i0[(c + 1) & RMASK];
+            s_ev_e1[jc] = F.i0[(c + 1) & Cfg::RMASK];
             s_ev_nd[jc] = F.nd[ri];
         }
         if (threadIdx.x == 0) s_block = INT_MAX;
@@ -1159,7 +1169,7 @@ scan_ring_kernel(ChainDev D, int tt)
             double m = margin;
             const double *ecol = F.e + ri;
             for (int i = 0; i < jc; i++)
-                m -= (ecol[(size_t)s_ev_a[i] * RING] + ecol[(size_t)s_ev_b[i] * RING]) * 1.000000001;
+                m -= (ecol[(size_t)s_ev_a[i] * Cfg::RING] + ecol[(size_t)s_ev_b[i] * Cfg::RING]) * 1.000000001;
             if (!(m > 0.0)) atomicMin(&s_block, jc);
         }
         __syncthreads();
@@ -1211,7 +1221,7 @@ scan_ring_kernel(ChainDev D, int tt)
                 }
             }
         }
-        if (threadIdx.x <= nlive && threadIdx.x <= RING_SLOTS && threadIdx.x < D.kcap) {
+        if (threadIdx.x <= nlive && threadIdx.x <= Cfg::SLOTS && threadIdx.x < D.kcap) {
             const int n = s_np[threadIdx.x];
             F.npd[threadIdx.x] = n > 0 ? (double)n : 0.0;
             F.npd1[threadIdx.x] = n > 1 ? (double)(n - 1) : 0.0;
@@ -1232,7 +1242,7 @@ scan_ring_kernel(ChainDev D, int tt)
                     if (d) {
                         atomicAdd(reinterpret_cast<unsigned long long *>(D.qnew_i + cc), (unsigned long long)d);
                         if (cc < head)
-                            atomicAdd(reinterpret_cast<unsigned long long *>(F.qi + (cc & RMASK)), (unsigned long long)d);
+                            atomicAdd(reinterpret_cast<unsigned long long *>(F.qi + (cc & Cfg::RMASK)), (unsigned long long)d);
                     }
                 }
             };
@@ -1253,7 +1263,7 @@ scan_ring_kernel(ChainDev D, int tt)
         __syncthreads(); // corrections done (global ones ordered before the copies issued below)
         const int adv = nev ? lo - pos : We;
         pos += adv;
-        if (nev == 0) W = min(WIN_CELLS, W * 2);
+        if (nev == 0 || adv > W / 2) W = min(Cfg::WINC, W * 2); // (rounds get far: wider windows, fewer rounds)
         else if (adv < W / 4 && nev < MAX_EV) W = max(WIN_MIN, W / 2);
         if (opened) {
             // ---- the new column, scored by the whole cluster; then the ring is filled again
@@ -1265,18 +1275,18 @@ scan_ring_kernel(ChainDev D, int tt)
             cluster.sync();
             score_new_column<NCH>(D, f, b, 0, csize, s_isig16, lane, warp);
             cluster.sync();
-            if (b + 1 > RING_SLOTS) { // a 33rd cluster: the generic walk takes over here
+            if (b + 1 > Cfg::SLOTS) { // a 33rd cluster: the generic walk takes over here
                 resume = pos;
                 break;
             }
-            ring_issue(D, F, pos & ~3, head, b + 1);
+            ring_issue<Cfg>(D, F, pos & ~3, head, b + 1);
             cp_async_wait_all();
             __syncthreads();
         }
         // ---- copies for the cells the window will reach after the next round
         {
-            const int nh = min(Npad, (pos & ~3) + RING);
-            ring_issue(D, F, head, nh, s_nlive);
+            const int nh = min(Npad, (pos & ~3) + Cfg::RING);
+            ring_issue<Cfg>(D, F, head, nh, s_nlive);
             head = max(head, nh);
         }
     }
@@ -1753,7 +1763,7 @@ inline int current_device()
     return d;
 }
 
-template <int NCH>
+template <int NCH, typename Cfg>
 int ring_cluster_size(size_t smem)
 {
     static size_t known_smem_d[MAX_DEVICES] = {};
@@ -1767,8 +1777,8 @@ int ring_cluster_size(size_t smem)
     known_smem = smem;
     known = 0;
     if (smem > 227 * 1024) return 0;
-    if (cudaFuncSetAttribute(scan_ring_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(scan_ring_kernel<NCH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    if (cudaFuncSetAttribute(scan_ring_kernel<NCH, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(scan_ring_kernel<NCH, Cfg>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
     }
@@ -1790,13 +1800,35 @@ int ring_cluster_size(size_t smem)
         cfg.attrs = &at;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, scan_ring_kernel<NCH>, &cfg) == cudaSuccess && n >= 1) {
+        if (cudaOccupancyMaxActiveClusters(&n, scan_ring_kernel<NCH, Cfg>, &cfg) == cudaSuccess && n >= 1) {
             known = cs;
             break;
         }
         (void)cudaGetLastError();
     }
     return known;
+}
+
+template <int NCH, typename Cfg>
+int launch_ring(const ChainDev &D, int tt, cudaStream_t st)
+{
+    const size_t smem_ring = ring_smem_bytes<Cfg>(D.R, D.kcap);
+    const int csize = ring_cluster_size<NCH, Cfg>(smem_ring);
+    if (csize <= 0) return CS_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize);
+    cfg.blockDim = dim3(WIN_THREADS);
+    cfg.dynamicSmemBytes = smem_ring;
+    cfg.stream = st;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = csize;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    CS_CUDA(cudaLaunchKernelEx(&cfg, scan_ring_kernel<NCH, Cfg>, D, tt));
+    return CS_OK;
 }
 
 template <int NCH>
@@ -1836,25 +1868,11 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
             index_scan_kernel<<<1, 1024, 0, st>>>(D);
             index_fill_kernel<<<nsm * 8, 256, 0, st>>>(D);
             if (ev) CS_CUDA(cudaEventRecord(ev[4], st));
-            // the resident-window walk (sweeps with at most 32 live clusters), then the generic one
-            // for whatever it left (nothing, unless a 33rd cluster opened)
-            const size_t smem_ring = ring_smem_bytes(D.R, D.kcap);
-            const int csize = ring_cluster_size<NCH>(smem_ring);
-            if (csize > 0) {
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(csize);
-                cfg.blockDim = dim3(WIN_THREADS);
-                cfg.dynamicSmemBytes = smem_ring;
-                cfg.stream = st;
-                cudaLaunchAttribute at;
-                at.id = cudaLaunchAttributeClusterDimension;
-                at.val.clusterDim.x = csize;
-                at.val.clusterDim.y = 1;
-                at.val.clusterDim.z = 1;
-                cfg.attrs = &at;
-                cfg.numAttrs = 1;
-                CS_CUDA(cudaLaunchKernelEx(&cfg, scan_ring_kernel<NCH>, D, tt));
-            }
+            // the resident-window walks — the wide shape while there are few clusters, the deep one
+            // for up to 32 — then the generic one for whatever they left (nothing, unless a 33rd
+            // cluster opened); each starts where the one before stopped
+            { int rc2 = launch_ring<NCH, RingWide>(D, tt, st); if (rc2) return rc2; }
+            { int rc2 = launch_ring<NCH, RingDeep>(D, tt, st); if (rc2) return rc2; }
             scan_kernel<NCH><<<1, WIN_THREADS, smem_scan, st>>>(D, tt);
         }
     }
