@@ -456,7 +456,7 @@ def run_ours(a):
                                  f"niter={niter}, Philox; one independent chain per GPU",
                         step="one full chain of niter sweeps", l2="per-sweep working set (X 240 MB + Q + J) exceeds the 126 MB L2",
                         binning=f"{NB} cells x {G} genes -> {B} bins per GPU"),
-            e2e=e2e, gpu_launches=int(a.steps * niter * 14),
+            e2e=e2e, gpu_launches=int(a.steps * niter * 15),
             roofline=dict(bound="hbm", kernel="scan_ring_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
                           frac=ach / hbm_peak, traffic=SCAN_TRAFFIC_BYTES, peak_source=peak_src,
                           note="latency-bound sequential commit (one CTA walks the cells in the sweep's order; "
