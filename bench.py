@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 METRIC = "nCRP Gibbs cell-updates/sec at 100k cells x 300 segs; bin-count GB/s vs HBM"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures (profiles/r1_scan_ring_full.txt: sweep 3 of the bench workload; profiles/r1_prepare_full.txt)
-SCAN_TRAFFIC_BYTES = 34_788_352
+SCAN_TRAFFIC_BYTES = 38_916_352
 PREPARE_TRAFFIC_BYTES = 350_580_480
 
 
