@@ -795,7 +795,8 @@ scan_kernel(ChainDev D, int tt)
 //   * opening a cluster rewrites cached columns of all later cells: the other CTAs of the
 //     cluster (parked at the cluster barrier in between) score the new column together with
 //     this one, then the ring is filled again (cluster.sync invalidates L1);
-//   * when a 33rd cluster opens the walk is handed to scan_kernel at that cell.
+//   * when a cluster opens that the ring has no slot for, the walk is handed on at that cell
+//     (to the other shape of this kernel, then to scan_kernel).
 // two shapes of the resident window: cells in the ring x live clusters it holds x widest window
 template <int RING_, int SLOTS_, int WINC_>
 struct RingCfg {
@@ -1275,7 +1276,7 @@ scan_ring_kernel(ChainDev D, int tt)
             cluster.sync();
             score_new_column<NCH>(D, f, b, 0, csize, s_isig16, lane, warp);
             cluster.sync();
-            if (b + 1 > Cfg::SLOTS) { // a 33rd cluster: the generic walk takes over here
+            if (b + 1 > Cfg::SLOTS) { // one cluster more than the ring holds: the next walk takes over here
                 resume = pos;
                 break;
             }
