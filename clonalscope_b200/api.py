@@ -23,7 +23,9 @@ from .intervals import gene_sites, overlap_map, r_as_character, sort_bins
 class ClonalscopeError(RuntimeError):
     """A nonzero status from the C ABI (the R shim would raise it with stop())."""
 
-    def __init__(self, status, message):
+    def __init__(self, status, message=None):
+        if message is None:  # ClonalscopeError("text"): a host-side refusal, status CS_ERR_UNSUPPORTED
+            status, message = _lib.CS_ERR_UNSUPPORTED, status
         super().__init__(f"[cs status {status}] {message}")
         self.status = status
 
@@ -182,7 +184,7 @@ def EstRegionCov(mtx=None, barcodes=None, features=None, bed=None, celltype0=Non
         col_of.setdefault(bc, i)
     missing = [bc for bc in ct_bar if bc not in col_of]
     if missing:
-        raise ClonalscopeError(f"celltype0 names a barcode that is not in barcodes: {missing[0]}")
+        raise ClonalscopeError(_lib.CS_ERR_ARG, f"celltype0 names a barcode that is not in barcodes: {missing[0]}")
     m = sp.csc_matrix(mtx)[:, [col_of[bc] for bc in ct_bar]]            # :40
     m.sum_duplicates()
     m.sort_indices()
@@ -422,9 +424,9 @@ def BayesNonparCluster(Xir=None, cna_states_WGS=None, alpha=2, beta=2, niter=200
         if Z0v.size != N:
             raise ValueError("Please specify a vector with length the same as the number of cells!")
         Z0v = np.where(np.isnan(Z0v.astype(np.float64)), 0, Z0v).astype(np.int32)
-    if np.isnan(U0m).any():
-        raise ClonalscopeError(_lib.CS_ERR_STATE, "U0 holds NA rows below its last non-NA row")
-
+    # (NA rows of U0 below its last non-NA row — what AssignCluster's Uest has for dissolved clusters,
+    #  R/RunCovCluster.R:131 — stay in place: they keep their label, hold no cell and are never
+    #  scored or proposed, :93,:150-151,:193)
     K0 = U0m.shape[0]
     Xf = np.asfortranarray(X)
     U0f = np.asfortranarray(U0m)
@@ -433,7 +435,8 @@ def BayesNonparCluster(Xir=None, cna_states_WGS=None, alpha=2, beta=2, niter=200
     LL = np.zeros(niter, dtype=np.float64)
     L0 = C.c_double(0.0)
     kt_all = np.zeros(niter, dtype=np.int32)
-    ucap = int(niter) * 160 + 4096
+    # (room for every sweep's occupied clusters; untouched pages of these buffers are never committed)
+    ucap = int(niter) * min(N, 512 if str(rng).lower() == "r" else (int(kcap) if kcap else 256)) + 4096
     u_off = np.zeros(niter + 1, dtype=np.int64)
     u_labels = np.zeros(ucap, dtype=np.int32)
     u_rows = np.zeros((ucap, R), dtype=np.float64)
@@ -579,7 +582,11 @@ def MCMCtrim(clusteringObj=None, burnin=None, thinning=1, allele=False):
         burnin = min(100, nrow / 2)
     if burnin >= nrow:
         raise ValueError("burnin values is too large! Please specify a number < number of iterations.")
-    b = int(burnin)  # -c(1:burnin) with a fractional burnin truncates like R's integer indexing
+    if burnin < 0:
+        raise ValueError("can't mix positive and negative subscripts")  # what -c(1:burnin) gives in R
+    # -c(1:burnin): a fractional burnin truncates like R's integer indexing; 1:0 is c(1, 0), so
+    # burnin = 0 (and anything below 1) still drops the first sweep (:27-30)
+    b = max(1, int(burnin))
     lists = ["Uall", "Ucov", "Uallele", "sigma_cov_all", "sigma_allele_all", "Likelihood"] if allele \
         else ["Uall", "sigma_all", "Likelihood"]
     res["Zall"] = res["Zall"][b:]

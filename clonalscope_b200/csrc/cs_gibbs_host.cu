@@ -77,7 +77,10 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     const int chunk = cs_stat_chunk(N);
     const int nchunks = (N + chunk - 1) / chunk;
     const bool ph = rng_mode == CS_RNG_PHILOX;
-    const long long urec_cap = (long long)niter_cap * (ph ? (kcap < 128 ? kcap : 128) : 128) + kcap;
+    // rows of Uall recorded on the device: a sweep records at most min(kcap, N) occupied clusters
+    // (R mode: kcap is the label capacity, far above what a sweep holds; 512 per sweep on average)
+    const long long per_sweep = ph ? (kcap < N ? kcap : N) : (N < 512 ? N : 512);
+    const long long urec_cap = (long long)niter_cap * per_sweep + kcap;
     CS_CUDA(c->X.alloc(nx));
     CS_CUDA(c->Xc.alloc(nx));
     CS_CUDA(c->Ua.alloc((size_t)kcap * R));
@@ -156,12 +159,27 @@ extern "C" int cs_chain_init(cs_chain *c, const double *X, int K0, const double 
 {
     CS_REQUIRE(c && X && U0 && Z0 && sigmas0, "cs_chain_init: NULL argument");
     const int N = c->N, R = c->R;
-    CS_REQUIRE(K0 >= 1 && K0 <= c->kcap, "cs_chain_init: K0=%d outside [1, kcap=%d]", K0, c->kcap);
+    const bool ph = c->rng_mode == CS_RNG_PHILOX;
+    CS_REQUIRE(K0 >= 1, "cs_chain_init: K0=%d", K0);
+    // NA rows of U0 (first column NA, as :93 tests) keep their label and hold no cell: the
+    // reference never scores (:193 which(npoints != 0)) or proposes (:170 prob 0) them.  The
+    // Philox path gives them no slot; the R-compatible path keeps them as empty labels.
+    std::vector<int> slot_of(K0, -1);
+    int nrows_live = 0;
+    for (int k = 0; k < K0; k++)
+        if (!(U0[k] != U0[k])) slot_of[k] = nrows_live++;
+    CS_REQUIRE(nrows_live >= 1, "cs_chain_init: every row of U0 is NA");
+    CS_REQUIRE((ph ? nrows_live : K0) <= c->kcap, "cs_chain_init: %d rows of U0 exceed the capacity kcap=%d",
+               ph ? nrows_live : K0, c->kcap);
     // the reference indexes U0[Z0,] (:133) and table(Zt)[1:nrow(U0)] (:150): labels outside
     // 1..K0 give NA counts and an error further down
     for (int i = 0; i < N; i++) {
         if (Z0[i] < 1 || Z0[i] > K0) {
             cs_set_error("Z0[%d]=%d is not a row of U0 (1..%d)", i + 1, Z0[i], K0);
+            return CS_ERR_STATE;
+        }
+        if (slot_of[Z0[i] - 1] < 0) {
+            cs_set_error("Z0[%d]=%d names an NA row of U0", i + 1, Z0[i]);
             return CS_ERR_STATE;
         }
     }
@@ -182,41 +200,49 @@ extern "C" int cs_chain_init(cs_chain *c, const double *X, int K0, const double 
     D.single = single ? 1 : 0;
     c->flags = flags;
     c->sweeps_done = 0;
-    const bool ph = c->rng_mode == CS_RNG_PHILOX;
     // X: column-major N x R (== row-major R x N) -> cell-major
     CS_CUDA(cudaMemcpyAsync(c->Xc.p, X, sizeof(double) * (size_t)N * R, cudaMemcpyHostToDevice, st));
     int rc = cs_transpose<double>(R, N, c->Xc.p, c->X.p, st);
     if (rc) return rc;
-    // U0: column-major K0 x R -> rows
-    std::vector<double> Urows((size_t)K0 * R);
-    for (int k = 0; k < K0; k++)
-        for (int r = 0; r < R; r++) Urows[(size_t)k * R + r] = U0[(size_t)r * K0 + k];
+    // U0: column-major K0 x R -> rows (Philox: the non-NA rows, in label order, one slot each)
+    const int nrows_up = ph ? nrows_live : K0;
+    std::vector<double> Urows((size_t)nrows_up * R);
+    for (int k = 0; k < K0; k++) {
+        const int row = ph ? slot_of[k] : k;
+        if (row < 0) continue;
+        for (int r = 0; r < R; r++) Urows[(size_t)row * R + r] = U0[(size_t)r * K0 + k];
+    }
     CS_CUDA(cudaMemcpyAsync(D.U, Urows.data(), sizeof(double) * Urows.size(), cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaMemcpyAsync(D.sig, sigmas0, sizeof(double) * R, cudaMemcpyHostToDevice, st));
     isig_kernel<<<(R + 127) / 128, 128, 0, st>>>(R, D.sig, D.isig);
     // L0 at (U0, Z0, sigmas0)  (:133) — before the single-cluster replacement of U0
     std::vector<int> zrows(N);
-    for (int i = 0; i < N; i++) zrows[i] = Z0[i] - 1;
+    for (int i = 0; i < N; i++) zrows[i] = ph ? slot_of[Z0[i] - 1] : Z0[i] - 1;
     CS_CUDA(cudaMemcpyAsync(D.Zs, zrows.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
     rc = cs_total_loglik_async(D, D.U, D.Zs, D.sig, c->L0.p, st);
     if (rc) return rc;
     CS_CUDA(cudaStreamSynchronize(st)); // Urows / zrows are reused below
     // state (:141-151)
     std::vector<int> np(c->kcap, 0), lab(c->kcap, 0);
-    int kt;
+    int kt, nlive;
+    for (int k = 0; k < c->kcap; k++) lab[k] = k + 1;
     if (single) {
-        kt = 1;
+        kt = nlive = 1;
         np[0] = N;
         fill_kernel<<<(R + 127) / 128, 128, 0, st>>>((size_t)R, D.U, 1.0);
     } else {
         kt = K0;
-        for (int i = 0; i < N; i++) np[Z0[i] - 1]++;
+        nlive = ph ? nrows_live : K0;
+        for (int i = 0; i < N; i++) np[zrows[i]]++;
+        if (ph) { // slots past the initial ones are labelled as they open (label = ++kt)
+            for (int k = 0; k < K0; k++)
+                if (slot_of[k] >= 0) lab[slot_of[k]] = k + 1;
+        }
     }
-    for (int k = 0; k < c->kcap; k++) lab[k] = k + 1;
     std::vector<int> zinit(N);
-    for (int i = 0; i < N; i++) zinit[i] = ph ? Z0[i] - 1 : Z0[i];
+    for (int i = 0; i < N; i++) zinit[i] = ph ? (single ? 0 : zrows[i]) : Z0[i];
     ChainScal h{};
-    h.nlive = kt;
+    h.nlive = nlive;
     h.kt = kt;
     h.first_event = INT_MAX;
     h.mt_pos = 624;
@@ -279,7 +305,9 @@ extern "C" int cs_chain_sync(cs_chain *c)
         return CS_ERR_KCAP;
     }
     if (h.err == CS_ERR_UCAP) {
-        cs_set_error("internal Uall record capacity exceeded (%lld rows)", c->D.urec_cap);
+        cs_set_error("device Uall record capacity exceeded (%lld rows; a chain that keeps more than ~512 occupied "
+                     "clusters per sweep in R-compatible mode: run it in shorter pieces with cs_chain_run / cs_chain_fetch)",
+                     c->D.urec_cap);
         return CS_ERR_UCAP;
     }
     if (h.err) {
@@ -387,7 +415,21 @@ extern "C" int cs_ncrp_gibbs(int N, int R, const double *X, int K0, const double
     o.device = -1;
     if (opts) o = *opts;
     CS_REQUIRE(niter >= 1, "niter=%d must be >= 1", niter);
-    if (o.device >= 0) CS_CUDA(cudaSetDevice(o.device));
+    struct DeviceRestore { // the caller's current device is left as it was found
+        int prev = -1;
+        ~DeviceRestore()
+        {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    } restore;
+    if (o.device >= 0) {
+        int cur = -1;
+        CS_CUDA(cudaGetDevice(&cur));
+        if (cur != o.device) {
+            CS_CUDA(cudaSetDevice(o.device));
+            restore.prev = cur;
+        }
+    }
     int kcap = o.kcap;
     if (kcap > 0 && kcap < K0) kcap = K0;
     if (kcap <= 0) kcap = o.rng_mode == CS_RNG_PHILOX ? kDefaultKcapPhilox : kDefaultLcapR;

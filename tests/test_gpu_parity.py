@@ -352,20 +352,81 @@ def test_speculative_and_sequential_evaluation_agree(cs):
     assert np.array_equal(a["results"]["Likelihood"], b["results"]["Likelihood"])
 
 
-def test_philox_chain_is_in_the_reference_envelope(cs):
-    """Distributional criterion for the Philox stream: P5931, 200 sweeps,
-    burn-in 100, majority vote — ARI against the reference's posterior clustering inside the
-    reference's own seed-to-seed envelope (0.954-0.964) with a tolerance, 6-8 subclones."""
-    g = load_golden("sampler_P5931.npz")
-    out = cs.BayesNonparCluster(g["X"], cna_states_WGS=g["cna_states_WGS"], alpha=2, beta=2, niter=200,
-                                sigmas0=g["sigmas0"], U0=g["U0"], Z0=g["Z0"], seed=200, rng="philox")
+@pytest.mark.parametrize("name,mincell,ari_lo,ari_hi,ncl_lo,ncl_hi", [
+    ("P5931", 13, 0.95, 0.975, 5, 8),
+    ("BC_ductal2", 40, 0.70, 0.84, 12, 17)])
+def test_philox_chain_is_in_the_reference_envelope(cs, name, mincell, ari_lo, ari_hi, ncl_lo, ncl_hi):
+    """Distributional criterion for the Philox stream: 200 sweeps, burn-in 100,
+    majority vote -> ARI against the reference's own posterior clustering (its shipped Zall) and the
+    number of clusters above mincell.  The reference's own seed-to-seed envelope (R stream, seeds
+    200-203): P5931 ARI 0.954-0.964 / 6-8 clusters, BC_ductal2 0.737-0.778 / 14-17.  The
+    Philox stream over seeds 200-207, measured on the B200 (profiles/r2_philox_envelope.json,
+    tools/envelope.py): P5931 0.956-0.972 / 5-7, BC_ductal2 0.709-0.830 / 12-16 — the same
+    distribution sampled eight times instead of four; the bounds asserted here are the union of
+    the two ranges."""
+    g = load_golden(f"sampler_{name}.npz")
+    out = cs.BayesNonparCluster(g["X"], cna_states_WGS=g["cna_states_WGS"], alpha=float(g["alpha"]),
+                                beta=float(g["beta"]), niter=200, sigmas0=g["sigmas0"], U0=g["U0"], Z0=g["Z0"],
+                                seed=200, rng="philox")
     zm = cs.majority_vote(cs.MCMCtrim(out)["results"]["Zall"])
     zr = cs.majority_vote(g["Zall"][100:].astype(np.int32))
     ari = _ari(zm, zr)
     lab, cnt = np.unique(zm, return_counts=True)
-    nclu = int((cnt > 13).sum())
-    print("philox P5931 ARI", ari, "subclones", nclu)
-    assert ari >= 0.93 and 5 <= nclu <= 9
+    nclu = int((cnt > mincell).sum())
+    print("philox", name, "ARI", ari, "subclones", nclu)
+    assert ari_lo <= ari <= ari_hi and ncl_lo <= nclu <= ncl_hi
+
+
+@pytest.mark.parametrize("rng_name", ["philox", "R"])
+def test_tracing_flow_u0_with_na_rows(cs, oracle, rng_name):
+    """The tracing / update flow of R/RunCovCluster.R:118-134: AssignCluster's Uest — NA rows for every
+    dissolved or never-occupied label — goes back in as U0.  The reference keeps those rows (:47 only
+    truncates behind the last non-NA row): they hold no cell, are never scored (:193) or proposed
+    (:170), and still count towards kt and the numbering of new labels (:150-151, :209-218)."""
+    g = load_golden("sampler_P5931.npz")
+    X, R = g["X"], g["X"].shape[1]
+    obj = dict(results=dict(Zall=g["Zall"][100:].astype(np.int32), Uall=[np.zeros((int(g["kt"][-1]), R))]),
+               priors=dict(U0=g["U0"], cna_states_WGS=g["cna_states_WGS"], wU0=True), data=X)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res0 = cs.AssignCluster(obj, mincell=13)
+    Uest = res0["Uest"].values if hasattr(res0["Uest"], "values") else res0["Uest"]
+    assert Uest.shape[0] == 424 and np.isnan(Uest[:, 0]).sum() == 424 - 8
+    niter = 8
+    got = cs.BayesNonparCluster(X, cna_states_WGS=g["cna_states_WGS"], niter=niter, U0=Uest, seed=200, rng=rng_name)
+    U0t = Uest[:192]                                     # :47 up to the last non-NA row (label 192)
+    live = np.nonzero(~np.isnan(U0t[:, 0]))[0]
+    assert got["priors"]["U0"].shape == (192, R) and got["priors"]["wU0"] is True
+    sig0 = np.full(R, 0.25)
+    Z0 = (live[oracle.loglik_matrix(X, U0t[live], sig0).argmax(axis=1)] + 1).astype(np.int32)
+    assert np.array_equal(got["priors"]["Z0"], Z0)
+    want = oracle.gibbs(X, U0t, Z0, sig0, 2.0, 2.0, niter, 200,
+                        rng_mode=oracle.RNG_PHILOX if rng_name == "philox" else oracle.RNG_R, ucap_rows=niter * 512)
+    _assert_same_chain(got, want, niter)
+    assert want["kt"][0] > 192 and set(np.unique(want["Zall"][0])) - set(live + 1)   # new labels start at 193
+
+
+def test_u0_na_rows_synthetic_and_errors(cs, oracle):
+    """NA rows in front of, between and (truncated) behind the live rows; a live row without cells."""
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(1500, R=40, seed=31, K_true=5)
+    R = 40
+    nan = np.full(R, np.nan)
+    U0 = np.vstack([nan, s["U0"][0], nan, nan, s["U0"][1], np.full(R, 2.4), nan, nan])
+    live = np.array([1, 4, 5])
+    Z0 = (live[oracle.loglik_matrix(s["X"], U0[live], s["sigmas0"]).argmax(axis=1)] + 1).astype(np.int32)
+    for rng_name, mode in (("philox", oracle.RNG_PHILOX), ("R", oracle.RNG_R)):
+        got = cs.BayesNonparCluster(s["X"], niter=6, sigmas0=s["sigmas0"], U0=U0, seed=9, rng=rng_name)
+        assert np.array_equal(got["priors"]["Z0"], Z0) and got["priors"]["U0"].shape[0] == 6
+        want = oracle.gibbs(s["X"], U0[:6], Z0, s["sigmas0"], 2.0, 2.0, 6, 9, rng_mode=mode, ucap_rows=6 * 512)
+        _assert_same_chain(got, want, 6)
+        assert want["kt"][0] >= 6
+    Zbad = Z0.copy()
+    Zbad[3] = 3                                          # an NA row of U0
+    with pytest.raises(cs.ClonalscopeError) as e:
+        cs.BayesNonparCluster(s["X"], niter=2, sigmas0=s["sigmas0"], U0=U0, Z0=Zbad, rng="philox")
+    assert e.value.status == 6 and "NA row" in str(e.value)
 
 
 def test_kcap_overflow_is_reported(cs):
@@ -515,6 +576,56 @@ def test_full_size_binning_properties(cs):
         assert torch.equal(ocp, ocp2) and torch.equal(ori, ori2) and torch.equal(ox, ox2)
     finally:
         L.cs_bin_plan_destroy(plan)
+
+
+def test_full_size_binning_vs_oracle(cs, oracle):
+    """BASELINE config 4 at full size against the oracle itself: 100k cells x 30k genes -> 14,385
+    bins, every output slot (column pointers, bin ids, sums) byte-identical to the CPU restatement's
+    sparse sweep (~6 s on one core)."""
+    import ctypes as C
+    import torch
+    import bench
+    from clonalscope_b200 import synth
+    dev = torch.device("cuda", 0)
+    L = cs.lib()
+    N, G = 100000, 30000
+    bins, genes = synth.geometry(G=G)
+    mp, mb = synth.geometry_map(bins, genes)
+    B = len(bins["chr"])
+    colptr, rowidx, x = bench.synth_counts_gpu(torch, dev, N, G, seed=1001)
+    dp = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    plan = C.c_void_p()
+    assert L.cs_bin_plan_create(G, B, dp(mp, C.c_int32), dp(mb, C.c_int32), C.byref(plan)) == 0
+    try:
+        ocp = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        nnz = C.c_int64()
+        assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp), None, None, 0, C.byref(nnz), None) == 0
+        cap = nnz.value
+        ori = torch.empty(cap, dtype=torch.int32, device=dev)
+        ox = torch.empty(cap, dtype=torch.float64, device=dev)
+        assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp), vp(ori), vp(ox), cap, C.byref(nnz), None) == 0, L.cs_last_error()
+    finally:
+        L.cs_bin_plan_destroy(plan)
+    wcp, wri, wx = oracle.bin_counts(G, N, B, colptr.cpu().numpy(), rowidx.cpu().numpy(), x.cpu().numpy(), mp, mb)
+    assert nnz.value == len(wri) > 2e8
+    assert np.array_equal(ocp.cpu().numpy(), wcp)
+    assert np.array_equal(ori.cpu().numpy(), wri)
+    assert np.array_equal(ox.cpu().numpy(), wx)
+
+
+def test_full_size_sampler_vs_oracle(cs, oracle):
+    """BASELINE config 4 at full size against the oracle itself: 100k cells x 300 segments, the first
+    five (event-dense: ~22k, ~27k, ... label changes) sweeps of the bench chain, label for label and
+    Uall / sigma / Likelihood against the CPU restatement's sequential chain (~3.5 s per sweep)."""
+    from clonalscope_b200 import synth
+    N, R, niter = 100000, 300, 5
+    s = synth.sampler_input(N, R=R)
+    Z0 = (cs.loglik_matrix(s["X"], s["U0"], s["sigmas0"]).argmax(axis=1) + 1).astype(np.int32)
+    got, want = _philox_pair(cs, oracle, s["X"], s["U0"], Z0, s["sigmas0"], niter)
+    _assert_same_chain(got, want, niter)
+    moved = sum(int((want["Zall"][t] != want["Zall"][t - 1]).sum()) for t in range(1, niter))
+    assert moved > 30000
 
 
 def test_full_size_sampler_properties(cs):

@@ -154,6 +154,30 @@ def test_mcmctrim_slicing_and_quirk():
     short = dict(results=dict(Zall=Z[:30], Uall=list(range(30)), sigma_all=list(range(30)),
                               Likelihood=np.arange(30.0)), priors={}, data=None)
     assert MCMCtrim(short)["trim"]["burnin"] == 15
+    # -c(1:0) is -c(1, 0): burnin = 0 still drops the first sweep (R/MCMCtrim.R:27-30)
+    t0 = MCMCtrim(obj, burnin=0)
+    assert np.array_equal(t0["results"]["Zall"], Z[1:]) and t0["results"]["Uall"] == list(range(1, 200))
+    assert len(t0["results"]["Likelihood"]) == 199
+    assert np.array_equal(MCMCtrim(obj, burnin=2.7)["results"]["Zall"], Z[2:])
+
+
+def test_documented_refusals_raise_clonalscope_error(cs):
+    """The host-side refusals raise ClonalscopeError with their message (none needs a device: they
+    fire before any library call)."""
+    from clonalscope_b200 import _lib
+    e = cs.ClonalscopeError("only a message")
+    assert e.status == _lib.CS_ERR_UNSUPPORTED and "only a message" in str(e)
+    assert cs.ClonalscopeError(3, "m").status == 3
+    obj = dict(results=dict(Zall=np.ones((4, 5), dtype=np.int32), Uall=[np.ones((1, 2))]), priors={},
+               data=np.ones((5, 2)))
+    with pytest.raises(cs.ClonalscopeError, match="rm_extreme"):
+        cs.AssignCluster(obj, rm_extreme=True)
+    import scipy.sparse as sp
+    with pytest.raises(cs.ClonalscopeError, match="not in barcodes") as ei:
+        cs.EstRegionCov(sp.csc_matrix(np.ones((2, 2))), ["a", "b"], ["g1", "g2"],
+                        np.array([["1", 0, 10, "g1"], ["1", 20, 30, "g2"]], dtype=object),
+                        np.array([["a", "tumor"], ["zz", "normal"]], dtype=object))
+    assert ei.value.status == _lib.CS_ERR_ARG
 
 
 def test_bayesnonparcluster_argument_errors(cs):
