@@ -32,6 +32,7 @@
 #include "cs_common.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -722,6 +723,347 @@ bin_fill_stream_kernel(int N, int B, const int64_t *__restrict__ colptr,
     }
 }
 
+// ---- one-pass streaming aggregation (regular maps, sorted columns) --------------------------
+// The same rank-space idea as bin_fill_stream_kernel, organised so that (i) the matrix is read
+// from DRAM once and the result written once — no separate count kernel, no column scan: a
+// column's output offset comes from a decoupled look-back over the per-column counts — and
+// (ii) there is no shared-memory atomic per hit (ATOMS retires one lane every two cycles:
+// at ~2,500 hits per column it alone costs more than the column's share of a 60 %-of-HBM
+// budget).  Almost every hit opens a bin of its own (2 genes per 200-kb tile, 7 % of them
+// expressed in a cell), so the NEW part of every interval — [max(f, M), e) — is written with
+// plain stores, and only the part that falls on bins an earlier entry opened — [f, min(e, M)),
+// a tenth of the hits — is added atomically, after the stores of the tile are visible.
+//
+// One WARP per column (columns are handed out by a ticket, so a column's predecessors are
+// always held by running warps), no CTA barrier anywhere.  A column is traversed twice in tiles
+// of 256 entries (eight consecutive entries per lane, 256-bit loads):
+//   count  row indices only: interval ends, prefix max M across the tile (lane-serial over the
+//          eight entries + one warp scan), number of new bins -> the column's count; published,
+//          and the exclusive prefix over the columns in front is collected (look-back);
+//   fill   row indices again (L2 hits: they were read microseconds ago) + values; the ranks of
+//          new bins are the running count C; sums and bin ids go to a per-warp ring of 512
+//          ranks in shared memory and are flushed to the output in rank order (coalesced) as
+//          soon as no later entry can touch them: every rank below C - (M - f_last).
+// Exactness as in the other kernels: values must be integers (checked), and a column whose
+// n_entries x 2^bits(max |v|) could overflow an int32 sum raises FLAG_INEXACT (FP64 re-run).
+constexpr int OP_THREADS = 256;
+constexpr int OP_WARPS = OP_THREADS / 32;
+constexpr int OP_RING = 512;
+constexpr int OP_MASK = OP_RING - 1;
+constexpr int OP_EPL = 8;
+constexpr int OP_TILE = 32 * OP_EPL;
+constexpr int OP_MAXNH = 32; // widest gene, in bins, this kernel takes (8 x OP_MAXNH + OP_MAXNH ranks must fit the ring)
+constexpr unsigned long long OP_FLAG_A = 1ull << 62, OP_FLAG_P = 2ull << 62, OP_VALMASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ void op_load_g8(const int32_t *__restrict__ p, int (&g)[8], bool last_use)
+{
+    if (last_use)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]), "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7])
+                     : "l"(p));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]), "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7])
+                     : "l"(p));
+}
+__device__ __forceinline__ void op_load_x4(const double *__restrict__ p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
+                 : "l"(p));
+}
+__device__ __forceinline__ unsigned long long op_ld_status(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void op_st_status(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int warp_incl_sum(int v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(CS_FULL, v, off);
+        if (lane >= off) v += t;
+    }
+    return v;
+}
+
+// row indices of this lane's eight entries and their packed map words.  Outside the column:
+// -1 in front of it, INT_MAX behind it (so that "ascending" can be tested on all eight), word 0.
+__device__ __forceinline__ void op_tile_words(const int32_t *__restrict__ rowidx, const uint32_t *__restrict__ gmap,
+                                              int64_t gb, int64_t e0, int64_t e1, bool last_use, int (&g)[8],
+                                              uint32_t (&w)[8])
+{
+    if (gb >= e0 && gb + OP_EPL <= e1) {
+        op_load_g8(rowidx + gb, g, last_use);
+#pragma unroll
+        for (int i = 0; i < OP_EPL; i++) w[i] = __ldg(gmap + g[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < OP_EPL; i++) {
+            const bool in = gb + i >= e0 && gb + i < e1;
+            g[i] = in ? __ldg(rowidx + gb + i) : (gb + i < e0 ? -1 : INT_MAX);
+            w[i] = in ? __ldg(gmap + g[i]) : 0u;
+        }
+    }
+}
+
+// shared-memory accesses of the ring by 32-bit shared address ({sum, bin id} pairs of 8 bytes)
+__device__ __forceinline__ void op_ring_store_if(int cond_gt, int than, unsigned addr, int sum, int bin)
+{
+    asm volatile("{ .reg .pred p; setp.gt.s32 p, %0, %1; @p st.shared.v2.s32 [%2], {%3, %4}; }" ::"r"(cond_gt), "r"(than),
+                 "r"(addr), "r"(sum), "r"(bin)
+                 : "memory");
+}
+__device__ __forceinline__ void op_ring_add(unsigned addr, int v)
+{
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void op_ring_load(unsigned addr, int &sum, int &bin)
+{
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(sum), "=r"(bin) : "r"(addr) : "memory");
+}
+
+template <int CTAS_PER_SM>
+__global__ void __launch_bounds__(OP_THREADS, CTAS_PER_SM)
+bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                   const double *__restrict__ x, const uint32_t *__restrict__ gmap,
+                   int64_t *__restrict__ out_colptr, int32_t *__restrict__ out_rowidx, double *__restrict__ out_x,
+                   int64_t out_cap, int do_fill, unsigned long long *__restrict__ status, int *__restrict__ ticket,
+                   int *__restrict__ counts_actual, int *__restrict__ flags)
+{
+    __shared__ int2 s_ring_all[OP_WARPS][OP_RING];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring_all[wid][0]);
+    constexpr unsigned RB = OP_MASK * 8u; // byte mask of a ring offset
+    bool inexact = false, irregular = false;
+
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(ticket, 1);
+        c = __shfl_sync(CS_FULL, c, 0);
+        if (c >= N) break;
+        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+        const int64_t tb = e0 & ~(int64_t)(OP_EPL - 1);
+        // ---------------- count: number of distinct bins the column touches
+        int cnt = 0;
+        {
+            int carryM = 0, carryG = -1;
+            for (int64_t t0 = tb; t0 < e1; t0 += OP_TILE) {
+                int g[OP_EPL];
+                uint32_t w[OP_EPL];
+                op_tile_words(rowidx, gmap, t0 + OP_EPL * lane, e0, e1, !do_fill, g, w);
+                int before = __shfl_up_sync(CS_FULL, g[OP_EPL - 1], 1);
+                if (lane == 0) before = carryG;
+                bool bad = g[0] < before; // (row indices must ascend)
+                int lmax = 0;
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) {
+                    lmax = max(lmax, (int)(w[i] & 0xFFFFF) + (int)(w[i] >> 20));
+                    if (i) bad |= g[i] < g[i - 1];
+                }
+                irregular |= bad;
+                carryG = __shfl_sync(CS_FULL, g[OP_EPL - 1], 31);
+                const int incl = warp_incl_max(lmax, lane);
+                int m = __shfl_up_sync(CS_FULL, incl, 1);
+                if (lane == 0) m = 0;
+                m = max(m, carryM);
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) {
+                    const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
+                    cnt += max(0, e - max(f, m));
+                    m = max(m, e);
+                }
+                carryM = max(carryM, __shfl_sync(CS_FULL, incl, 31));
+            }
+            cnt = (int)__reduce_add_sync(CS_FULL, (unsigned)cnt);
+        }
+        // ---------------- the column's offset: publish the count now; the prefix over the columns in
+        // front is collected (look-back) only when the first ranks are about to be written, by
+        // which time the columns handed out just before this one have published theirs as well
+        if (lane == 0) op_st_status(status + c, OP_FLAG_A | (unsigned long long)cnt);
+        long long excl = 0;
+        auto look_back = [&]() {
+            int j = c - 1;
+            while (j >= 0) {
+                const int idx = j - lane;
+                unsigned long long sv = OP_FLAG_P; // (in front of column 0: an inclusive prefix of zero)
+                if (idx >= 0) {
+                    sv = op_ld_status(status + idx);
+                    while ((sv >> 62) == 0ull) {
+                        __nanosleep(100);
+                        sv = op_ld_status(status + idx);
+                    }
+                }
+                const unsigned pm = __ballot_sync(CS_FULL, (sv >> 62) == 2ull);
+                const int first = pm ? __ffs(pm) - 1 : 32; // nearest column whose inclusive prefix is known
+                long long v = (lane <= first) ? (long long)(sv & OP_VALMASK) : 0ll;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(CS_FULL, v, off);
+                excl += v;
+                if (pm) break;
+                j -= 32;
+            }
+            if (lane == 0) {
+                op_st_status(status + c, OP_FLAG_P | (unsigned long long)(excl + cnt));
+                out_colptr[c] = excl;
+                if (c == N - 1) out_colptr[N] = excl + cnt;
+            }
+        };
+        if (!do_fill) {
+            look_back();
+            continue;
+        }
+        // ---------------- fill
+        bool have_excl = false, skip = false;
+        int32_t *__restrict__ ocol_i = out_rowidx;
+        double *__restrict__ ocol_x = out_x;
+        int carryM = 0, carryC = 0, carryF = 0, flushed = 0, nz = 0;
+        unsigned orbits = 0;
+        for (int64_t t0 = tb; t0 < e1 && !skip; t0 += OP_TILE) {
+            const int64_t gb = t0 + OP_EPL * lane;
+            int g[OP_EPL], iv[OP_EPL];
+            uint32_t w[OP_EPL];
+            op_tile_words(rowidx, gmap, gb, e0, e1, true, g, w);
+            if (gb >= e0 && gb + OP_EPL <= e1) {
+                double v[OP_EPL];
+                op_load_x4(x + gb, v[0], v[1], v[2], v[3]);
+                op_load_x4(x + gb + 4, v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) {
+                    iv[i] = __double2int_rz(v[i]);
+                    inexact |= __int2double_rn(iv[i]) != v[i];
+                    orbits |= (unsigned)abs(iv[i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) {
+                    iv[i] = 0;
+                    if (gb + i >= e0 && gb + i < e1) {
+                        const double v = __ldcs(x + gb + i);
+                        iv[i] = __double2int_rz(v);
+                        inexact |= __int2double_rn(iv[i]) != v;
+                        orbits |= (unsigned)abs(iv[i]);
+                    }
+                }
+            }
+            // a tile goes through the ring in one round unless its new bins do not fit (then lane by lane)
+            for (;;) {
+                int lmax = 0, lf = 0;
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) {
+                    lmax = max(lmax, (int)(w[i] & 0xFFFFF) + (int)(w[i] >> 20));
+                    lf = max(lf, (int)(w[i] & 0xFFFFF)); // (starts do not decrease: the last one with a bin is the largest)
+                }
+                const int incl = warp_incl_max(lmax, lane);
+                int m0 = __shfl_up_sync(CS_FULL, incl, 1);
+                if (lane == 0) m0 = 0;
+                m0 = max(m0, carryM);
+                int ln = 0;
+                {
+                    int m = m0;
+#pragma unroll
+                    for (int i = 0; i < OP_EPL; i++) {
+                        const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
+                        ln += max(0, e - max(f, m));
+                        m = max(m, e);
+                    }
+                }
+                const int cincl = warp_incl_sum(ln, lane);
+                const int room = OP_RING - (carryC - flushed);
+                const int hi = __popc(__ballot_sync(CS_FULL, cincl <= room)); // lanes [0, hi) fit (cincl is non-decreasing)
+                const bool act = lane < hi;
+                unsigned oi[OP_EPL]; // old part of entry i: ring offset (bytes) of its first bin | number of bins << 16
+                {
+                    int m = m0, cr = act ? carryC + cincl - ln : 0;
+#pragma unroll
+                    for (int i = 0; i < OP_EPL; i++) {
+                        const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
+                        const int s = max(f, m);
+                        const int nn = act ? e - s : 0, old = act ? min(e, m) - f : 0;
+                        oi[i] = old > 0 ? ((((unsigned)(cr - m + f)) << 3) & RB) | ((unsigned)old << 16) : 0u;
+                        op_ring_store_if(nn, 0, ring + (((unsigned)cr << 3) & RB), iv[i], s);
+                        op_ring_store_if(nn, 1, ring + (((unsigned)(cr + 1) << 3) & RB), iv[i], s + 1);
+                        if (nn > 2) {
+#pragma unroll 1
+                            for (int k = 2; k < nn; k++)
+                                op_ring_store_if(1, 0, ring + (((unsigned)(cr + k) << 3) & RB), iv[i], s + k);
+                        }
+                        cr += max(nn, 0);
+                        m = max(m, e);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) {
+                    if (oi[i]) {
+                        const unsigned base = oi[i] & 0xFFFFu;
+                        const int n = (int)(oi[i] >> 16);
+#pragma unroll 1
+                        for (int k = 0; k < n; k++) op_ring_add(ring + ((base + 8u * k) & RB), iv[i]);
+                    }
+                }
+                __syncwarp();
+                const int src = (hi > 0 ? hi : 1) - 1;
+                carryM = max(carryM, __shfl_sync(CS_FULL, incl, src));
+                carryC += __shfl_sync(CS_FULL, cincl, src);
+                carryF = max(carryF, __reduce_max_sync(CS_FULL, act ? lf : 0));
+                if (carryC > cnt) { // (cannot happen for ascending rows: the count pass saw the same entries)
+                    irregular = true;
+                    skip = true;
+                    break;
+                }
+                // every rank below the bins the last start can still reach is final: flush them
+                const bool done = hi == 32 && t0 + OP_TILE >= e1;
+                const int frontier = done ? carryC : carryC - max(0, carryM - carryF);
+                if (frontier > flushed) {
+                    if (!have_excl) {
+                        look_back();
+                        have_excl = true;
+                        if (excl + cnt > out_cap) { // caller's buffers too small: report, write nothing
+                            if (lane == 0) flags[FLAG_CAP] = 1;
+                            skip = true;
+                            break;
+                        }
+                        ocol_i = out_rowidx + excl;
+                        ocol_x = out_x + excl;
+                    }
+                    for (int r = flushed + lane; r < frontier; r += 32) {
+                        int sv, bv;
+                        op_ring_load(ring + (((unsigned)r << 3) & RB), sv, bv);
+                        __stcs(ocol_x + r, (double)sv);
+                        __stcs(ocol_i + r, bv);
+                        nz += (sv != 0) ? 1 : 0;
+                    }
+                    flushed = frontier;
+                    __syncwarp();
+                }
+                if (hi == 32) break;
+                if (act) { // (these lanes are done: neutral from here on)
+#pragma unroll
+                    for (int i = 0; i < OP_EPL; i++) w[i] = 0u;
+                }
+            }
+        }
+        if (!have_excl) look_back(); // (empty columns, or columns given up on)
+        nz = (int)__reduce_add_sync(CS_FULL, (unsigned)nz);
+        orbits = __reduce_or_sync(CS_FULL, orbits);
+        if (lane == 0 && !skip) {
+            counts_actual[c] = nz;
+            if (nz != cnt) flags[FLAG_SHRUNK] = 1;
+            // an int32 sum takes at most (e1 - e0) values below 2^bits(orbits)
+            const int bits = 32 - __clz(orbits);
+            if (bits >= 31 || ((unsigned long long)(e1 - e0) << bits) > 2147483647ull) flags[FLAG_INEXACT] = 1;
+        }
+    }
+    if (inexact) flags[FLAG_INEXACT] = 1;
+    if (irregular) flags[FLAG_IRREG] = 1;
+}
+
 // closes the gaps left by dropped zero sums: column c's first nwritten entries (all of its
 // padded range when nwritten == NULL) are copied, zeros skipped, to the compact offsets
 __global__ void compact_columns_kernel(int N, const int64_t *__restrict__ old_colptr,
@@ -759,6 +1101,9 @@ struct cs_bin_plan {
     int G = 0, B = 0;
     bool regular = false; // contiguous hits with non-decreasing first bin: streaming kernels apply
     bool stream_fill = true; // (cleared for good when a matrix with unsorted columns shows up)
+    bool onepass = false; // regular and no gene wider than OP_MAXNH bins: the one-pass kernel applies
+    DevBuf<unsigned long long> status; // one-pass kernel: per-column look-back words
+    DevBuf<int> ticket;
     DevBuf<uint32_t> gmap;
     DevBuf<int32_t> map_ptr, map_bin;
     DevBuf<int> counts, counts2, flags;
@@ -817,6 +1162,10 @@ extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const in
             last_b0 = b0;
         }
         p->regular = reg;
+        int maxnh = 0;
+        for (int g = 0; g < G; g++)
+            if (gm[g] != GMAP_ESC) maxnh = maxnh > (int)(gm[g] >> 20) ? maxnh : (int)(gm[g] >> 20);
+        p->onepass = reg && maxnh <= OP_MAXNH;
     }
     int rc = CS_OK;
     do {
@@ -826,6 +1175,7 @@ extern "C" int cs_bin_plan_create(int G, int B, const int32_t *map_ptr, const in
         TRY(p->map_bin.alloc(nhits));
         TRY(p->flags.alloc(NFLAGS));
         TRY(p->grand.alloc(1));
+        TRY(p->ticket.alloc(1));
         TRY(cudaMallocHost((void **)&p->h_pinned, 64));
         for (int i = 0; i < 4; i++) TRY(cudaEventCreate(&p->ev[i]));
         TRY(cudaMemcpy(p->gmap.p, gm.data(), sizeof(uint32_t) * G, cudaMemcpyHostToDevice));
@@ -890,6 +1240,45 @@ static int run_scan(cs_bin_plan *p, int N, const int *counts, int64_t *out, cuda
     return CS_OK;
 }
 
+// what follows a fill whose flags are in p->h_pinned: the FP64 re-run for values an int32 sum cannot
+// carry, and the compaction of bins whose sum is zero (zeros_inline: the fill left them in place)
+static int finish_fill(cs_bin_plan *p, int N, const int64_t *d_colptr, const int32_t *d_rowidx, const double *d_x,
+                       int64_t *d_out_colptr, int32_t *d_out_rowidx, double *d_out_x, int64_t out_cap,
+                       int64_t *nnz_out, cudaStream_t st, bool streamed)
+{
+    int rc;
+    int64_t *h_nnz = reinterpret_cast<int64_t *>(p->h_pinned + NFLAGS);
+    bool zeros_inline = streamed; // the streaming fill leaves zero sums in place, the generic one drops them
+    if (p->h_pinned[FLAG_INEXACT]) { // non-integer / huge values: exact-order-free FP64 accumulators
+        zeros_inline = false;
+        CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
+        rc = launch_fill<double>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
+        if (rc) return rc;
+        CS_CUDA(cudaMemcpyAsync(p->h_pinned, p->flags.p, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+    }
+    if (p->h_pinned[FLAG_SHRUNK]) { // some touched bins summed to zero: close the gaps
+        const int64_t padded = *h_nnz;
+        CS_CUDA(p->colptr2.reserve((size_t)N + 1));
+        CS_CUDA(p->tmp_i.reserve((size_t)padded));
+        CS_CUDA(p->tmp_x.reserve((size_t)padded));
+        rc = run_scan(p, N, p->counts2.p, p->colptr2.p, st);
+        if (rc) return rc;
+        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, zeros_inline ? nullptr : p->counts2.p,
+                                                                 p->colptr2.p, d_out_rowidx, d_out_x, p->tmp_i.p,
+                                                                 p->tmp_x.p);
+        CS_CUDA(cudaGetLastError());
+        CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        *nnz_out = *h_nnz;
+        CS_CUDA(cudaMemcpyAsync(d_out_colptr, p->colptr2.p, sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyDeviceToDevice, st));
+        CS_CUDA(cudaMemcpyAsync(d_out_rowidx, p->tmp_i.p, sizeof(int32_t) * (size_t)*h_nnz, cudaMemcpyDeviceToDevice, st));
+        CS_CUDA(cudaMemcpyAsync(d_out_x, p->tmp_x.p, sizeof(double) * (size_t)*h_nnz, cudaMemcpyDeviceToDevice, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+    }
+    return CS_OK;
+}
+
 extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
                                  const int32_t *d_rowidx, const double *d_x,
                                  int64_t *d_out_colptr, int32_t *d_out_rowidx, double *d_out_x,
@@ -906,6 +1295,50 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
     CS_CUDA(p->counts.reserve(N));
     CS_CUDA(p->counts2.reserve(N));
     CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
+    if (d_out_rowidx) CS_REQUIRE(d_out_x != nullptr, "cs_bin_counts_dev: d_out_x is NULL");
+    // one pass (count, look-back and fill in one kernel) when the map is regular and the slots are
+    // aligned for 256-bit loads; CS_BIN_ONEPASS=0 keeps the count / scan / fill kernels
+    const bool onepass_env = !(getenv("CS_BIN_ONEPASS") && atoi(getenv("CS_BIN_ONEPASS")) == 0);
+    if (p->onepass && p->stream_fill && onepass_env && ((uintptr_t)d_rowidx % 32 == 0) && ((uintptr_t)d_x % 32 == 0)) {
+        CS_CUDA(p->status.reserve(N));
+        CS_CUDA(cudaMemsetAsync(p->status.p, 0, sizeof(unsigned long long) * (size_t)N, st));
+        CS_CUDA(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
+        // (CS_BIN_OP_CTAS = 2 | 3 | 4 CTAs per SM: registers per thread against warps in flight)
+        int ctas = getenv("CS_BIN_OP_CTAS") ? atoi(getenv("CS_BIN_OP_CTAS")) : 3;
+        auto kern = ctas == 4 ? bin_onepass_kernel<4> : (ctas == 2 ? bin_onepass_kernel<2> : bin_onepass_kernel<3>);
+        int per_sm = 0;
+        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OP_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        int grid = cs_num_sms() * per_sm;
+        if (grid > (N + OP_WARPS - 1) / OP_WARPS) grid = (N + OP_WARPS - 1) / OP_WARPS;
+        p->timed = false;
+        CS_CUDA(cudaEventRecord(p->ev[0], st));
+        CS_CUDA(cudaEventRecord(p->ev[1], st));
+        CS_CUDA(cudaEventRecord(p->ev[2], st));
+        kern<<<grid, OP_THREADS, 0, st>>>(N, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr, d_out_rowidx, d_out_x, out_cap,
+                                          d_out_rowidx ? 1 : 0, p->status.p, p->ticket.p, p->counts2.p, p->flags.p);
+        CS_CUDA(cudaGetLastError());
+        CS_CUDA(cudaEventRecord(p->ev[3], st));
+        int64_t *h_nnz1 = reinterpret_cast<int64_t *>(p->h_pinned + NFLAGS);
+        CS_CUDA(cudaMemcpyAsync(h_nnz1, d_out_colptr + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaMemcpyAsync(p->h_pinned, p->flags.p, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        *nnz_out = *h_nnz1;
+        if (p->h_pinned[FLAG_IRREG]) { // a column with unsorted rows (or a gene too wide): the generic kernels from now on
+            p->stream_fill = false;
+            p->regular = false;
+            return cs_bin_counts_dev(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, nnz_out,
+                                     stream);
+        }
+        if (!d_out_rowidx) return CS_OK;
+        p->timed = true;
+        if (p->h_pinned[FLAG_CAP]) {
+            cs_set_error("cs_bin_counts_dev: output capacity %lld < %lld entries needed", (long long)out_cap,
+                         (long long)*h_nnz1);
+            return CS_ERR_UCAP;
+        }
+        return finish_fill(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, nnz_out, st, true);
+    }
     const int words = (p->B + 31) / 32;
     int grid1 = cs_num_sms() * 16;
     if (grid1 > N) grid1 = N;
@@ -968,35 +1401,7 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         return cs_bin_counts_dev(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, nnz_out,
                                  stream);
     }
-    bool zeros_inline = streamed; // the streaming fill leaves zero sums in place, the generic one drops them
-    if (p->h_pinned[FLAG_INEXACT]) { // non-integer / huge values: exact-order-free FP64 accumulators
-        zeros_inline = false;
-        CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
-        rc = launch_fill<double>(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, st);
-        if (rc) return rc;
-        CS_CUDA(cudaMemcpyAsync(p->h_pinned, p->flags.p, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
-        CS_CUDA(cudaStreamSynchronize(st));
-    }
-    if (p->h_pinned[FLAG_SHRUNK]) { // some touched bins summed to zero: close the gaps
-        const int64_t padded = *h_nnz;
-        CS_CUDA(p->colptr2.reserve((size_t)N + 1));
-        CS_CUDA(p->tmp_i.reserve((size_t)padded));
-        CS_CUDA(p->tmp_x.reserve((size_t)padded));
-        rc = run_scan(p, N, p->counts2.p, p->colptr2.p, st);
-        if (rc) return rc;
-        compact_columns_kernel<<<cs_num_sms() * 8, 128, 0, st>>>(N, d_out_colptr, zeros_inline ? nullptr : p->counts2.p,
-                                                                 p->colptr2.p, d_out_rowidx, d_out_x, p->tmp_i.p,
-                                                                 p->tmp_x.p);
-        CS_CUDA(cudaGetLastError());
-        CS_CUDA(cudaMemcpyAsync(h_nnz, p->grand.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        CS_CUDA(cudaStreamSynchronize(st));
-        *nnz_out = *h_nnz;
-        CS_CUDA(cudaMemcpyAsync(d_out_colptr, p->colptr2.p, sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyDeviceToDevice, st));
-        CS_CUDA(cudaMemcpyAsync(d_out_rowidx, p->tmp_i.p, sizeof(int32_t) * (size_t)*h_nnz, cudaMemcpyDeviceToDevice, st));
-        CS_CUDA(cudaMemcpyAsync(d_out_x, p->tmp_x.p, sizeof(double) * (size_t)*h_nnz, cudaMemcpyDeviceToDevice, st));
-        CS_CUDA(cudaStreamSynchronize(st));
-    }
-    return CS_OK;
+    return finish_fill(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, nnz_out, st, streamed);
 }
 
 // ------------------------------------------------------- host (R-layout) form

@@ -14,6 +14,7 @@ struct ChainScal {
     int open_cell;    // Philox ring scan: command to the helper CTAs (cell that opened a cluster, -1 = leave)
     int open_slot;    //                    the slot it opened
     long long cells_scanned, n_events, n_reject, u_used;
+    long long n_rounds, cut_margin, cut_open, cut_maxev; // walk diagnostics: rounds, and what ended a round's commits early
 };
 
 // one entry of the inverse source index: a (cell, segment) whose proposal copies the source
@@ -55,7 +56,8 @@ struct ChainDev {
     int *icnt;        // N+1        inverse source index: offsets (after the scan)
     int *icur;        // N          fill cursors
     InvEntry *inv;    // N x R      inverse source index, entries grouped by source cell
-    int *nd;          // N          nearest later cell whose proposal copies this cell
+    unsigned *near;   // N x CS_NEAR_CAP  proposal sources at most CS_NEAR_W cells in front of the cell
+                      //            (source << 10 | segment; CS_NEAR_EMPTY behind the last; CS_NEAR_OVER: more than fit)
     long long *tile_sums; // scan scratch
     double *mean;     // kcap x R cluster means
     double *psum;     // partial sums workspace
@@ -73,6 +75,11 @@ struct ChainDev {
     double *u_rows;   // urec_cap x R
     long long urec_cap;
 };
+
+// near sources of a cell's proposal: the cells within CS_NEAR_W in front of it whose cluster state
+// it copies (what an event inside the same window of the walk can invalidate)
+constexpr int CS_NEAR_W = 512, CS_NEAR_CAP = 8;
+constexpr unsigned CS_NEAR_EMPTY = 0xFFFFFFFFu, CS_NEAR_OVER = 0xFFFFFFFEu;
 
 // cells per deterministic reduction chunk: at most 512 chunks, at least 256 cells each
 inline int cs_stat_chunk(int N) { const int c = (N + 511) / 512; return c < 256 ? 256 : ((c + 31) / 32) * 32; }

@@ -25,7 +25,8 @@ struct cs_chain {
     DevBuf<double> X, Xc, Ua, Ub, sig, isig, Q, E, qmin, ua, mean, psum, sigma_all, LL, u_rows, L0;
     DevBuf<long long> qnew_i, tile_sums, wn_q;
     DevBuf<double> wn_w;
-    DevBuf<int> kmin, icnt, icur, nd;
+    DevBuf<int> kmin, icnt, icur;
+    DevBuf<unsigned> near;
     DevBuf<InvEntry> inv;
     DevBuf<int> Zs, np, np0, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
     DevBuf<long long> u_off;
@@ -110,7 +111,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
         CS_CUDA(c->kmin.alloc((size_t)N + 8));
         CS_CUDA(c->icnt.alloc((size_t)N + 8));
         CS_CUDA(c->icur.alloc(N));
-        CS_CUDA(c->nd.alloc((size_t)N + 8));
+        CS_CUDA(c->near.alloc(((size_t)N + 8) * CS_NEAR_CAP));
         CS_CUDA(c->inv.alloc(nx));
         CS_CUDA(c->tile_sums.alloc((size_t)N / 1024 + 8));
         CS_CUDA(c->J.alloc(nx));
@@ -131,7 +132,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     D.slot_label = c->slot_label.p; D.sig = c->sig.p; D.isig = c->isig.p; D.Q = c->Q.p; D.J = c->J.p;
     D.E = c->E.p; D.qmin = c->qmin.p; D.ua = c->ua.p; D.qnew_i = c->qnew_i.p; D.icnt = c->icnt.p;
     D.wn_q = c->wn_q.p; D.wn_w = c->wn_w.p; D.kmin = c->kmin.p;
-    D.icur = c->icur.p; D.inv = c->inv.p; D.nd = c->nd.p; D.tile_sums = c->tile_sums.p;
+    D.icur = c->icur.p; D.inv = c->inv.p; D.near = c->near.p; D.tile_sums = c->tile_sums.p;
     D.zspec = c->zspec.p; D.qcols = c->qcols.p; D.mean = c->mean.p; D.psum = c->psum.p; D.pcnt = c->pcnt.p;
     D.newslot = c->newslot.p; D.mt = c->mt.p; D.scal = c->scal.p;
     D.Zall = c->Zall.p; D.sigma_all = c->sigma_all.p; D.LL = c->LL.p; D.kt_all = c->kt_all.p;
@@ -364,6 +365,19 @@ extern "C" int cs_chain_stats(cs_chain *c, int64_t *cells_scanned, int64_t *n_ev
     if (cells_scanned) *cells_scanned = h.cells_scanned;
     if (n_events) *n_events = h.n_events;
     if (n_reject) *n_reject = h.n_reject;
+    return CS_OK;
+}
+
+extern "C" int cs_chain_walk_stats(cs_chain *c, int64_t *rounds, int64_t *cut_margin, int64_t *cut_open, int64_t *cut_list)
+{
+    CS_REQUIRE(c != nullptr, "cs_chain_walk_stats: NULL chain");
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    ChainScal h;
+    CS_CUDA(cudaMemcpy(&h, c->D.scal, sizeof(h), cudaMemcpyDeviceToHost));
+    if (rounds) *rounds = h.n_rounds;
+    if (cut_margin) *cut_margin = h.cut_margin;
+    if (cut_open) *cut_open = h.cut_open;
+    if (cut_list) *cut_list = h.cut_maxev;
     return CS_OK;
 }
 

@@ -420,11 +420,21 @@ prepare_kernel(ChainDev D, int tt, int *__restrict__ rej)
             attempt++;
         }
         if (reject_live && lane == 0) rej[c] = (int)attempt;
+        int nnear = 0; // sources at most CS_NEAR_W cells in front of this one: what the walk re-checks within a round
 #pragma unroll
         for (int i = 0; i < NCH; i++) {
             const int r = lane + 32 * i;
             if (r < D.R) D.J[(size_t)c * D.R + r] = jj[i];
+            const bool nr = r < D.R && jj[i] >= 0 && jj[i] < c && c - jj[i] <= CS_NEAR_W;
+            const unsigned nb = __ballot_sync(CS_FULL, nr);
+            if (nr) {
+                const int slot = nnear + __popc(nb & ((1u << lane) - 1u));
+                if (slot < CS_NEAR_CAP) D.near[(size_t)c * CS_NEAR_CAP + slot] = ((unsigned)jj[i] << 10) | (unsigned)r;
+            }
+            nnear += __popc(nb);
         }
+        if (lane < CS_NEAR_CAP && lane >= nnear) D.near[(size_t)c * CS_NEAR_CAP + lane] = CS_NEAR_EMPTY;
+        if (nnear > CS_NEAR_CAP && lane == 0) D.near[(size_t)c * CS_NEAR_CAP + CS_NEAR_CAP - 1] = CS_NEAR_OVER;
         const long long qn = q_regs<NCH>(x, mu, s_isig16, D.R, lane);
         double ua, ub;
         cs_philox_draw(D.seed, (uint32_t)c, 0u, (uint32_t)tt, CS_PH_ASSIGN, 0u, ua, ub);
@@ -527,9 +537,49 @@ __global__ void index_fill_kernel(ChainDev D)
             en.pad = 0u;
             en.x = D.X[e];
             *reinterpret_cast<int4 *>(D.inv + p) = *reinterpret_cast<const int4 *>(&en);
-            atomicMin(&D.nd[j], cc); // nearest later cell whose proposal copies cell j
         }
     }
+}
+
+
+// ---------------------------------------------------------------- near sources inside a round
+// A round of the walks commits several events; a cell behind some of them keeps its draw when
+// (i) the counts' changes stay inside its margin and (ii) so does the change of its new-table
+// weight, if its proposal copied the cluster state of a cell that moves in the same round.
+// This is (ii): the cell's near sources (prepare_kernel) are looked up among the round's
+// candidates in front of it (s_cidx: candidate number of a window cell, 255 = none), the
+// proposal distance is corrected exactly as the commit will correct it, and the margin is
+// charged with the change of the weight (only the threshold u * total moves with it: by at
+// most that change).  Returns the margin that is left (<= 0: the cell has to be re-drawn).
+__device__ __forceinline__ double charge_near_sources(const ChainDev &D, const unsigned *nearc, int c, int pos, int K,
+                                                      const unsigned char *s_cidx, const int *s_ev_a, const int *s_ev_b,
+                                                      const double *s_isig16, long long qi, double qmin, double w_new,
+                                                      double m)
+{
+    long long dq = 0;
+    bool dep = false;
+#pragma unroll 1
+    for (int k = 0; k < CS_NEAR_CAP; k++) {
+        const unsigned en = nearc[k];
+        if (en == CS_NEAR_EMPTY) break;
+        if (en == CS_NEAR_OVER) return -1.0; // (more near sources than the list holds: re-drawn next round)
+        const int j = (int)(en >> 10);
+        if (j < pos) continue;
+        const int ci = s_cidx[j - pos];
+        if (ci >= K) continue;               // (not a candidate, or one this round cannot reach)
+        const int r = (int)(en & 1023u);
+        const double xv = D.X[(size_t)c * D.R + r];
+        dep = true;
+        if (!cs_isna(xv))
+            dq += tint(xv, D.U[(size_t)s_ev_b[ci] * D.R + r], s_isig16[r]) - tint(xv, D.U[(size_t)s_ev_a[ci] * D.R + r], s_isig16[r]);
+    }
+    if (dep && dq != 0) {
+        const double q2 = (double)(qi + dq) * Q_SCALE;
+        if (!(q2 >= qmin)) return -1.0;      // (the proposal would become the reference of the cached exponentials)
+        const double w2 = __dmul_rn(D.beta, exp(-0.5 * (q2 - qmin)));
+        m -= fabs(w2 - w_new) * 1.000000001 + 1e-300;
+    }
+    return m;
 }
 
 // ---------------------------------------------------------------- scan (one CTA, thread per cell)
@@ -550,12 +600,15 @@ scan_kernel(ChainDev D, int tt)
     int *s_np0 = s_label + D.kcap;            // counts at the start of the sweep
     __shared__ int s_nlive, s_kt, s_err, s_block, s_wcnt[WIN_THREADS / 32];
     // the round's event candidates in cell order: cell, old slot, new slot, dependents' range, nearest dependent
-    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV], s_ev_nd[MAX_EV];
+    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV];
+    __shared__ unsigned char s_cidx[WIN_CELLS]; // candidate number of every window cell (255: not a candidate)
     __shared__ long long s_scanned, s_events;
+    __shared__ int s_diag[4]; // rounds, rounds cut short by a margin / an opened cluster / the event list
 
     const int f0 = D.scal->first_event;
     if (f0 >= D.N) return;
     for (int r = threadIdx.x; r < D.R; r += WIN_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
+    if (threadIdx.x < 4) s_diag[threadIdx.x] = 0;
     for (int s = threadIdx.x; s < D.kcap; s += WIN_THREADS) {
         const int n = D.np[s];
         s_np[s] = n;
@@ -631,28 +684,18 @@ scan_kernel(ChainDev D, int tt)
             s_ev_b[jc] = z;
             s_ev_e0[jc] = D.icnt[c];     // range of its dependents in the inverse index
             s_ev_e1[jc] = D.icnt[c + 1];
-            s_ev_nd[jc] = D.nd[c];       // nearest later cell whose proposal copies it
         }
+        if (threadIdx.x < WIN_CELLS) s_cidx[threadIdx.x] = (cand && jc < MAX_EV) ? (unsigned char)jc : (unsigned char)255;
         if (threadIdx.x == 0) s_block = INT_MAX;
         __syncthreads();
         // ---- how many of them can be committed in this round, in order, with every draw in front
-        // of each provably unchanged.  Candidate j is out when it lies behind the nearest cell
-        // whose proposal copied an earlier candidate of the round (that cell's distance is about
-        // to be corrected) or behind a candidate that opens a cluster (a column the window has not
-        // scored) ...
+        // of each provably unchanged.  Candidate j is out when it lies behind a candidate that
+        // opens a cluster (a column the window has not scored) ...
         int K = min(ncand, MAX_EV);
-        {
-            int lim = min(D.N, pos + W);
-            for (int j = 0; j < K; j++) {
-                if (s_ev_f[j] >= lim) {
-                    K = j;
-                    break;
-                }
-                if (s_ev_b[j] == nlive) {
-                    K = j + 1;
-                    break;
-                }
-                lim = min(lim, s_ev_nd[j]);
+        for (int j = 0; j < K; j++) {
+            if (s_ev_b[j] == nlive) {
+                K = j + 1;
+                break;
             }
         }
         // ... or when a cell between the previous candidate and itself (itself included) runs out
@@ -661,13 +704,19 @@ scan_kernel(ChainDev D, int tt)
         // no special case: its weight n * E[.] changes by at most E[.], and re-referencing the
         // exponentials to another minimum rescales all weights of a cell by one factor — relative
         // effect ~1e-15, inside the allowance.)
+        // ... or when the proposal of such a cell copied the cluster state of a cell that moves in this
+        // round and its new-table weight changes by more than what is left of the margin.
         if (active && jc >= 1 && jc < K) {
             double m = margin;
             for (int i = 0; i < jc && m > 0.0; i++)
                 m -= (s_e[s_ev_a[i] * WIN_CELLS + threadIdx.x] + s_e[s_ev_b[i] * WIN_CELLS + threadIdx.x]) * 1.000000001;
+            if (m > 0.0)
+                m = charge_near_sources(D, D.near + (size_t)c * CS_NEAR_CAP, c, pos, K, s_cidx, s_ev_a, s_ev_b, s_isig16,
+                                        __ldcg(D.qnew_i + c), D.qmin[c], D.wn_w[c], m);
             if (!(m > 0.0)) atomicMin(&s_block, jc);
         }
         __syncthreads();
+        const int K0 = K;
         K = min(K, s_block);
         const int nev = K;
         const bool opened = nev > 0 && s_ev_b[nev - 1] == nlive;
@@ -705,7 +754,11 @@ scan_kernel(ChainDev D, int tt)
             s_npd[sl] = n > 0 ? (double)n : 0.0;
             s_npd1[sl] = n > 1 ? (double)(n - 1) : 0.0;
         }
-        if (threadIdx.x == 0) s_events += nev;
+        if (threadIdx.x == 0) {
+            s_events += nev;
+            s_diag[0]++;
+            if (nev < ncand) s_diag[nev < K0 ? 1 : (opened ? 2 : 3)]++;
+        }
         __syncthreads();
         if (s_err) break;
         // ---- proposals that copied a moved cell's cluster state: correct their distance exactly
@@ -777,6 +830,10 @@ scan_kernel(ChainDev D, int tt)
         D.scal->kt = s_kt;
         D.scal->cells_scanned += s_scanned;
         D.scal->n_events += s_events;
+        D.scal->n_rounds += s_diag[0];
+        D.scal->cut_margin += s_diag[1];
+        D.scal->cut_open += s_diag[2];
+        D.scal->cut_maxev += s_diag[3];
         if (s_err) D.scal->err = s_err;
     }
 }
@@ -823,7 +880,8 @@ struct RingFixed {
     long long qi[Cfg::RING], wq[Cfg::RING];        // proposal distance (fixed point); the one the cached weight is for
     double w[Cfg::RING], qmin[Cfg::RING], ua[Cfg::RING]; // cached new-table weight, reference, uniform
     double e[Cfg::SLOTS * Cfg::RING];         // cached exponentials [slot][cell]
-    int z[Cfg::RING], km[Cfg::RING], i0[Cfg::RING], nd[Cfg::RING]; // old slot, cluster at the reference, dependents' offset, nearest dependent
+    int z[Cfg::RING], km[Cfg::RING], i0[Cfg::RING]; // old slot, cluster at the reference, dependents' offset
+    unsigned near[Cfg::RING * CS_NEAR_CAP];         // near sources of the proposal (see charge_near_sources)
     InvEntry dep[DEP_STAGE];             // staged index entries of the round's dependents
     double npd[Cfg::SLOTS + 2], npd1[Cfg::SLOTS + 2];
 };
@@ -845,6 +903,13 @@ __device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed<Cfg> &F,
     const size_t N = (size_t)D.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = warp; k < nlive + 9; k += WIN_THREADS / 32) {
+        if (k == nlive + 8) { // near sources: CS_NEAR_CAP words = two 16-byte groups per cell
+            for (int q = lane; q < ncell * 2; q += 32) {
+                const int c = lo + (q >> 1), h = (q & 1) * 4;
+                cp_async_16_cg(F.near + (size_t)(c & Cfg::RMASK) * CS_NEAR_CAP + h, D.near + (size_t)c * CS_NEAR_CAP + h);
+            }
+            continue;
+        }
         if (k < nlive + 5) {
             const double *src;
             double *dst;
@@ -887,12 +952,9 @@ __device__ __forceinline__ void ring_issue(const ChainDev &D, RingFixed<Cfg> &F,
             } else if (k == nlive + 6) {
                 src = D.kmin;
                 dst = F.km;
-            } else if (k == nlive + 7) {
+            } else {
                 src = D.icnt;
                 dst = F.i0;
-            } else {
-                src = D.nd;
-                dst = F.nd;
             }
             for (int q = lane; q < ncell / 4; q += 32) {
                 const int c = lo + 4 * q;
@@ -1029,9 +1091,11 @@ scan_ring_kernel(ChainDev D, int tt)
     int *s_label = s_np + D.kcap, *s_np0 = s_label + D.kcap;
     double *s_isig16 = reinterpret_cast<double *>(s_ring_raw + sizeof(RingFixed<Cfg>) + sizeof(int) * ((3 * (size_t)D.kcap + 1) & ~(size_t)1));
     __shared__ int s_nlive, s_kt, s_err, s_block, s_wcnt[WIN_THREADS / 32];
-    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV], s_ev_nd[MAX_EV];
+    __shared__ int s_ev_f[MAX_EV], s_ev_a[MAX_EV], s_ev_b[MAX_EV], s_ev_e0[MAX_EV], s_ev_e1[MAX_EV];
+    __shared__ unsigned char s_cidx[Cfg::WINC]; // candidate number of every window cell (255: not a candidate)
     __shared__ int s_ev_off[MAX_EV + 1]; // dependents in front of each candidate's own (prefix of e1 - e0)
     __shared__ long long s_scanned, s_events;
+    __shared__ int s_diag[4]; // rounds, rounds cut short by a margin / an opened cluster / the event list
 
     // (uniform over the cluster: the scalars are written back only after the last cluster barrier)
     const int f0 = D.scal->first_event;
@@ -1068,6 +1132,7 @@ scan_ring_kernel(ChainDev D, int tt)
         s_scanned = 0;
         s_events = 0;
     }
+    if (threadIdx.x < 4) s_diag[threadIdx.x] = 0;
     const size_t N = (size_t)D.N;
     const int Npad = (D.N + 4) & ~3; // cells 0..N, in whole groups of four
     int pos = f0, W = WIN_MIN;
@@ -1128,29 +1193,18 @@ scan_ring_kernel(ChainDev D, int tt)
             s_ev_b[jc] = z;
             s_ev_e0[jc] = F.i0[ri];
             s_ev_e1[jc] = F.i0[(c + 1) & Cfg::RMASK];
-            s_ev_nd[jc] = F.nd[ri];
         }
+        if (threadIdx.x < Cfg::WINC) s_cidx[threadIdx.x] = (cand && jc < MAX_EV) ? (unsigned char)jc : (unsigned char)255;
         if (threadIdx.x == 0) s_block = INT_MAX;
         __syncthreads();
         // ---- how many can be committed in this round (scan_kernel's rules; every warp works it
-        // out for itself, one candidate per lane): candidate j is out when it lies at or behind
-        // the nearest dependent of an earlier candidate, or behind one that opens a cluster
+        // out for itself, one candidate per lane): candidate j is out when it lies behind one that
+        // opens a cluster
         int K = min(ncand, MAX_EV);
         {
             const bool mine = lane < K;
-            const int fj = mine ? s_ev_f[lane] : 0;
-            int lim = mine ? s_ev_nd[lane] : INT_MAX; // -> min over candidates in front of this lane
             const bool opens = mine && s_ev_b[lane] == nlive;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int o = __shfl_up_sync(CS_FULL, lim, off);
-                if (lane >= off) lim = min(lim, o);
-            }
-            lim = __shfl_up_sync(CS_FULL, lim, 1);
-            if (lane == 0) lim = INT_MAX;
-            const unsigned bad = __ballot_sync(CS_FULL, mine && fj >= lim);
             const unsigned opn = __ballot_sync(CS_FULL, opens);
-            if (bad) K = min(K, __ffs(bad) - 1);
             if (opn) K = min(K, __ffs(opn));
             if (warp == 0) { // where each candidate's dependents start in the round's flattened list
                 int len = lane < K ? s_ev_e1[lane] - s_ev_e0[lane] : 0, inc = len;
@@ -1166,14 +1220,20 @@ scan_ring_kernel(ChainDev D, int tt)
         // ... or when a cell between the previous candidate and itself (itself included) runs out
         // of margin: each of the jc events in front of a cell moves its sums and threshold by at
         // most E[a] + E[b]
+        // most E[a] + E[b]; so does its new-table weight when its proposal copied the cluster state of
+        // a cell that moves in this round (charge_near_sources)
         if (active && jc >= 1 && jc < K) {
             double m = margin;
             const double *ecol = F.e + ri;
             for (int i = 0; i < jc; i++)
                 m -= (ecol[(size_t)s_ev_a[i] * Cfg::RING] + ecol[(size_t)s_ev_b[i] * Cfg::RING]) * 1.000000001;
+            if (m > 0.0)
+                m = charge_near_sources(D, F.near + (size_t)ri * CS_NEAR_CAP, c, pos, K, s_cidx, s_ev_a, s_ev_b, s_isig16,
+                                        F.qi[ri], F.qmin[ri], F.w[ri], m);
             if (!(m > 0.0)) atomicMin(&s_block, jc);
         }
         __syncthreads();
+        const int K0 = K;
         K = min(K, s_block);
         const int nev = K;
         const bool opened = nev > 0 && s_ev_b[nev - 1] == nlive;
@@ -1230,6 +1290,8 @@ scan_ring_kernel(ChainDev D, int tt)
         if (threadIdx.x == 0) {
             s_events += nev;
             s_scanned += (nev ? lo - pos : min(We, D.N - pos));
+            s_diag[0]++;
+            if (nev < ncand) s_diag[nev < K0 ? 1 : (opened ? 2 : 3)]++;
         }
         __syncthreads();
         if (s_err) break;
@@ -1303,6 +1365,10 @@ scan_ring_kernel(ChainDev D, int tt)
         D.scal->kt = s_kt;
         D.scal->cells_scanned += s_scanned;
         D.scal->n_events += s_events;
+        D.scal->n_rounds += s_diag[0];
+        D.scal->cut_margin += s_diag[1];
+        D.scal->cut_open += s_diag[2];
+        D.scal->cut_maxev += s_diag[3];
         D.scal->first_event = s_err ? D.N : resume; // what is left for scan_kernel
         if (s_err) D.scal->err = s_err;
     }
@@ -1864,7 +1930,6 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
             seq_scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, 0, rej);
         } else {
             CS_CUDA(cudaMemsetAsync(D.icnt, 0, sizeof(int) * ((size_t)D.N + 1), st));
-            CS_CUDA(cudaMemsetAsync(D.nd, 0x7f, sizeof(int) * (size_t)D.N, st));
             index_count_kernel<<<nsm * 8, 256, 0, st>>>(D);
             index_scan_kernel<<<1, 1024, 0, st>>>(D);
             index_fill_kernel<<<nsm * 8, 256, 0, st>>>(D);

@@ -146,4 +146,71 @@ extern "C" int cs_sigma_stats_dev(int N, int R, int K, const double *d_X, const 
     return CS_OK;
 }
 
+// ---- host (R layout) forms: what a `.Call` stub can bind (AssignCluster :46-53, :67-77) ---------
+template <typename T>
+int cs_transpose(int rows, int cols, const T *d_in, T *d_out, cudaStream_t st);
+
+// X: N x R column-major; Z: N labels (labels outside 1..K are skipped, like cells AssignCluster has
+// set aside); sum_x / cnt_x: K x R column-major; n_k: K
+extern "C" int cs_cluster_stats(int N, int R, int K, const double *X, const int *Z, double *sum_x, double *cnt_x,
+                                double *n_k)
+{
+    CS_REQUIRE(N >= 0 && R >= 1 && K >= 1 && sum_x && cnt_x && n_k && (N == 0 || (X && Z)), "cs_cluster_stats: bad arguments");
+    DevBuf<double> dXc, dX, dS, dC, dSc, dCc, dN;
+    DevBuf<int> dZ;
+    const size_t nx = (size_t)N * R, nk = (size_t)K * R;
+    CS_CUDA(dXc.alloc(nx));
+    CS_CUDA(dX.alloc(nx));
+    CS_CUDA(dZ.alloc(N));
+    CS_CUDA(dS.alloc(nk));
+    CS_CUDA(dC.alloc(nk));
+    CS_CUDA(dSc.alloc(nk));
+    CS_CUDA(dCc.alloc(nk));
+    CS_CUDA(dN.alloc(K));
+    int rc;
+    if (N) {
+        CS_CUDA(cudaMemcpy(dXc.p, X, sizeof(double) * nx, cudaMemcpyHostToDevice));
+        CS_CUDA(cudaMemcpy(dZ.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
+        if ((rc = cs_transpose<double>(R, N, dXc.p, dX.p, 0))) return rc; // column-major N x R -> cell-major
+    }
+    if ((rc = cs_cluster_stats_dev(N, R, K, dX.p, dZ.p, dS.p, dC.p, dN.p, nullptr))) return rc;
+    // row-major K x R -> column-major K x R (== row-major R x K)
+    if ((rc = cs_transpose<double>(K, R, dS.p, dSc.p, 0))) return rc;
+    if ((rc = cs_transpose<double>(K, R, dC.p, dCc.p, 0))) return rc;
+    CS_CUDA(cudaMemcpy(sum_x, dSc.p, sizeof(double) * nk, cudaMemcpyDeviceToHost));
+    CS_CUDA(cudaMemcpy(cnt_x, dCc.p, sizeof(double) * nk, cudaMemcpyDeviceToHost));
+    CS_CUDA(cudaMemcpy(n_k, dN.p, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost));
+    return CS_OK;
+}
+
+// U: K x R column-major; sq[r] = sum over cells with a label in 1..K of (x - U[z, r])^2 (NA skipped),
+// cnt[r] = number of non-NA x in segment r over ALL cells (R/BayesNonparCluster.R:234)
+extern "C" int cs_sigma_stats(int N, int R, int K, const double *X, const int *Z, const double *U, double *sq,
+                              double *cnt)
+{
+    CS_REQUIRE(N >= 0 && R >= 1 && K >= 1 && U && sq && cnt && (N == 0 || (X && Z)), "cs_sigma_stats: bad arguments");
+    DevBuf<double> dXc, dX, dUc, dU, dQ, dC;
+    DevBuf<int> dZ;
+    const size_t nx = (size_t)N * R, nk = (size_t)K * R;
+    CS_CUDA(dXc.alloc(nx));
+    CS_CUDA(dX.alloc(nx));
+    CS_CUDA(dZ.alloc(N));
+    CS_CUDA(dUc.alloc(nk));
+    CS_CUDA(dU.alloc(nk));
+    CS_CUDA(dQ.alloc(R));
+    CS_CUDA(dC.alloc(R));
+    int rc;
+    if (N) {
+        CS_CUDA(cudaMemcpy(dXc.p, X, sizeof(double) * nx, cudaMemcpyHostToDevice));
+        CS_CUDA(cudaMemcpy(dZ.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
+        if ((rc = cs_transpose<double>(R, N, dXc.p, dX.p, 0))) return rc;
+    }
+    CS_CUDA(cudaMemcpy(dUc.p, U, sizeof(double) * nk, cudaMemcpyHostToDevice));
+    if ((rc = cs_transpose<double>(R, K, dUc.p, dU.p, 0))) return rc;
+    if ((rc = cs_sigma_stats_dev(N, R, K, dX.p, dZ.p, dU.p, dQ.p, dC.p, nullptr))) return rc;
+    CS_CUDA(cudaMemcpy(sq, dQ.p, sizeof(double) * (size_t)R, cudaMemcpyDeviceToHost));
+    CS_CUDA(cudaMemcpy(cnt, dC.p, sizeof(double) * (size_t)R, cudaMemcpyDeviceToHost));
+    return CS_OK;
+}
+
 // allele variant lives in cs_allele.cu

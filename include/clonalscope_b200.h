@@ -157,6 +157,9 @@ int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *ind
                     double *eos_ms);
 /* number of cells the sequential scan kernel had to process (diagnostics) */
 int cs_chain_stats(cs_chain *c, int64_t *cells_scanned, int64_t *n_events, int64_t *n_reject);
+/* the windowed walk's rounds since cs_chain_init, and how many of them stopped committing before the
+ * window's last candidate because a cell ran out of margin / a cluster opened / the event list was full */
+int cs_chain_walk_stats(cs_chain *c, int64_t *rounds, int64_t *cut_margin, int64_t *cut_open, int64_t *cut_list);
 int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double *LL, double *L0,
                    int *kt_all, int64_t ucap_rows, int64_t *u_off, int *u_labels,
                    double *u_rows);
@@ -200,6 +203,14 @@ int cs_cluster_stats_dev(int N, int R, int K, const double *d_X, const int *d_Z,
                          double *d_sum_x, double *d_cnt_x, double *d_nk, void *stream);
 int cs_sigma_stats_dev(int N, int R, int K, const double *d_X, const int *d_Z,
                        const double *d_U, double *d_sq, double *d_cnt, void *stream);
+/* Host (R layout) forms — what AssignCluster's `.Call` stubs bind for its means and sigmas
+ *   R/AssignCluster.R:46-53, :67-77 (colMeans per cluster, sqrt(1/N * colSums((X - U[Z,])^2))).
+ * X: N x R, sum_x / cnt_x / U: K x R, all column-major; labels outside 1..K are skipped
+ * (the cells AssignCluster has set aside); cnt[r] counts the non-NA entries of ALL cells. */
+int cs_cluster_stats(int N, int R, int K, const double *X, const int *Z,
+                     double *sum_x, double *cnt_x, double *n_k);
+int cs_sigma_stats(int N, int R, int K, const double *X, const int *Z, const double *U,
+                   double *sq, double *cnt);
 
 /* ------------------------------------------------------------------------
  * per-gene sums and sums of squares over the cells of a G x N dgCMatrix (slots @i @x, nnz

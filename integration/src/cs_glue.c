@@ -1,9 +1,11 @@
 /*
  * cs_glue.c — `.Call` glue between R and libclonalscope_b200.so.
  *
- * NOT compiled in this repository's image (no R headers there): written against the
- * documented R C API and kept deliberately thin — unpack SEXPs, call the C ABI of
- * include/clonalscope_b200.h, pack the results.  No arithmetic happens here.
+ * Written against the documented R C API and kept deliberately thin — unpack SEXPs, call the
+ * C ABI of include/clonalscope_b200.h, pack the results.  No arithmetic happens here.
+ * R is not installed in this repository's image: the file is compiled in the CPU test suite
+ * against a declarations-only copy of the R API (integration/rstub/) so that any drift against
+ * include/clonalscope_b200.h is a compile error; it is linked and run only in an R installation.
  *
  * Conventions: R owns all memory (allocVector + PROTECT); inputs are read
  * only; errors are raised with Rf_error() from this outermost C frame only, after every
@@ -22,7 +24,16 @@ static void check(int rc)
     if (rc != CS_OK) Rf_error("clonalscope_b200: %s", cs_last_error());
 }
 
-/* .Call("cs_R_loglik_matrix", X, U, sigma): N x K matrix */
+/* rows of Uall the one-shot samplers may record: niter x min(N, kcap) + slack (kcap: the
+ * library's default capacities, include/clonalscope_b200.h cs_gibbs_opts.kcap) */
+static int64_t ucap_rows(int niter, int N, int rng_mode)
+{
+    const int per = rng_mode == CS_RNG_R ? 512 : 256;
+    return (int64_t)niter * (N < per ? N : per) + 4096;
+}
+
+/* .Call("cs_R_loglik_matrix", X, U, sigma): N x K matrix
+ * (R/BayesNonparCluster.R:91-96 Z0 default, R/AssignCluster.R:58 orphans' scores) */
 SEXP cs_R_loglik_matrix(SEXP X, SEXP U, SEXP sigma)
 {
     const int N = Rf_nrows(X), R = Rf_ncols(X), K = Rf_nrows(U);
@@ -33,7 +44,8 @@ SEXP cs_R_loglik_matrix(SEXP X, SEXP U, SEXP sigma)
     return LL;
 }
 
-/* .Call("cs_R_bin_counts", p, i, x, G, map_ptr, map_bin, B): list(p, i, x) of the bin x cell dgCMatrix */
+/* .Call("cs_R_bin_counts", p, i, x, G, map_ptr, map_bin, B): list(p, i, x) of the bin x cell dgCMatrix
+ * (R/Gene_bin_cell_rna_filtered.R:69-81; R/EstRegionCov.R:88-93,131-137 with segments as bins) */
 SEXP cs_R_bin_counts(SEXP p, SEXP i, SEXP x, SEXP G, SEXP map_ptr, SEXP map_bin, SEXP B)
 {
     const int N = LENGTH(p) - 1;
@@ -55,16 +67,17 @@ SEXP cs_R_bin_counts(SEXP p, SEXP i, SEXP x, SEXP G, SEXP map_ptr, SEXP map_bin,
 }
 
 /* .Call("cs_R_ncrp_gibbs", X, U0, Z0, sigmas0, alpha, beta, niter, seed, rng_mode, device)
- * -> list(Zall, sigma_all, Likelihood, L0, kt, u_off, u_labels, u_rows, rng_state) */
+ * -> list(Zall, sigma_all, Likelihood, L0, kt, u_off, u_labels, u_rows, rng_state)
+ * (R/BayesNonparCluster.R:133-277) */
 SEXP cs_R_ncrp_gibbs(SEXP X, SEXP U0, SEXP Z0, SEXP sigmas0, SEXP alpha, SEXP beta, SEXP niter_, SEXP seed,
                      SEXP rng_mode, SEXP device)
 {
     const int N = Rf_nrows(X), R = Rf_ncols(X), K0 = Rf_nrows(U0), niter = Rf_asInteger(niter_);
-    const int64_t ucap = (int64_t)niter * 160 + 4096;
     cs_gibbs_opts o;
     memset(&o, 0, sizeof(o));
     o.rng_mode = Rf_asInteger(rng_mode);
     o.device = Rf_asInteger(device);
+    const int64_t ucap = ucap_rows(niter, N, o.rng_mode);
     SEXP Zall = PROTECT(Rf_allocMatrix(INTSXP, niter, N));
     SEXP sig = PROTECT(Rf_allocMatrix(REALSXP, R, niter));
     SEXP LL = PROTECT(Rf_allocVector(REALSXP, niter));
@@ -90,7 +103,48 @@ SEXP cs_R_ncrp_gibbs(SEXP X, SEXP U0, SEXP Z0, SEXP sigmas0, SEXP alpha, SEXP be
     return out;
 }
 
-/* .Call("cs_R_majority_vote", Zall): integer vector, one label per cell */
+/* .Call("cs_R_ncrp_gibbs_allele", Xcov, Xallele, U0, Z0, sig0_cov, sig0_allele, alpha, beta, niter, seed,
+ *       maxcp, rng_mode, device)
+ * -> list(Zall, sigma_cov_all, sigma_allele_all, Likelihood, L0, kt, u_off, u_labels, u_state, u_cov, u_allele)
+ * (R/BayesNonparAlleleCluster.R:101-290, R/genotype_neighbor.R:7-40); U0: integer state ids */
+SEXP cs_R_ncrp_gibbs_allele(SEXP Xcov, SEXP Xallele, SEXP U0, SEXP Z0, SEXP sig0_cov, SEXP sig0_allele, SEXP alpha,
+                            SEXP beta, SEXP niter_, SEXP seed, SEXP maxcp, SEXP rng_mode, SEXP device)
+{
+    const int N = Rf_nrows(Xcov), R = Rf_ncols(Xcov), K0 = Rf_nrows(U0), niter = Rf_asInteger(niter_);
+    cs_gibbs_opts o;
+    memset(&o, 0, sizeof(o));
+    o.rng_mode = Rf_asInteger(rng_mode);
+    o.device = Rf_asInteger(device);
+    const int64_t ucap = ucap_rows(niter, N, o.rng_mode);
+    SEXP Zall = PROTECT(Rf_allocMatrix(INTSXP, niter, N));
+    SEXP sigc = PROTECT(Rf_allocMatrix(REALSXP, R, niter));
+    SEXP siga = PROTECT(Rf_allocMatrix(REALSXP, R, niter));
+    SEXP LL = PROTECT(Rf_allocVector(REALSXP, niter));
+    SEXP L0 = PROTECT(Rf_allocVector(REALSXP, 1));
+    SEXP kt = PROTECT(Rf_allocVector(INTSXP, niter));
+    SEXP uoff = PROTECT(Rf_allocVector(REALSXP, niter + 1));
+    SEXP ulab = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)ucap));
+    SEXP ustate = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)ucap * R));
+    SEXP ucov = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)ucap * R));
+    SEXP uall = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)ucap * R));
+    int64_t *off = (int64_t *)R_alloc((size_t)niter + 1, sizeof(int64_t));
+    int rc = cs_ncrp_gibbs_allele(N, R, REAL(Xcov), REAL(Xallele), K0, INTEGER(U0), INTEGER(Z0), REAL(sig0_cov),
+                                  REAL(sig0_allele), Rf_asReal(alpha), Rf_asReal(beta), niter,
+                                  (uint32_t)Rf_asInteger(seed), Rf_asInteger(maxcp), &o, INTEGER(Zall), REAL(sigc),
+                                  REAL(siga), REAL(LL), REAL(L0), INTEGER(kt), ucap, off, INTEGER(ulab),
+                                  INTEGER(ustate), REAL(ucov), REAL(uall));
+    for (int t = 0; t <= niter; t++) REAL(uoff)[t] = (double)off[t];
+    const char *names[] = {"Zall", "sigma_cov_all", "sigma_allele_all", "Likelihood", "L0", "kt", "u_off", "u_labels",
+                           "u_state", "u_cov", "u_allele", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SEXP parts[] = {Zall, sigc, siga, LL, L0, kt, uoff, ulab, ustate, ucov, uall};
+    for (int k = 0; k < 11; k++) SET_VECTOR_ELT(out, k, parts[k]);
+    UNPROTECT(12);
+    check(rc);
+    return out;
+}
+
+/* .Call("cs_R_majority_vote", Zall): integer vector, one label per cell (R/AssignCluster.R:37, :232) */
 SEXP cs_R_majority_vote(SEXP Zall)
 {
     const int T = Rf_nrows(Zall), N = Rf_ncols(Zall);
@@ -101,7 +155,7 @@ SEXP cs_R_majority_vote(SEXP Zall)
     return z;
 }
 
-/* .Call("cs_R_gene_moments", i, x, G): list(sum, sumsq), one entry per gene (EstRegionCov :42-43) */
+/* .Call("cs_R_gene_moments", i, x, G): list(sum, sumsq), one entry per gene (R/EstRegionCov.R:42-43) */
 SEXP cs_R_gene_moments(SEXP i, SEXP x, SEXP G)
 {
     const int g = Rf_asInteger(G);
@@ -115,12 +169,50 @@ SEXP cs_R_gene_moments(SEXP i, SEXP x, SEXP G)
     return out;
 }
 
+/* .Call("cs_R_cluster_stats", X, Z, K): list(sum, count, n) — K x R sums and non-NA counts of the
+ * cells of each label, and the cluster sizes (R/AssignCluster.R:46-51, :67-72; labels NA / outside
+ * 1..K are skipped: NA_integer_ is INT_MIN) */
+SEXP cs_R_cluster_stats(SEXP X, SEXP Z, SEXP K_)
+{
+    const int N = Rf_nrows(X), R = Rf_ncols(X), K = Rf_asInteger(K_);
+    SEXP s = PROTECT(Rf_allocMatrix(REALSXP, K, R)), c = PROTECT(Rf_allocMatrix(REALSXP, K, R));
+    SEXP n = PROTECT(Rf_allocVector(REALSXP, K));
+    int rc = cs_cluster_stats(N, R, K, REAL(X), INTEGER(Z), REAL(s), REAL(c), REAL(n));
+    const char *names[] = {"sum", "count", "n", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, s);
+    SET_VECTOR_ELT(out, 1, c);
+    SET_VECTOR_ELT(out, 2, n);
+    UNPROTECT(4);
+    check(rc);
+    return out;
+}
+
+/* .Call("cs_R_sigma_stats", X, Z, U): list(sq, count) — per-segment squared residuals against the
+ * cells' own cluster rows and non-NA counts (R/AssignCluster.R:53, :77) */
+SEXP cs_R_sigma_stats(SEXP X, SEXP Z, SEXP U)
+{
+    const int N = Rf_nrows(X), R = Rf_ncols(X), K = Rf_nrows(U);
+    SEXP q = PROTECT(Rf_allocVector(REALSXP, R)), c = PROTECT(Rf_allocVector(REALSXP, R));
+    int rc = cs_sigma_stats(N, R, K, REAL(X), INTEGER(Z), REAL(U), REAL(q), REAL(c));
+    const char *names[] = {"sq", "count", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, q);
+    SET_VECTOR_ELT(out, 1, c);
+    UNPROTECT(3);
+    check(rc);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
     {"cs_R_loglik_matrix", (DL_FUNC)&cs_R_loglik_matrix, 3},
     {"cs_R_bin_counts", (DL_FUNC)&cs_R_bin_counts, 7},
     {"cs_R_ncrp_gibbs", (DL_FUNC)&cs_R_ncrp_gibbs, 10},
+    {"cs_R_ncrp_gibbs_allele", (DL_FUNC)&cs_R_ncrp_gibbs_allele, 13},
     {"cs_R_majority_vote", (DL_FUNC)&cs_R_majority_vote, 1},
     {"cs_R_gene_moments", (DL_FUNC)&cs_R_gene_moments, 3},
+    {"cs_R_cluster_stats", (DL_FUNC)&cs_R_cluster_stats, 3},
+    {"cs_R_sigma_stats", (DL_FUNC)&cs_R_sigma_stats, 3},
     {NULL, NULL, 0}};
 
 void R_init_Clonalscope(DllInfo *dll)

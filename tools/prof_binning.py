@@ -25,6 +25,14 @@ nnz = C.c_int64()
 assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp), None, None, 0, C.byref(nnz), None) == 0
 ori = torch.empty(nnz.value, dtype=torch.int32, device=dev)
 ox = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+if os.environ.get("CS_BIN_COMPARE"):
+    # the one-pass kernel against the count / scan / fill kernels on the same buffers
+    os.environ["CS_BIN_ONEPASS"] = "0"
+    ocp0, ori0, ox0 = torch.zeros_like(ocp), torch.empty_like(ori), torch.empty_like(ox)
+    assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp0), vp(ori0), vp(ox0), nnz.value, C.byref(nnz), None) == 0
+    os.environ["CS_BIN_ONEPASS"] = "1"
+    assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp), vp(ori), vp(ox), nnz.value, C.byref(nnz), None) == 0
+    print("same colptr", torch.equal(ocp, ocp0), "same bins", torch.equal(ori, ori0), "same sums", torch.equal(ox, ox0), flush=True)
 for _ in range(reps):
     assert L.cs_bin_counts_dev(plan, N, vp(colptr), vp(rowidx), vp(x), vp(ocp), vp(ori), vp(ox), nnz.value, C.byref(nnz), None) == 0
     t = [C.c_double() for _ in range(3)]

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Per-sweep diagnostics of the Philox sampler's windowed walk on the bench workload:
+time of the sweep (CUDA events on the chain's stream), events, rounds of the walk and what cut
+the rounds short.   python tools/walk_diag.py [nsweeps] [seed] [N] [R]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import clonalscope_b200 as cs  # noqa: E402
+from clonalscope_b200 import _lib, synth  # noqa: E402
+
+nsw = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
+R = int(sys.argv[4]) if len(sys.argv) > 4 else 300
+L = cs.lib()
+s = synth.sampler_input(N, R=R)
+X = np.asfortranarray(s["X"])
+U0 = np.asfortranarray(s["U0"])
+sig0 = np.ascontiguousarray(s["sigmas0"])
+Z0 = (cs.loglik_matrix(X, s["U0"], sig0).argmax(axis=1) + 1).astype(np.int32)
+dp = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+chain = C.c_void_p()
+assert L.cs_chain_create(N, R, 0, nsw, _lib.RNG_PHILOX, C.byref(chain)) == 0
+assert L.cs_chain_init(chain, dp(X, C.c_double), 2, dp(U0, C.c_double), dp(Z0, C.c_int), dp(sig0, C.c_double),
+                       C.c_double(2.0), C.c_double(2.0), C.c_uint32(seed), 2) == 0
+prev = np.zeros(6, dtype=np.int64)
+tot = 0.0
+for t in range(nsw):
+    assert L.cs_chain_run(chain, 1, int(t == nsw - 1), 1) == 0, L.cs_last_error()
+    ms = [C.c_double() for _ in range(5)]
+    L.cs_chain_timing(chain, *[C.byref(m) for m in ms])
+    v = [C.c_int64() for _ in range(7)]
+    L.cs_chain_stats(chain, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]))
+    L.cs_chain_walk_stats(chain, C.byref(v[3]), C.byref(v[4]), C.byref(v[5]), C.byref(v[6]))
+    cur = np.array([v[1].value, v[3].value, v[4].value, v[5].value, v[6].value, v[0].value])
+    d = cur - prev
+    prev = cur
+    tot += ms[0].value
+    print("sweep %3d: run %7.2f ms  prepare %5.2f index %5.2f scan %7.2f eos %5.2f | events %6d rounds %5d (margin %5d open %3d list %5d) ev/round %5.1f us/round %5.2f"
+          % (t, ms[0].value, ms[1].value, ms[2].value, ms[3].value, ms[4].value, d[0], d[1], d[2], d[3], d[4],
+             d[0] / max(d[1], 1), 1e3 * ms[3].value / max(d[1], 1)), flush=True)
+print("total %.1f ms" % tot)
