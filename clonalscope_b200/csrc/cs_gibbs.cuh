@@ -59,6 +59,13 @@ struct ChainDev {
     unsigned *near;   // N x CS_NEAR_CAP  proposal sources at most CS_NEAR_W cells in front of the cell
                       //            (source << 10 | segment; CS_NEAR_EMPTY behind the last; CS_NEAR_OVER: more than fit)
     long long *tile_sums; // scan scratch
+    // fixed-point walk (fix_walk_kernel): second copy of the hypothesis (the first is zspec), two
+    // copies of the moved-cell bitmap, the tiles' net moves per slot and their prefix over the
+    // tiles ((kcap + 1) rows of fx_tpad(N) tiles), the per-step minima
+    int *zh1;
+    unsigned *fx_bits;
+    int *fx_td, *fx_tp;
+    int *fx_scal;
     double *mean;     // kcap x R cluster means
     double *psum;     // partial sums workspace
     int *pcnt;        // partial counts workspace

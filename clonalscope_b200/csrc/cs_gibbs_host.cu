@@ -9,7 +9,7 @@
 
 template <typename T>
 int cs_transpose(int rows, int cols, const T *d_in, T *d_out, cudaStream_t st);
-int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, cudaStream_t st,
+int cs_philox_sweep(const ChainDev &D, int tt, int last, int flags, int *rej, cudaStream_t st,
                     cudaEvent_t *ev);
 int cs_total_loglik_async(const ChainDev &D, const double *U, const int *Zrows, const double *sig, double *d_out,
                           cudaStream_t st);
@@ -26,7 +26,8 @@ struct cs_chain {
     DevBuf<long long> qnew_i, tile_sums, wn_q;
     DevBuf<double> wn_w;
     DevBuf<int> kmin, icnt, icur;
-    DevBuf<unsigned> near;
+    DevBuf<unsigned> near, fx_bits;
+    DevBuf<int> zh1, fx_td, fx_tp, fx_scal;
     DevBuf<InvEntry> inv;
     DevBuf<int> Zs, np, np0, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
     DevBuf<long long> u_off;
@@ -114,10 +115,18 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
         CS_CUDA(c->near.alloc(((size_t)N + 8) * CS_NEAR_CAP));
         CS_CUDA(c->inv.alloc(nx));
         CS_CUDA(c->tile_sums.alloc((size_t)N / 1024 + 8));
-        CS_CUDA(c->J.alloc(nx));
+        CS_CUDA(c->J.alloc(nx + 256)); // (the fixed-point walk copies whole 128-entry steps)
         CS_CUDA(c->zspec.alloc(N));
         CS_CUDA(c->qcols.alloc(N));
         CS_CUDA(c->rej.alloc(N));
+        const size_t tiles = ((size_t)N + 255) / 256, tpad = (tiles + 31) & ~(size_t)31;
+        CS_CUDA(c->zh1.alloc(N));
+        CS_CUDA(c->fx_bits.alloc(2 * tiles * 8));
+        CS_CUDA(c->fx_td.alloc(((size_t)kcap + 1) * tpad));
+        CS_CUDA(c->fx_tp.alloc(((size_t)kcap + 1) * tpad));
+        CS_CUDA(c->fx_scal.alloc(8));
+        CS_CUDA(cudaMemset(c->fx_td.p, 0, sizeof(int) * ((size_t)kcap + 1) * tpad));
+        CS_CUDA(cudaMemset(c->fx_tp.p, 0, sizeof(int) * ((size_t)kcap + 1) * tpad));
     }
     CS_CUDA(c->Zall.alloc((size_t)niter_cap * N));
     CS_CUDA(c->sigma_all.alloc((size_t)niter_cap * R));
@@ -133,6 +142,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     D.E = c->E.p; D.qmin = c->qmin.p; D.ua = c->ua.p; D.qnew_i = c->qnew_i.p; D.icnt = c->icnt.p;
     D.wn_q = c->wn_q.p; D.wn_w = c->wn_w.p; D.kmin = c->kmin.p;
     D.icur = c->icur.p; D.inv = c->inv.p; D.near = c->near.p; D.tile_sums = c->tile_sums.p;
+    D.zh1 = c->zh1.p; D.fx_bits = c->fx_bits.p; D.fx_td = c->fx_td.p; D.fx_tp = c->fx_tp.p; D.fx_scal = c->fx_scal.p;
     D.zspec = c->zspec.p; D.qcols = c->qcols.p; D.mean = c->mean.p; D.psum = c->psum.p; D.pcnt = c->pcnt.p;
     D.newslot = c->newslot.p; D.mt = c->mt.p; D.scal = c->scal.p;
     D.Zall = c->Zall.p; D.sigma_all = c->sigma_all.p; D.LL = c->LL.p; D.kt_all = c->kt_all.p;
@@ -281,7 +291,7 @@ extern "C" int cs_chain_run(cs_chain *c, int nsweeps, int is_last, int sync)
         if (nsweeps > 0) rc = cs_rmode_run(c->D, c->kcap, t0, t1, is_last ? t1 - 1 : -1, c->mean.p, c->st);
     } else {
         for (int tt = t0; tt < t1 && rc == CS_OK; tt++) {
-            rc = cs_philox_sweep(c->D, tt, is_last && tt == t1 - 1, c->flags & 1, c->rej.p, c->st,
+            rc = cs_philox_sweep(c->D, tt, is_last && tt == t1 - 1, c->flags, c->rej.p, c->st,
                                  prof ? &c->sweep_ev[5 * (size_t)(tt - t0)] : nullptr);
             double *t = c->D.U;
             c->D.U = c->D.Unext;

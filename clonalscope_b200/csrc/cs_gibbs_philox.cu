@@ -871,6 +871,9 @@ __device__ __forceinline__ void cp_async_16_cg(void *dst, const void *src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NLEFT>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory"); }
 
 constexpr int DEP_STAGE = 2 * WIN_THREADS; // dependents' index entries staged per round
 // fixed part of the kernel's shared memory (compile-time offsets); behind it: np, label, np0
@@ -1490,6 +1493,440 @@ seq_scan_kernel(ChainDev D, int tt, int force_all, int *__restrict__ rej)
     }
 }
 
+// ---------------------------------------------------------------- fixed-point walk (all SMs, cooperative)
+// The sequential sweep as the fixed point of a parallel map.  Let h be a hypothesis for the
+// outcome of every cell of the sweep (the slot it ends in).  F(h)[c] = the draw of cell c
+// against the state that h[0..c) induces: counts = counts at the start of the sweep + the moves
+// h makes in front of c, proposal = the cluster states of its source cells (h for sources in
+// front of c, the sweep's start for the others), same uniform.  The sequential chain is the
+// only h with F(h) = h (induction over c: cell 0 sees the start state; if h is right in front
+// of c, F(h)[c] is the sequential draw), and from ANY h the iteration h <- F(h) is right up to
+// and including the first cell it changes — so it ends after at most N steps, in practice after
+// a handful: a draw flips only when the moves in front of it shift its cumulative weights past
+// its uniform, and each step's flips are a small fraction of the previous step's.  Every step
+// is one pass of ALL SMs over the cells behind the last settled one; there is no sequential
+// walk, no margin bookkeeping and no inverse index.  Per step and 256-cell tile:
+//   pull   (warp per cell) the proposal distance under h: the cell's sources (J) are looked up
+//          in a bitmap of the cells h moves; for a hit the segment's term is exchanged exactly
+//          (fixed point): tint(x, U[h[j]]) - tint(x, U[Zs[j]]);
+//   draw   (thread per cell) counts in front of the cell = prefix over the tiles (a small scan
+//          between two grid barriers) + prefix over the tile's warps + ballots inside the warp;
+//          weights from the cached exponentials while their reference still is the minimum
+//          over today's candidates, re-exponentiated otherwise — the arithmetic of
+//          draw_cell_warp in the same order;
+//   publish the tile's net moves per slot, its bits of the bitmap, the first changed cell, the
+//          first cell that opens a cluster.
+// A cell that opens a cluster stops the prefix: when everything up to it has settled, its
+// proposal becomes the new row (:209-212), the new column is scored for all later cells by the
+// whole grid, and the iteration goes on behind it with one slot more.
+constexpr int FX_THREADS = 256, FX_WARPS = FX_THREADS / 32;
+constexpr int FX_STEP = 128;      // source entries per warp and step of the pull (16 bytes per lane)
+constexpr int FX_NS = 6;          // steps in the ring of asynchronous copies
+constexpr int FX_HCAP = 256;      // collected hits per warp
+constexpr int FX_INF = 0x7f7f7f7f; // (what cudaMemsetAsync(0x7f) leaves)
+
+struct FixScal {
+    int fc[2], fo[2]; // per step parity: first changed cell, first cell that opens a cluster
+};
+
+__host__ __device__ inline int fx_tiles(int N) { return (N + FX_THREADS - 1) / FX_THREADS; }
+__host__ __device__ inline int fx_tpad(int N) { return (fx_tiles(N) + 31) & ~31; }
+__host__ __device__ inline int fx_words(int N) { return ((N + FX_THREADS - 1) / FX_THREADS) * FX_WARPS; }
+inline size_t fix_smem_bytes(int N, int R, int kcap, bool bits_in_smem)
+{
+    return sizeof(double) * (size_t)R + sizeof(long long) * FX_THREADS + sizeof(int) * (size_t)(kcap + 1) * (FX_WARPS + 1) +
+           sizeof(int) * FX_WARPS * FX_NS * FX_STEP + sizeof(int2) * FX_WARPS * FX_HCAP +
+           (bits_in_smem ? sizeof(unsigned) * (size_t)fx_words(N) : 0) + 48;
+}
+
+// the tile's net moves per slot (tdelta[s][tile]), its 256 bits of the moved-cell bitmap, the
+// first cell whose hypothesis opens a cluster
+__device__ __forceinline__ void fx_publish(const ChainDev &D, int tile, int c, bool active, bool counts_open, int z, int zo,
+                                           int nmat, int *s_td, unsigned *bits_a, unsigned *bits_b, int *fo)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Tp = fx_tpad(D.N);
+    for (int s = threadIdx.x; s <= nmat; s += FX_THREADS) s_td[s] = 0;
+    __syncthreads();
+    const bool moved = active && z != zo;
+    if (moved) {
+        atomicAdd(&s_td[z], 1);
+        atomicAdd(&s_td[zo], -1);
+    }
+    const unsigned bal = __ballot_sync(CS_FULL, moved);
+    if (lane == 0) {
+        bits_a[tile * FX_WARPS + warp] = bal;
+        if (bits_b) bits_b[tile * FX_WARPS + warp] = bal;
+    }
+    const unsigned opn = __ballot_sync(CS_FULL, counts_open && z == nmat);
+    if (opn && lane == 0) atomicMin(fo, tile * FX_THREADS + warp * 32 + __ffs(opn) - 1);
+    __syncthreads();
+    for (int s = threadIdx.x; s <= nmat; s += FX_THREADS) D.fx_td[(size_t)s * Tp + tile] = s_td[s];
+    (void)c;
+}
+
+// exclusive prefix of tdelta over the tiles, per slot (a warp per slot, warps of the whole grid)
+__device__ __forceinline__ void fx_scan_tiles(const ChainDev &D, int nmat)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * FX_WARPS + (threadIdx.x >> 5), nw = gridDim.x * FX_WARPS;
+    const int T = fx_tiles(D.N), Tp = fx_tpad(D.N);
+    for (int s = gw; s <= nmat; s += nw) {
+        int run = 0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            const int v = t < T ? D.fx_td[(size_t)s * Tp + t] : 0;
+            int inc = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(CS_FULL, inc, off);
+                if (lane >= off) inc += o;
+            }
+            if (t < T) D.fx_tp[(size_t)s * Tp + t] = run + inc - v;
+            run += __shfl_sync(CS_FULL, inc, 31);
+        }
+    }
+}
+
+// the column of a cluster opened at cell f (slot b) for every later cell: score_new_column over
+// the warps of the whole grid
+template <int NCH>
+__device__ __forceinline__ void fx_score_column(const ChainDev &D, int f, int b, const double *s_isig16)
+{
+    const size_t N = (size_t)D.N;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * FX_WARPS + (threadIdx.x >> 5), stride = gridDim.x * FX_WARPS;
+    double ur[NCH], x[NCH];
+    load_row<NCH>(D.U + (size_t)b * D.R, D.R, lane, ur);
+    for (int cc = f + 1 + gw; cc < D.N; cc += stride) {
+        load_row<NCH>(D.X + (size_t)cc * D.R, D.R, lane, x);
+        const double qm = D.qmin[cc];
+        const long long q = q_regs<NCH>(x, ur, s_isig16, D.R, lane);
+        const double qd = (double)q * Q_SCALE;
+        if (qd < qm) {
+            // the new cluster is this cell's best candidate: it becomes the reference of the
+            // cached exponentials (slots 0..b re-exponentiated, one lane each)
+            for (int s = lane; s <= b; s += 32) {
+                const double qs = (s == b) ? qd : D.Q[(size_t)s * N + cc];
+                D.E[(size_t)s * N + cc] = exp(-0.5 * (qs - qd));
+            }
+            if (lane == 0) {
+                D.Q[(size_t)b * N + cc] = qd;
+                D.qmin[cc] = qd;
+                D.kmin[cc] = b < 255 ? b : 255;
+            }
+        } else if (lane == 0) {
+            D.Q[(size_t)b * N + cc] = qd;
+            D.E[(size_t)b * N + cc] = exp(-0.5 * (qd - qm)); // cached like the other slots'
+        }
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(FX_THREADS, 3)
+fix_walk_kernel(ChainDev D, int tt, int bits_in_smem)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char s_fx_raw[];
+    double *s_isig16 = reinterpret_cast<double *>(s_fx_raw);            // R
+    long long *s_qh = reinterpret_cast<long long *>(s_isig16 + D.R);    // what h changes in the proposal distances of the tile's cells
+    int *s_base = reinterpret_cast<int *>(s_qh + FX_THREADS);           // kcap + 1: counts in front of the tile
+    int *s_wd = s_base + (D.kcap + 1);                                  // FX_WARPS x (kcap + 1): moves in front of each warp
+    const int KS = D.kcap + 1;
+    int *s_ring = reinterpret_cast<int *>((reinterpret_cast<uintptr_t>(s_wd + FX_WARPS * KS) + 15) & ~(uintptr_t)15); // FX_WARPS rings of FX_NS x FX_STEP source entries (16-byte copies)
+    int2 *s_hits = reinterpret_cast<int2 *>(s_ring + FX_WARPS * FX_NS * FX_STEP);
+    unsigned *s_bits = reinterpret_cast<unsigned *>(s_hits + FX_WARPS * FX_HCAP);
+
+    // (uniform over the grid: the scalars are rewritten only behind the last grid barrier)
+    const int f0 = D.scal->first_event;
+    if (f0 >= D.N) return;
+    int nmat = D.scal->nlive, kt = D.scal->kt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const size_t N = (size_t)D.N;
+    const int T = fx_tiles(D.N), Tp = fx_tpad(D.N), NW = fx_words(D.N);
+    for (int r = threadIdx.x; r < D.R; r += FX_THREADS) s_isig16[r] = D.isig[r] * 65536.0;
+    int *zh[2] = {D.zspec, D.zh1};
+    unsigned *bits[2] = {D.fx_bits, D.fx_bits + NW};
+    FixScal *fxs = reinterpret_cast<FixScal *>(D.fx_scal);
+
+    // ---- step -1: the hypothesis is prepare_kernel's draws against the start of the sweep
+    for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {
+        const int c = tile * FX_THREADS + threadIdx.x;
+        const bool active = c < D.N;
+        const int z = active ? D.zspec[c] : -1, zo = active ? D.Zs[c] : -1;
+        if (active) D.zh1[c] = z;
+        // (rows of slots that open later in the sweep: nothing of an earlier sweep may be left in them)
+        for (int s2 = nmat + 1 + threadIdx.x; s2 <= D.kcap; s2 += FX_THREADS) D.fx_td[(size_t)s2 * Tp + tile] = 0;
+        fx_publish(D, tile, c, active, active, z, zo, nmat, s_wd, bits[0], bits[1], &fxs->fo[1]);
+        __syncthreads();
+    }
+    grid.sync();
+    int open_cur = *reinterpret_cast<volatile int *>(&fxs->fo[1]);
+    fx_scan_tiles(D, nmat);
+    grid.sync();
+
+    int lo = f0, err = 0, steps = 0, opened = 0;
+    long long evaluated = 0;
+    for (int it = 0;; it++) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { // the other parity's minima: read by everyone before the last barrier
+            fxs->fc[nxt] = FX_INF;
+            fxs->fo[nxt] = FX_INF;
+        }
+        const unsigned *bcur = bits[cur];
+        if (bits_in_smem) {
+            for (int w = threadIdx.x; w < NW; w += FX_THREADS) s_bits[w] = bcur[w];
+            bcur = s_bits;
+        }
+        const int *zcur = zh[cur];
+        steps++;
+        for (int tile = lo / FX_THREADS + blockIdx.x; tile < T; tile += gridDim.x) {
+            __syncthreads();
+            const int c = tile * FX_THREADS + threadIdx.x;
+            const bool active = c < D.N, evalc = active && c >= lo;
+            const int zo = active ? D.Zs[c] : -1, zc = active ? zcur[c] : -1;
+            // ---- counts in front of the tile, moves in front of each warp
+            for (int e = threadIdx.x; e < FX_WARPS * KS; e += FX_THREADS) s_wd[e] = 0;
+            s_qh[threadIdx.x] = 0;
+            for (int s = threadIdx.x; s <= nmat; s += FX_THREADS) s_base[s] = (s < D.kcap ? D.np0[s] : 0) + D.fx_tp[(size_t)s * Tp + tile];
+            __syncthreads();
+            const bool moved = active && zc != zo;
+            if (moved) {
+                atomicAdd(&s_wd[warp * KS + zc], 1);
+                atomicAdd(&s_wd[warp * KS + zo], -1);
+            }
+            const bool warp_moves = __any_sync(CS_FULL, moved);
+            __syncthreads();
+            for (int s = threadIdx.x; s <= nmat; s += FX_THREADS) {
+                int run = 0;
+#pragma unroll
+                for (int w = 0; w < FX_WARPS; w++) {
+                    const int t = s_wd[w * KS + s];
+                    s_wd[w * KS + s] = run;
+                    run += t;
+                }
+            }
+            __syncthreads();
+            // ---- pull: what h changes in the proposal distances of this warp's 32 cells.  Their
+            // source lists are one contiguous stretch of J (and of X).  The warp streams over it
+            // through a ring of asynchronous copies (FX_NS steps of 128 entries; nothing waits on
+            // DRAM latency), looks every source up in the bitmap of moved cells and collects the
+            // hits; the collected hits are then worked off a lane each — both slots and the value
+            // loaded together, the term exchanged exactly, the difference added to the cell's sum.
+            {
+                const int cbase = tile * FX_THREADS + warp * 32;
+                const int k0 = max(0, lo - cbase), k1 = min(32, D.N - cbase);
+                if (k0 < k1) {
+                    const size_t ebase = (size_t)cbase * D.R;
+                    const int *Jw = D.J + ebase;
+                    const double *Xw = D.X + ebase;
+                    const int le0 = k0 * D.R, le1 = k1 * D.R; // entries relative to the warp's first cell
+                    const unsigned long long rdiv = (0x100000000ull + (unsigned)D.R - 1) / (unsigned)D.R; // le / R for le < 2^16
+                    int *ring = s_ring + warp * (FX_NS * FX_STEP);
+                    int2 *hits = s_hits + warp * FX_HCAP;
+                    int nh = 0;
+                    auto flush = [&]() {
+                        __syncwarp();
+#pragma unroll 2
+                        for (int idx = lane; idx < nh; idx += 32) {
+                            const int2 h = hits[idx];
+                            const int le = h.x, j = h.y;
+                            const int zj = zcur[j], zs = D.Zs[j];
+                            const double xv = Xw[le];
+                            const int kc = (int)(((unsigned long long)le * rdiv) >> 32), r = le - kc * D.R;
+                            // (a source that opens a cluster lies behind the settled prefix: no row yet)
+                            const bool ok = zj < nmat && !cs_isna(xv);
+                            const double u1 = ok ? D.U[(size_t)zj * D.R + r] : 0.0, u0 = ok ? D.U[(size_t)zs * D.R + r] : 0.0;
+                            if (ok) {
+                                const double is = s_isig16[r];
+                                const long long d = tint(xv, u1, is) - tint(xv, u0, is);
+                                if (d) atomicAdd(reinterpret_cast<unsigned long long *>(s_qh + warp * 32 + kc), (unsigned long long)d);
+                            }
+                        }
+                        nh = 0;
+                        __syncwarp();
+                    };
+                    const int sbeg = le0 & ~(FX_STEP - 1);
+                    const int nsteps = (le1 - sbeg + FX_STEP - 1) / FX_STEP;
+#pragma unroll
+                    for (int p = 0; p < FX_NS - 1; p++) { // (the list is padded: a step may read past the stretch)
+                        if (p < nsteps) cp_async_16_cg(ring + p * FX_STEP + 4 * lane, Jw + sbeg + p * FX_STEP + 4 * lane);
+                        cp_async_commit();
+                    }
+                    for (int st = 0; st < nsteps; st++) {
+                        cp_async_wait_group<FX_NS - 2>();
+                        __syncwarp();
+                        const int *stage = ring + (st % FX_NS) * FX_STEP;
+                        int jj[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) jj[u] = stage[u * 32 + lane];
+                        __syncwarp();
+                        {
+                            const int p = st + FX_NS - 1;
+                            if (p < nsteps) cp_async_16_cg(ring + (p % FX_NS) * FX_STEP + 4 * lane, Jw + sbeg + p * FX_STEP + 4 * lane);
+                            cp_async_commit();
+                        }
+                        const int s0 = sbeg + st * FX_STEP;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int le = s0 + u * 32 + lane;
+                            const int j = jj[u];
+                            const int kc = (int)(((unsigned long long)le * rdiv) >> 32);
+                            const bool h = le >= le0 && le < le1 && j >= 0 && j < cbase + kc && ((bcur[j >> 5] >> (j & 31)) & 1u);
+                            const unsigned hb = __ballot_sync(CS_FULL, h);
+                            if (h) hits[nh + __popc(hb & ltmask)] = make_int2(le, j);
+                            nh += __popc(hb);
+                        }
+                        if (nh > FX_HCAP - FX_STEP) flush();
+                    }
+                    flush();
+                    cp_async_wait_all();
+                }
+                __syncwarp();
+            }
+            // ---- draw (the slot loops are uniform over the warp: the counts come from ballots)
+            int z = zc;
+            {
+                const long long qi = evalc ? D.qnew_i[c] + s_qh[threadIdx.x] : 0;
+                const double q_new = (double)qi * Q_SCALE;
+                const double qmin_c = evalc ? D.qmin[c] : 0.0, ua = evalc ? D.ua[c] : 0.0;
+                const int km = evalc ? D.kmin[c] : 255;
+                const int *wd = s_wd + warp * KS;
+                auto count_at = [&](int s) -> int { // cells in slot s in front of this cell (itself included while it has not moved)
+                    int n = s_base[s] + wd[s];
+                    if (warp_moves) {
+                        const unsigned bn = __ballot_sync(CS_FULL, zc == s), bo = __ballot_sync(CS_FULL, zo == s);
+                        n += __popc(bn & ltmask) - __popc(bo & ltmask);
+                    }
+                    return n;
+                };
+                int nkm = 1, nzo = 0;
+                for (int s = 0; s < nmat; s++) {
+                    const int n = count_at(s);
+                    if (s == km) nkm = n;
+                    if (s == zo) nzo = n;
+                }
+                // (the conditions under which the cached exponentials are today's: their reference
+                //  still is the minimum over the candidates)
+                bool fast = (km != 255 ? (q_new >= qmin_c && nkm - (km == zo ? 1 : 0) > 0) : q_new == qmin_c);
+                if (evalc && fast && D.np0[zo] < 2 && nzo >= 2 && D.Q[(size_t)zo * N + c] < qmin_c) fast = false;
+                double qref = qmin_c;
+                if (__any_sync(CS_FULL, evalc && !fast)) {
+                    double qm = q_new;
+                    for (int s = 0; s < nmat; s++) {
+                        const int n = count_at(s) - (s == zo ? 1 : 0);
+                        if (evalc && !fast && n > 0) qm = fmin(qm, D.Q[(size_t)s * N + c]);
+                    }
+                    if (!fast) {
+                        fast = qm == qmin_c;
+                        qref = qm;
+                    }
+                }
+                const double w_new = __dmul_rn(D.beta, exp(-0.5 * (q_new - qref)));
+                auto weight = [&](int s) -> double {
+                    const int n = count_at(s) - (s == zo ? 1 : 0);
+                    double w = 0.0;
+                    if (evalc && n > 0) {
+                        const double e = fast ? D.E[(size_t)s * N + c] : exp(-0.5 * (D.Q[(size_t)s * N + c] - qref));
+                        w = __dmul_rn((double)n, e);
+                    }
+                    return w;
+                };
+                double run = 0.0;
+                for (int s = 0; s < nmat; s++) run = __dadd_rn(run, weight(s));
+                const double t = __dmul_rn(ua, __dadd_rn(run, w_new));
+                run = 0.0;
+                int zz = -1, lastpos = -1;
+                for (int s = 0; s < nmat; s++) {
+                    const double w = weight(s);
+                    if (w > 0.0) {
+                        run = __dadd_rn(run, w);
+                        lastpos = s;
+                        if (zz < 0 && run > t) zz = s;
+                    }
+                }
+                if (zz < 0) zz = (w_new > 0.0) ? nmat : lastpos;
+                if (evalc) z = zz;
+            }
+            if (evalc) {
+                zh[nxt][c] = z;
+                if (z != zc) atomicMin(&fxs->fc[cur], c);
+            }
+            __syncthreads();
+            fx_publish(D, tile, c, active, evalc, z, zo, nmat, s_wd, bits[nxt], nullptr, &fxs->fo[cur]);
+            if (threadIdx.x == 0) evaluated += min(D.N, (tile + 1) * FX_THREADS) - max(lo, tile * FX_THREADS);
+        }
+        grid.sync();
+        const int changed_min = *reinterpret_cast<volatile int *>(&fxs->fc[cur]);
+        const int open_next = *reinterpret_cast<volatile int *>(&fxs->fo[cur]);
+        if (changed_min >= FX_INF && open_cur >= FX_INF) break; // nothing changed, nothing opens: h is the chain
+        if (open_cur < changed_min) {
+            // ---- everything up to the cell that opens a cluster has settled: its proposal becomes
+            // the row of slot nmat (:209-212), scored for every later cell by the whole grid
+            const int f = open_cur, b = nmat;
+            if (b >= D.kcap) {
+                err = CS_ERR_KCAP;
+                break;
+            }
+            if (blockIdx.x == 0) {
+                const int *Jrow = D.J + (size_t)f * D.R;
+                for (int r = threadIdx.x; r < D.R; r += FX_THREADS) {
+                    const int j = Jrow[r];
+                    double v;
+                    if (j < 0) v = fresh_state(D, f, r, tt, 0u);
+                    else v = D.U[(size_t)(j < f ? zh[nxt][j] : D.Zs[j]) * D.R + r];
+                    D.U[(size_t)b * D.R + r] = v;
+                }
+                if (threadIdx.x == 0) D.slot_label[b] = kt + 1;
+            }
+            kt++;
+            nmat++;
+            opened++;
+            grid.sync();
+            fx_score_column<NCH>(D, f, b, s_isig16);
+            lo = f + 1;
+            open_cur = FX_INF;
+        } else {
+            // (that cell's new draw saw a settled prefix, so it is settled itself; it is evaluated
+            //  once more so that both copies of h receive it)
+            lo = changed_min;
+            open_cur = open_next;
+        }
+        fx_scan_tiles(D, nmat);
+        grid.sync();
+    }
+    // ---- h is the sweep's outcome (both copies agree): assignments, counts, scalars
+    {
+        const int *zf = zh[0];
+        long long nev = 0;
+        for (int c = blockIdx.x * FX_THREADS + threadIdx.x; c < D.N; c += gridDim.x * FX_THREADS) {
+            const int z = zf[c];
+            if (z != D.Zs[c]) {
+                D.Zs[c] = z;
+                nev++;
+            }
+        }
+        nev = warp_sum_ll(nev);
+        if (lane == 0 && nev) atomicAdd(reinterpret_cast<unsigned long long *>(&D.scal->n_events), (unsigned long long)nev);
+        if (threadIdx.x == 0 && evaluated) atomicAdd(reinterpret_cast<unsigned long long *>(&D.scal->cells_scanned), (unsigned long long)evaluated);
+        if (blockIdx.x == 0) {
+            for (int s = threadIdx.x; s < nmat; s += FX_THREADS) {
+                int tot = 0;
+                for (int t = 0; t < T; t++) tot += D.fx_td[(size_t)s * Tp + t];
+                D.np[s] = D.np0[s] + tot;
+            }
+            if (threadIdx.x == 0) {
+                D.scal->nlive = nmat;
+                D.scal->kt = kt;
+                D.scal->n_rounds += steps;
+                D.scal->cut_open += opened;
+                if (err) D.scal->err = err;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- end of sweep
 // per-chunk per-cluster sums of X and non-NA counts (R/BayesNonparCluster.R:223)
 __global__ void __launch_bounds__(1024)
@@ -1898,9 +2335,43 @@ int launch_ring(const ChainDev &D, int tt, cudaStream_t st)
     return CS_OK;
 }
 
+// the fixed-point walk: a cooperative launch of as many CTAs as the device keeps resident (at
+// most one per tile)
 template <int NCH>
-int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cudaStream_t st, cudaEvent_t *ev)
+int launch_fix(const ChainDev &D, int tt, int nsm, cudaStream_t st)
 {
+    bool bits_in_smem = (size_t)fx_words(D.N) * sizeof(unsigned) <= 64 * 1024;
+    const size_t smem = fix_smem_bytes(D.N, D.R, D.kcap, bits_in_smem);
+    static size_t attr_d[MAX_DEVICES] = {};
+    static int occ_d[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (attr_d[dev] != smem) {
+        CS_CUDA(cudaFuncSetAttribute(fix_walk_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fix_walk_kernel<NCH>, FX_THREADS, smem));
+        if (occ < 1) {
+            cs_set_error("fix_walk_kernel cannot be resident with %zu bytes of shared memory", smem);
+            return CS_ERR_UNSUPPORTED;
+        }
+        occ_d[dev] = occ;
+        attr_d[dev] = smem;
+    }
+    int grid = occ_d[dev] * nsm;
+    if (const char *e = getenv("CS_FIX_CTAS_PER_SM")) grid = (atoi(e) < 1 ? 1 : (atoi(e) > occ_d[dev] ? occ_d[dev] : atoi(e))) * nsm;
+    const int tiles = fx_tiles(D.N);
+    if (grid > tiles) grid = tiles;
+    CS_CUDA(cudaMemsetAsync(D.fx_scal, 0x7f, sizeof(FixScal), st));
+    ChainDev Dc = D;
+    int tt_c = tt, bis = bits_in_smem ? 1 : 0;
+    void *args[] = {&Dc, &tt_c, &bis};
+    CS_CUDA(cudaLaunchCooperativeKernel((const void *)fix_walk_kernel<NCH>, dim3(grid), dim3(FX_THREADS), args, smem, st));
+    return CS_OK;
+}
+
+template <int NCH>
+int launch_sweep(const ChainDev &D, int tt, int flags, int *rej, int nsm, cudaStream_t st, cudaEvent_t *ev)
+{
+    const int force_all = flags & 1;
     const size_t smem_prep = sizeof(double) * D.R + sizeof(int) * D.kcap;
     const size_t smem_scan = sizeof(double) * ((size_t)D.R + 2 * D.kcap + 64 * WIN_CELLS) + sizeof(int) * 3 * D.kcap + 16;
     // (function attributes are set when the sizes change, not every sweep)
@@ -1928,7 +2399,10 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
         if (ev) CS_CUDA(cudaEventRecord(ev[1], st));
         if (reject_live) {
             seq_scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, 0, rej);
-        } else {
+        } else if (!(flags & 4)) {
+            if (ev) CS_CUDA(cudaEventRecord(ev[4], st));
+            { int rc2 = launch_fix<NCH>(D, tt, nsm, st); if (rc2) return rc2; }
+        } else { // (flags bit 2: the round-1 walk — inverse index + one-CTA ring walk)
             CS_CUDA(cudaMemsetAsync(D.icnt, 0, sizeof(int) * ((size_t)D.N + 1), st));
             index_count_kernel<<<nsm * 8, 256, 0, st>>>(D);
             index_scan_kernel<<<1, 1024, 0, st>>>(D);
@@ -1952,16 +2426,16 @@ int launch_sweep(const ChainDev &D, int tt, int force_all, int *rej, int nsm, cu
 int cs_philox_max_R() { return 1024; }
 
 // one full sweep (asynchronous).  D.U / D.Unext are swapped by the caller afterwards.
-int cs_philox_sweep(const ChainDev &D, int tt, int last, int force_all, int *rej, cudaStream_t st,
+int cs_philox_sweep(const ChainDev &D, int tt, int last, int flags, int *rej, cudaStream_t st,
                     cudaEvent_t *ev)
 {
     const int nsm = cs_num_sms();
     int rc;
-    if (D.R <= 32) rc = launch_sweep<1>(D, tt, force_all, rej, nsm, st, ev);
-    else if (D.R <= 64) rc = launch_sweep<2>(D, tt, force_all, rej, nsm, st, ev);
-    else if (D.R <= 128) rc = launch_sweep<4>(D, tt, force_all, rej, nsm, st, ev);
-    else if (D.R <= 320) rc = launch_sweep<10>(D, tt, force_all, rej, nsm, st, ev);
-    else if (D.R <= 1024) rc = launch_sweep<32>(D, tt, force_all, rej, nsm, st, ev);
+    if (D.R <= 32) rc = launch_sweep<1>(D, tt, flags, rej, nsm, st, ev);
+    else if (D.R <= 64) rc = launch_sweep<2>(D, tt, flags, rej, nsm, st, ev);
+    else if (D.R <= 128) rc = launch_sweep<4>(D, tt, flags, rej, nsm, st, ev);
+    else if (D.R <= 320) rc = launch_sweep<10>(D, tt, flags, rej, nsm, st, ev);
+    else if (D.R <= 1024) rc = launch_sweep<32>(D, tt, flags, rej, nsm, st, ev);
     else {
         cs_set_error("Philox sampler supports up to 1024 segments (R=%d)", D.R);
         return CS_ERR_UNSUPPORTED;

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Per-sweep diagnostics of the Philox sampler's windowed walk on the bench workload:
-time of the sweep (CUDA events on the chain's stream), events, rounds of the walk and what cut
-the rounds short.   python tools/walk_diag.py [nsweeps] [seed] [N] [R]"""
+"""Per-sweep diagnostics of the Philox sampler's walk on the bench workload: time of the sweep
+(CUDA events on the chain's stream), events (cells that move), steps of the fixed-point
+iteration, clusters opened, cells evaluated.
+python tools/walk_diag.py [nsweeps] [seed] [N] [R] [flags]   (flags 6 = the round-1 ring walk)"""
 import ctypes as C
 import os
 import sys
@@ -17,6 +18,7 @@ nsw = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 R = int(sys.argv[4]) if len(sys.argv) > 4 else 300
+flags = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 L = cs.lib()
 s = synth.sampler_input(N, R=R)
 X = np.asfortranarray(s["X"])
@@ -27,7 +29,7 @@ dp = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
 chain = C.c_void_p()
 assert L.cs_chain_create(N, R, 0, nsw, _lib.RNG_PHILOX, C.byref(chain)) == 0
 assert L.cs_chain_init(chain, dp(X, C.c_double), 2, dp(U0, C.c_double), dp(Z0, C.c_int), dp(sig0, C.c_double),
-                       C.c_double(2.0), C.c_double(2.0), C.c_uint32(seed), 2) == 0
+                       C.c_double(2.0), C.c_double(2.0), C.c_uint32(seed), flags) == 0
 prev = np.zeros(6, dtype=np.int64)
 tot = 0.0
 for t in range(nsw):
@@ -41,7 +43,7 @@ for t in range(nsw):
     d = cur - prev
     prev = cur
     tot += ms[0].value
-    print("sweep %3d: run %7.2f ms  prepare %5.2f index %5.2f scan %7.2f eos %5.2f | events %6d rounds %5d (margin %5d open %3d list %5d) ev/round %5.1f us/round %5.2f"
-          % (t, ms[0].value, ms[1].value, ms[2].value, ms[3].value, ms[4].value, d[0], d[1], d[2], d[3], d[4],
-             d[0] / max(d[1], 1), 1e3 * ms[3].value / max(d[1], 1)), flush=True)
+    print("sweep %3d: run %7.2f ms  prepare %5.2f index %5.2f walk %7.3f eos %5.2f | events %6d steps %5d opened %3d evaluated %8d  us/step %6.2f"
+          % (t, ms[0].value, ms[1].value, ms[2].value, ms[3].value, ms[4].value, d[0], d[1], d[3], d[5],
+             1e3 * ms[3].value / max(d[1], 1)), flush=True)
 print("total %.1f ms" % tot)
