@@ -19,7 +19,7 @@ SYMBOLS = [
     "cs_bin_plan_create", "cs_bin_plan_destroy", "cs_bin_plan_timing", "cs_bin_counts_dev",
     "cs_loglik_matrix", "cs_loglik_matrix_dev",
     "cs_ncrp_gibbs", "cs_release_cached", "cs_chain_create", "cs_chain_init", "cs_chain_run", "cs_chain_sync",
-    "cs_chain_sweeps_done", "cs_chain_timing", "cs_chain_stats", "cs_chain_walk_stats", "cs_chain_fetch", "cs_chain_destroy",
+    "cs_chain_sweeps_done", "cs_chain_timing", "cs_chain_stats", "cs_chain_walk_stats", "cs_chain_fix_prof", "cs_chain_fetch", "cs_chain_destroy",
     "cs_ncrp_gibbs_allele",
     "cs_majority_vote", "cs_majority_vote_dev",
     "cs_cluster_stats_dev", "cs_sigma_stats_dev", "cs_cluster_stats", "cs_sigma_stats", "cs_gene_moments",

@@ -50,7 +50,8 @@ struct ChainDev {
     long long *wn_q;  // N          proposal distance the cached new-table weight was computed at
     double *wn_w;     // N          beta * exp(-0.5 (q_new - qmin)) at wn_q
     int *kmin;        // N          a live cluster attaining qmin (255: only the proposal does)
-    int *J;           // N x R      proposal sources (cell index, -1 = fresh Uniform state)
+    int *J;           // N x R      row c: the proposal's sources in front of cell c, packed (source << 10 | segment)
+    int *jcnt;        // N          how many
     int *zspec;       // N          speculative draws
     int *qcols;       // N          (sequential kernel) valid columns of Q
     int *icnt;        // N+1        inverse source index: offsets (after the scan)

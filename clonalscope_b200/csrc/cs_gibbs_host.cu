@@ -27,7 +27,7 @@ struct cs_chain {
     DevBuf<double> wn_w;
     DevBuf<int> kmin, icnt, icur;
     DevBuf<unsigned> near, fx_bits;
-    DevBuf<int> zh1, fx_td, fx_tp, fx_scal;
+    DevBuf<int> zh1, fx_td, fx_tp, fx_scal, jcnt;
     DevBuf<InvEntry> inv;
     DevBuf<int> Zs, np, np0, slot_label, J, zspec, qcols, pcnt, newslot, rej, Zall, kt_all, u_labels;
     DevBuf<long long> u_off;
@@ -114,13 +114,14 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
         CS_CUDA(c->icur.alloc(N));
         CS_CUDA(c->near.alloc(((size_t)N + 8) * CS_NEAR_CAP));
         CS_CUDA(c->inv.alloc(nx));
-        CS_CUDA(c->tile_sums.alloc((size_t)N / 1024 + 8));
+        CS_CUDA(c->tile_sums.alloc((size_t)N / 1024 + 8 + 1024)); // (also the fixed-point walk's optional per-step timings)
         CS_CUDA(c->J.alloc(nx + 256)); // (the fixed-point walk copies whole 128-entry steps)
         CS_CUDA(c->zspec.alloc(N));
         CS_CUDA(c->qcols.alloc(N));
         CS_CUDA(c->rej.alloc(N));
         const size_t tiles = ((size_t)N + 255) / 256, tpad = (tiles + 31) & ~(size_t)31;
         CS_CUDA(c->zh1.alloc(N));
+        CS_CUDA(c->jcnt.alloc((size_t)N + 32));
         CS_CUDA(c->fx_bits.alloc(2 * tiles * 8));
         CS_CUDA(c->fx_td.alloc(((size_t)kcap + 1) * tpad));
         CS_CUDA(c->fx_tp.alloc(((size_t)kcap + 1) * tpad));
@@ -142,7 +143,7 @@ extern "C" int cs_chain_create(int N, int R, int kcap, int niter_cap, int rng_mo
     D.E = c->E.p; D.qmin = c->qmin.p; D.ua = c->ua.p; D.qnew_i = c->qnew_i.p; D.icnt = c->icnt.p;
     D.wn_q = c->wn_q.p; D.wn_w = c->wn_w.p; D.kmin = c->kmin.p;
     D.icur = c->icur.p; D.inv = c->inv.p; D.near = c->near.p; D.tile_sums = c->tile_sums.p;
-    D.zh1 = c->zh1.p; D.fx_bits = c->fx_bits.p; D.fx_td = c->fx_td.p; D.fx_tp = c->fx_tp.p; D.fx_scal = c->fx_scal.p;
+    D.jcnt = c->jcnt.p; D.zh1 = c->zh1.p; D.fx_bits = c->fx_bits.p; D.fx_td = c->fx_td.p; D.fx_tp = c->fx_tp.p; D.fx_scal = c->fx_scal.p;
     D.zspec = c->zspec.p; D.qcols = c->qcols.p; D.mean = c->mean.p; D.psum = c->psum.p; D.pcnt = c->pcnt.p;
     D.newslot = c->newslot.p; D.mt = c->mt.p; D.scal = c->scal.p;
     D.Zall = c->Zall.p; D.sigma_all = c->sigma_all.p; D.LL = c->LL.p; D.kt_all = c->kt_all.p;
@@ -388,6 +389,14 @@ extern "C" int cs_chain_walk_stats(cs_chain *c, int64_t *rounds, int64_t *cut_ma
     if (cut_margin) *cut_margin = h.cut_margin;
     if (cut_open) *cut_open = h.cut_open;
     if (cut_list) *cut_list = h.cut_maxev;
+    return CS_OK;
+}
+
+extern "C" int cs_chain_fix_prof(cs_chain *c, uint64_t *out1024)
+{
+    CS_REQUIRE(c && out1024, "cs_chain_fix_prof: NULL argument");
+    CS_CUDA(cudaStreamSynchronize(c->st));
+    CS_CUDA(cudaMemcpy(out1024, c->tile_sums.p, sizeof(uint64_t) * 1024, cudaMemcpyDeviceToHost));
     return CS_OK;
 }
 

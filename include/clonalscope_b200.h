@@ -157,9 +157,16 @@ int cs_chain_timing(cs_chain *c, double *run_ms, double *prepare_ms, double *ind
                     double *eos_ms);
 /* number of cells the sequential scan kernel had to process (diagnostics) */
 int cs_chain_stats(cs_chain *c, int64_t *cells_scanned, int64_t *n_events, int64_t *n_reject);
-/* the windowed walk's rounds since cs_chain_init, and how many of them stopped committing before the
- * window's last candidate because a cell ran out of margin / a cluster opened / the event list was full */
+/* the walk since cs_chain_init: steps of the fixed-point iteration (rounds), clusters opened
+ * inside sweeps (cut_open); the other two count what cut the rounds of the round-1 ring walk
+ * (init flag bit 2) short */
 int cs_chain_walk_stats(cs_chain *c, int64_t *rounds, int64_t *cut_margin, int64_t *cut_open, int64_t *cut_list);
+/* diagnostics (environment CS_FIX_PROF=1): per step of the last sweep's fixed-point walk, eight
+ * words — max and sum over the CTAs of the evaluation time, CTA 0's wait at the first grid
+ * barrier, its scan, its wait at the second barrier (ns), the first unsettled cell, the number of
+ * CTAs that had a tile, unused; 64 steps; then, per step, the sums over the CTAs of the time
+ * before the pull, in the pull and in the draw (8 words per step again) */
+int cs_chain_fix_prof(cs_chain *c, uint64_t *out1024);
 int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double *LL, double *L0,
                    int *kt_all, int64_t ucap_rows, int64_t *u_off, int *u_labels,
                    double *u_rows);

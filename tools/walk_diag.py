@@ -46,4 +46,13 @@ for t in range(nsw):
     print("sweep %3d: run %7.2f ms  prepare %5.2f index %5.2f walk %7.3f eos %5.2f | events %6d steps %5d opened %3d evaluated %8d  us/step %6.2f"
           % (t, ms[0].value, ms[1].value, ms[2].value, ms[3].value, ms[4].value, d[0], d[1], d[3], d[5],
              1e3 * ms[3].value / max(d[1], 1)), flush=True)
+    if os.environ.get("CS_FIX_PROF"):
+        pr = np.zeros(1024, dtype=np.uint64)
+        L.cs_chain_fix_prof(chain, dp(pr, C.c_uint64))
+        pr = pr.reshape(128, 8).astype(np.int64)
+        for k in range(min(int(d[1]), 64)):
+            n = max(int(pr[k, 6]), 1)
+            print("      step %2d: lo %6d  eval max %7.1f us  mean(busy CTAs) %7.1f us (%3d CTAs)  barrier1 %6.1f  scan %6.1f  barrier2 %6.1f | per tile: setup %5.1f pull %5.1f draw %5.1f"
+                  % (k, pr[k, 5], pr[k, 0] / 1e3, pr[k, 1] / 1e3 / n, pr[k, 6], pr[k, 2] / 1e3, pr[k, 3] / 1e3, pr[k, 4] / 1e3,
+                     pr[64 + k, 0] / 1e3 / n, pr[64 + k, 1] / 1e3 / n, pr[64 + k, 2] / 1e3 / n))
 print("total %.1f ms" % tot)
