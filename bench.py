@@ -4,17 +4,25 @@
 Workload (BASELINE.json configs[3]): synthetic 100k cells x 30k genes -> 15k 200-kb bins
 -> 300 segments, 1 GPU.  A "step" is one complete BayesNonparCluster chain (niter = 200
 sweeps over 100,000 cells x 300 segments, Philox mode, sequential within-sweep order kept);
-the metric is Gibbs cell-updates/s = N * niter / time.  The gene->bin aggregation of the
-100k x 30k count matrix (nnz ~ 2e8) is timed in the same run and reported under "binning"
-as GB/s against the measured HBM peak.
+the metric is Gibbs cell-updates/s = N * niter / time.
 
-  value     device-resident: inputs already in HBM, CUDA events on the chain's stream
-  e2e       through the C ABI with HOST buffers (cs_ncrp_gibbs): H2D of X, the chain,
-            D2H of Zall / Uall / sigma / Likelihood inside the timed region
-  roofline  dominant kernel of the step (prepare_kernel: scores every cell against every
-            live cluster + proposal + speculative draw), algorithmic bytes = N*S*8 per launch
-  cpu_baseline  the CPU oracle (validated restatement of the reference's R algorithm,
-            R-compatible RNG, 1 core) on a bounded sample of the same workload
+  value      device-resident: inputs already in HBM, CUDA events on the chain's stream
+  e2e        through the C ABI with HOST buffers (cs_ncrp_gibbs): H2D of X, the chain,
+             D2H of Zall / Uall / sigma / Likelihood inside the timed region
+  roofline   dominant kernel of the step (prepare_kernel: every cell against every live
+             cluster + proposal + speculative draw); algorithmic bytes = N*S*8 per launch;
+             fix_walk_kernel (the sweep's fixed-point iteration) nested under it
+  ranks      per-rank ms_per_step / events (independent chains: seed + rank)
+  seeds      the same chain under seeds 200..207 (min / median / max): how much the
+             throughput depends on the trajectory
+  fixtures   Philox-mode and R-compatible chains on the reference's real data sets
+  kernels    log-likelihood matrix (K = 2, 20), posterior tally (T = 100), allele sampler
+  binning    gene->bin aggregation GB/s against the measured HBM peak (+ end to end)
+  config5    BASELINE.json configs[4]: --spots cells sharded over the ranks: per-rank
+             binning + log-likelihood matrix + sufficient statistics, the NCCL all-reduce of
+             the statistics (timed on its own), sharded tally — strong scaling
+  cpu_baseline  the CPU oracle (validated restatement of the reference's R algorithm) on a
+             bounded sample of the same workload, 1 core
 
 `--impl reference` times the reference's own algorithm on the host cores (oracle port in
 R-compatible mode, one independent chain per core) on the same workload/metric.
@@ -35,9 +43,18 @@ sys.path.insert(0, ROOT)
 
 METRIC = "nCRP Gibbs cell-updates/sec at 100k cells x 300 segs; bin-count GB/s vs HBM"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-# captures (profiles/r1_scan_ring_full.txt: sweep 3 of the bench workload; profiles/r1_prepare_full.txt)
-SCAN_TRAFFIC_BYTES = 38_916_352
-PREPARE_TRAFFIC_BYTES = 350_580_480
+# captures of sweep 10 of this workload (profiles/r2_prepare_full.txt, profiles/r2_fix_walk_full.txt)
+PREPARE_TRAFFIC_BYTES = None
+WALK_TRAFFIC_BYTES = None
+KERNELS_PER_SWEEP = 10  # prepare, fix_walk, 8 end-of-sweep kernels
+
+
+def workload_config(N, R, niter, NB, G, B):
+    return dict(workload=f"synthetic {N} cells x {R} segments (K_true=12, alpha=beta=2, sigmas0=0.25), "
+                         f"niter={niter}; one independent chain per GPU",
+                step="one full chain of niter sweeps (reference arm: a bounded sample of it, see cpu_baseline.sample)",
+                l2="per-sweep working set (X 240 MB + Q + J) exceeds the 126 MB L2",
+                binning=f"{NB} cells x {G} genes -> {B} bins per GPU")
 
 
 def peaks():
@@ -141,11 +158,15 @@ def run_reference(a):
         tot_u += rate * dt
     value = tot_u / tot_t
     sample = (f"{cores} independent chains x {sweeps} sweep(s) of the {N} x {R} workload per step "
-              f"(R-compatible RNG, every sample.int heap-sorted as in base R)")
+              f"(R-compatible RNG, every sample.int heap-sorted as in base R; the cost of a cell-update does not "
+              f"depend on the sweep, so one sweep per chain stands for the niter={a.niter} of the workload)")
+    from clonalscope_b200 import synth
+    bins, genes = synth.geometry(G=a.genes)
+    B = len(bins["chr"])
     line = dict(metric=METRIC, value=value, unit="cell-updates/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=1e3 * tot_t / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=f"synthetic {N} cells x {R} segments, K_true=12, alpha=beta=2", niter=sweeps),
+                config=workload_config(N, R, a.niter, a.bin_cells, a.genes, B),
                 cpu_baseline=dict(value=value, unit="cell-updates/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -180,6 +201,232 @@ def synth_counts_gpu(torch, dev, N, G, seed=1001, mean_genes=2000):
     u = torch.rand(rowidx.numel(), generator=g, device=dev, dtype=torch.float32)
     x = (torch.log(u) / np.log(0.4)).floor().clamp(0, 32766).to(torch.float64) + 1.0
     return colptr, rowidx, x
+
+
+def make_chain_runner(L, _lib, N, R, niter, X, U0, Z0, sig0, alpha, beta, rng_mode=None):
+    """create a device chain and return (run(seed, flags) -> timing list, stats() -> dict, destroy)."""
+    dp = lambda arr, t: arr.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    chain = C.c_void_p()
+    mode = _lib.RNG_PHILOX if rng_mode is None else rng_mode
+    rc = L.cs_chain_create(N, R, 0, niter, mode, C.byref(chain))
+    assert rc == 0, L.cs_last_error()
+    K0 = U0.shape[0]
+
+    def run(seed, flags=0, sweeps=None):
+        rc = L.cs_chain_init(chain, dp(X, C.c_double), K0, dp(U0, C.c_double), dp(Z0, C.c_int), dp(sig0, C.c_double),
+                             C.c_double(alpha), C.c_double(beta), C.c_uint32(seed), flags)
+        assert rc == 0, L.cs_last_error()
+        n = niter if sweeps is None else sweeps
+        rc = L.cs_chain_run(chain, n, 1, 1)
+        assert rc == 0, L.cs_last_error()
+        ms = [C.c_double() for _ in range(5)]
+        rc = L.cs_chain_timing(chain, *[C.byref(m) for m in ms])
+        assert rc == 0, L.cs_last_error()
+        return [m.value for m in ms]
+
+    def stats():
+        v = [C.c_int64() for _ in range(7)]
+        L.cs_chain_stats(chain, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]))
+        L.cs_chain_walk_stats(chain, C.byref(v[3]), C.byref(v[4]), C.byref(v[5]), C.byref(v[6]))
+        return dict(events=int(v[1].value), cells_evaluated=int(v[0].value), walk_steps=int(v[3].value),
+                    clusters_opened=int(v[5].value))
+
+    return run, stats, (lambda: L.cs_chain_destroy(chain))
+
+
+def leg_seeds(run, stats, N, niter, seeds):
+    """the headline chain under other seeds: throughput must not hinge on one trajectory"""
+    rows = []
+    for sd in seeds:
+        ms = run(sd)[0]
+        st = stats()
+        rows.append(dict(seed=sd, ms=ms, value=N * niter / (ms * 1e-3), events=st["events"], walk_steps=st["walk_steps"]))
+    v = sorted(r["value"] for r in rows)
+    return dict(unit="cell-updates/s", min=v[0], median=float(np.median(v)), max=v[-1], max_over_min=v[-1] / v[0],
+                per_seed=rows)
+
+
+def leg_fixtures(L, _lib, niter=200, r_mode_sweeps=20):
+    """chains on the reference's real data (tests/golden/*.npz, extracted from the RDS files the
+    reference ships): Philox mode all `niter` sweeps; R-compatible mode (bit-identical to the
+    reference's own chain) on the first `r_mode_sweeps` sweeps"""
+    out = {}
+    for name in ("P5931", "BC_ductal2", "P5847_allcells"):
+        path = os.path.join(ROOT, "tests", "golden", f"sampler_{name}.npz")
+        if not os.path.exists(path):
+            continue
+        g = np.load(path)
+        X = np.asfortranarray(g["X"])
+        N, R = X.shape
+        U0 = np.asfortranarray(g["U0"])
+        Z0 = np.ascontiguousarray(g["Z0"], dtype=np.int32)
+        sig0 = np.ascontiguousarray(g["sigmas0"])
+        row = dict(cells=N, segments=R)
+        run, stats, destroy = make_chain_runner(L, _lib, N, R, niter, X, U0, Z0, sig0, float(g["alpha"]), float(g["beta"]))
+        run(200)
+        ms = run(200)[0]
+        st = stats()
+        row["philox"] = dict(ms=ms, value=N * niter / (ms * 1e-3), unit="cell-updates/s", niter=niter,
+                             moved_fraction=st["events"] / (N * niter), walk_steps=st["walk_steps"])
+        destroy()
+        run, stats, destroy = make_chain_runner(L, _lib, N, R, r_mode_sweeps, X, U0, Z0, sig0, float(g["alpha"]),
+                                                float(g["beta"]), rng_mode=_lib.RNG_R)
+        ms = run(int(g["seed"]))[0]
+        row["r_compatible"] = dict(ms=ms, value=N * r_mode_sweeps / (ms * 1e-3), unit="cell-updates/s", niter=r_mode_sweeps,
+                                   note="the reference's own stream and seed: the chain it ships, label for label")
+        destroy()
+        out[name] = row
+    return out
+
+
+def leg_kernels(torch, dev, L, hbm_peak, N, R, reps=20):
+    """device-resident GB/s of the fixed-state log-likelihood matrix and the posterior tally"""
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    X = 0.3 + 2.2 * torch.rand(N, R, generator=g, device=dev, dtype=torch.float64)
+    sig = torch.full((R,), 0.25, device=dev, dtype=torch.float64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    for K in (2, 20):
+        U = 0.3 + 2.2 * torch.rand(K, R, generator=g, device=dev, dtype=torch.float64)
+        LL = torch.empty(N, K, device=dev, dtype=torch.float64)
+        for _ in range(3):
+            assert L.cs_loglik_matrix_dev(N, R, K, vp(X), vp(U), vp(sig), vp(LL), st) == 0, L.cs_last_error()
+        e0.record()
+        for _ in range(reps):
+            L.cs_loglik_matrix_dev(N, R, K, vp(X), vp(U), vp(sig), vp(LL), st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        by = N * R * 8 + N * K * 8
+        out[f"loglik_matrix_K{K}"] = dict(ms=ms, gbs=by / (ms * 1e-3) / 1e9, frac_of_hbm_peak=by / (ms * 1e-3) / 1e9 / hbm_peak,
+                                          algorithmic_bytes=by, gflops=5.0 * N * R * K / (ms * 1e-3) / 1e9,
+                                          l2="X (N*R*8 bytes) exceeds the 126 MB L2" if N * R * 8 > 126e6 else "fits L2")
+    T = 100
+    Zall = torch.randint(1, 21, (T, N), generator=g, device=dev, dtype=torch.int32)
+    zmaj = torch.empty(N, device=dev, dtype=torch.int32)
+    for _ in range(3):
+        assert L.cs_majority_vote_dev(T, N, vp(Zall), C.c_int64(N), C.c_int64(1), vp(zmaj), st) == 0, L.cs_last_error()
+    e0.record()
+    for _ in range(reps):
+        L.cs_majority_vote_dev(T, N, vp(Zall), C.c_int64(N), C.c_int64(1), vp(zmaj), st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    by = T * N * 4 + N * 4
+    out["tally_T100"] = dict(ms=ms, gbs=by / (ms * 1e-3) / 1e9, frac_of_hbm_peak=by / (ms * 1e-3) / 1e9 / hbm_peak,
+                             algorithmic_bytes=by, l2="40 MB: fits the 126 MB L2 (repeated launches re-read it from L2)")
+    return out
+
+
+def leg_allele(cs, niter=20):
+    """the allele variant (coverage + BAF) on a synthetic case, both RNG modes"""
+    rng = np.random.default_rng(0)
+    N, R = 2000, 20
+    G = np.array([[0.5 * ii, j / ii] for ii in range(1, 7) for j in range(ii + 1)])  # the maxcp = 6 genotype grid
+    true = rng.integers(1, len(G) + 1, size=(3, R))
+    true[0, :] = 4
+    z = rng.integers(0, 3, N)
+    Xc = G[true[z] - 1, 0] + 0.15 * rng.standard_normal((N, R))
+    Xa = np.clip(G[true[z] - 1, 1] + 0.08 * rng.standard_normal((N, R)), 0, 1)
+    out = dict(cells=N, segments=R, niter=niter)
+    import contextlib, io
+    for name in ("philox", "R"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            cs.BayesNonparAlleleCluster(Xc, Xa, cna_states_WGS=true[1], niter=2, seed=200, rng=name)
+            t0 = time.perf_counter()
+            cs.BayesNonparAlleleCluster(Xc, Xa, cna_states_WGS=true[1], niter=niter, seed=200, rng=name)
+            dt = time.perf_counter() - t0
+        out[name] = dict(ms=dt * 1e3, value=N * niter / dt, unit="cell-updates/s (host API, end to end)")
+    return out
+
+
+def leg_config5(torch, dist, dev, L, cs, synth, a, world, rank, hbm_peak, barrier, max_over_ranks):
+    """BASELINE.json configs[4]: `spots` cells in all, sharded over the ranks (strong scaling).
+    Per rank: gene->bin aggregation of its columns, log-likelihood matrix of its cells against
+    K = 20 clusters, sufficient statistics of its cells, ONE NCCL all-reduce of the statistics,
+    tally of its cells over T = 100 kept sweeps.  No other collective on the path."""
+    from clonalscope_b200 import distributed as D5
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lo, hi = D5.shard_range(a.spots, world, rank)
+    n = hi - lo
+    R, K, T, G = a.segs, 20, 100, a.genes
+    bins, genes = synth.geometry(G=G)
+    map_ptr, map_bin = synth.geometry_map(bins, genes)
+    B = len(bins["chr"])
+    dp = lambda arr, t: arr.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    colptr, rowidx, x = synth_counts_gpu(torch, dev, n, G, seed=5001 + rank, mean_genes=a.spot_genes)
+    nnz_in = int(colptr[-1].item())
+    plan = C.c_void_p()
+    assert L.cs_bin_plan_create(G, B, dp(map_ptr, C.c_int32), dp(map_bin, C.c_int32), C.byref(plan)) == 0, L.cs_last_error()
+    out_colptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    nnz_out = C.c_int64()
+    assert L.cs_bin_counts_dev(plan, n, vp(colptr), vp(rowidx), vp(x), vp(out_colptr), None, None, 0, C.byref(nnz_out), st) == 0
+    cap = nnz_out.value
+    out_rowidx = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_x = torch.empty(cap, dtype=torch.float64, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(77 + rank)
+    X = 0.3 + 2.2 * torch.rand(n, R, generator=g, device=dev, dtype=torch.float64)
+    U = 0.3 + 2.2 * torch.rand(K, R, generator=torch.Generator(device=dev).manual_seed(9), device=dev, dtype=torch.float64)
+    sig = torch.full((R,), 0.25, device=dev, dtype=torch.float64)
+    LL = torch.empty(n, K, device=dev, dtype=torch.float64)
+    Zall = torch.randint(1, K + 1, (T, n), generator=g, device=dev, dtype=torch.int32)
+    zmaj = torch.empty(n, device=dev, dtype=torch.int32)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+
+    def step():
+        ev[0].record()
+        assert L.cs_bin_counts_dev(plan, n, vp(colptr), vp(rowidx), vp(x), vp(out_colptr), vp(out_rowidx), vp(out_x), cap,
+                                   C.byref(nnz_out), st) == 0, L.cs_last_error()
+        ev[1].record()
+        assert L.cs_loglik_matrix_dev(n, R, K, vp(X), vp(U), vp(sig), vp(LL), st) == 0, L.cs_last_error()
+        ev[2].record()
+        assert L.cs_majority_vote_dev(T, n, vp(Zall), C.c_int64(n), C.c_int64(1), vp(zmaj), st) == 0, L.cs_last_error()
+        ev[3].record()
+        buf = D5.device_stats(X, zmaj, U, K)
+        ev[4].record()
+        if world > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        ev[5].record()
+        torch.cuda.synchronize()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(5)] + [ev[0].elapsed_time(ev[5])]
+
+    for _ in range(3):
+        step()
+    rows = []
+    for _ in range(5):
+        barrier()
+        rows.append(step())
+    m = np.mean(np.array(rows), axis=0)
+    tot = max_over_ranks(float(m[5]))
+    # the all-reduce on its own: latency of one exchange of the statistics
+    buf = torch.zeros(2 * K * R + K + 2 * R, dtype=torch.float64, device=dev)
+    lat = None
+    if world > 1:
+        for _ in range(5):
+            dist.all_reduce(buf)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            dist.all_reduce(buf)
+        e1.record()
+        torch.cuda.synchronize()
+        lat = max_over_ranks(e0.elapsed_time(e1) / 50 * 1e3)
+    bin_bytes = 12 * nnz_in + 12 * cap + 2 * 8 * (n + 1) + 4 * (G + 1 + len(map_bin))
+    L.cs_bin_plan_destroy(plan)
+    return dict(spots=a.spots, spots_per_rank=n, genes=G, bins=B, segments=R, K=K, T=T, scaling="strong",
+                value=a.spots / (tot * 1e-3), unit="spots/s (binning + log-likelihood matrix + tally + statistics + all-reduce)",
+                ms=tot, ms_binning=float(m[0]), ms_loglik=float(m[1]), ms_tally=float(m[2]), ms_stats=float(m[3]),
+                ms_allreduce_in_step=float(m[4]), allreduce_us=lat, allreduce_bytes=int(buf.numel() * 8),
+                binning_gbs_per_rank=bin_bytes / (float(m[0]) * 1e-3) / 1e9,
+                binning_frac_of_hbm_peak=bin_bytes / (float(m[0]) * 1e-3) / 1e9 / hbm_peak,
+                note="rank 0's stage times; `ms` is the max over ranks of the whole step")
+
 
 
 def run_ours(a):
@@ -223,38 +470,35 @@ def run_ours(a):
     Z0 = (cs.loglik_matrix(X, s["U0"], sig0).argmax(axis=1) + 1).astype(np.int32)
     seed = 200 + rank
     dp = lambda arr, t: arr.ctypes.data_as(C.POINTER(t))  # noqa: E731
-
-    chain = C.c_void_p()
-    rc = L.cs_chain_create(N, R, 0, niter, _lib.RNG_PHILOX, C.byref(chain))
-    assert rc == 0, L.cs_last_error()
-
-    def chain_step(flags):
-        rc = L.cs_chain_init(chain, dp(X, C.c_double), 2, dp(U0, C.c_double), dp(Z0, C.c_int), dp(sig0, C.c_double),
-                             C.c_double(2.0), C.c_double(2.0), C.c_uint32(seed), flags)
-        assert rc == 0, L.cs_last_error()
-        rc = L.cs_chain_run(chain, niter, 1, 1)
-        assert rc == 0, L.cs_last_error()
-        ms = [C.c_double() for _ in range(5)]
-        rc = L.cs_chain_timing(chain, *[C.byref(m) for m in ms])
-        assert rc == 0, L.cs_last_error()
-        return [m.value for m in ms]
+    run_chain, chain_stats, chain_destroy = make_chain_runner(L, _lib, N, R, niter, X, U0, Z0, sig0, 2.0, 2.0)
 
     for _ in range(a.warmup):
-        chain_step(0)
+        run_chain(seed)
     barrier()
     run_ms = []
     with ClockSampler(local) as clk:
         for _ in range(a.steps):
             barrier()
-            run_ms.append(chain_step(0)[0])
+            run_ms.append(run_chain(seed)[0])
         barrier()
-        # kernel-group split (events around every launch group; a separate, untimed-for-value pass)
-        prof = chain_step(2)
+        # kernel-group split (events around every launch group; a separate pass, not part of `value`)
+        prof = run_chain(seed, 2)
     clocks = clk.summary()
-    sc, ev, rj = C.c_int64(), C.c_int64(), C.c_int64()
-    L.cs_chain_stats(chain, C.byref(sc), C.byref(ev), C.byref(rj))
-    step_ms = max_over_ranks(float(np.mean(run_ms)))
+    cstats = chain_stats()
+    my_ms = float(np.mean(run_ms))
+    step_ms = max_over_ranks(my_ms)
     value = world * N * niter / (step_ms * 1e-3)
+    if world > 1:
+        t = torch.tensor([my_ms, float(cstats["events"]), float(cstats["walk_steps"])], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        ranks = [dict(rank=i, seed=200 + i, ms_per_step=float(v[0]), events=int(v[1]), walk_steps=int(v[2])) for i, v in enumerate(allr)]
+    else:
+        ranks = [dict(rank=0, seed=seed, ms_per_step=my_ms, events=cstats["events"], walk_steps=cstats["walk_steps"])]
+
+    seeds = None
+    if world == 1 and not a.no_seeds:
+        seeds = leg_seeds(run_chain, chain_stats, N, niter, list(range(200, 208)))
 
     # ---------------- end to end through the C ABI with host buffers
     Zall = np.zeros((niter, N), dtype=np.int32, order="F")
@@ -287,7 +531,7 @@ def run_ours(a):
     d2h = Zall.nbytes + sigma_all.nbytes + LLv.nbytes + kt_all.nbytes + int(u_off[-1]) * (R * 8 + 4) + u_off.nbytes
     e2e = dict(value=world * N * niter / (e2e_ms * 1e-3), unit="cell-updates/s", ms_per_step=e2e_ms,
                h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h))
-    L.cs_chain_destroy(chain)
+    chain_destroy()
 
     # ---------------- independent chains run concurrently on the GPU (supplementary: a chain's
     # sequential walk occupies one cluster of SMs, other chains' all-SM kernels fill the rest)
@@ -444,32 +688,57 @@ def run_ours(a):
                    binning_gbs=24.0 * int(cp_h[nb3]) / bdt / 1e9,
                    binning_sample=f"sparse restatement, {nb3} cells, 1 core")
 
+    fixtures = kernels = allele = None
+    if world == 1 and not a.no_extra:
+        fixtures = leg_fixtures(L, _lib)
+        kernels = leg_kernels(torch, dev, L, hbm_peak, N, R)
+        allele = leg_allele(cs)
+    config5 = None
+    if a.spots > 0:
+        config5 = leg_config5(torch, dist if world > 1 else None, dev, L, cs, synth, a, world, rank, hbm_peak, barrier, max_over_ranks)
+    if cpu is not None and not a.no_cpu:
+        # the same algorithm as the GPU path (Philox mode of the oracle), one sweep, one core
+        import oracle as O3
+        t0 = time.perf_counter()
+        O3.gibbs(s["X"][:cs_n], s["U0"], Z0[:cs_n], s["sigmas0"], 2.0, 2.0, 1, 200, rng_mode=O3.RNG_PHILOX, ucap_rows=512)
+        cpu["philox_port_value"] = cs_n / (time.perf_counter() - t0)
+        cpu["philox_port_note"] = "the oracle's Philox mode (the GPU path's own specification), 1 sweep, 1 core"
+
     if rank == 0:
-        scan_ms = prof[3] / niter  # dominant kernel of the step: the one-CTA sequential commit
+        prep_ms = prof[1] / niter  # dominant kernel of the step
+        walk_ms = prof[3] / niter
         alg_bytes = N * R * 8      # S*8 bytes per cell-update, N cell-updates per launch
-        ach = alg_bytes / (scan_ms * 1e-3) / 1e9
+        ach = alg_bytes / (prep_ms * 1e-3) / 1e9
         line = dict(
             metric=METRIC, value=value, unit="cell-updates/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
             ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-            data="synthetic",
-            config=dict(workload=f"synthetic {N} cells x {R} segments (K_true=12, alpha=beta=2, sigmas0=0.25), "
-                                 f"niter={niter}, Philox; one independent chain per GPU",
-                        step="one full chain of niter sweeps", l2="per-sweep working set (X 240 MB + Q + J) exceeds the 126 MB L2",
-                        binning=f"{NB} cells x {G} genes -> {B} bins per GPU"),
-            e2e=e2e, gpu_launches=int(a.steps * niter * 15),
-            roofline=dict(bound="hbm", kernel="scan_ring_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
-                          frac=ach / hbm_peak, traffic=SCAN_TRAFFIC_BYTES, peak_source=peak_src,
-                          note="latency-bound sequential commit (one CTA walks the cells in the sweep's order; "
-                               "15 more CTAs of its cluster only help when a cluster opens): algorithmic bytes "
-                               "are N*S*8 per launch, the kernel itself touches far less",
-                          ms_per_launch=scan_ms, share_of_step=prof[3] / max(prof[0], 1e-9),
-                          prepare_kernel=dict(ms_per_launch=prof[1] / niter,
-                                              achieved=alg_bytes / (prof[1] / niter * 1e-3) / 1e9,
-                                              frac=alg_bytes / (prof[1] / niter * 1e-3) / 1e9 / hbm_peak,
-                                              traffic=PREPARE_TRAFFIC_BYTES)),
-            sweep_split_ms=dict(run=prof[0], prepare=prof[1], index=prof[2], scan=prof[3], end_of_sweep=prof[4]),
-            scan=dict(cells_scanned=int(sc.value), events=int(ev.value)),
-            binning=binning, clocks=clocks)
+            data="synthetic", config=workload_config(N, R, niter, NB, G, B),
+            e2e=e2e, gpu_launches=int(a.steps * niter * KERNELS_PER_SWEEP),
+            roofline=dict(bound="hbm", kernel="prepare_kernel", achieved=ach, peak=hbm_peak, unit="GB/s",
+                          frac=ach / hbm_peak, traffic=PREPARE_TRAFFIC_BYTES, peak_source=peak_src,
+                          note="one launch per sweep: reads X once (N*S*8 algorithmic bytes), scores every cell against "
+                               "every live cluster in 64-bit fixed point, draws the proposal (Philox) and the speculative "
+                               "assignment; instruction-bound (see profiles/), so the HBM fraction is low by construction",
+                          ms_per_launch=prep_ms, share_of_step=prof[1] / max(prof[0], 1e-9),
+                          fix_walk_kernel=dict(ms_per_launch=walk_ms, share_of_step=prof[3] / max(prof[0], 1e-9),
+                                               achieved=alg_bytes / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None,
+                                               frac=alg_bytes / (walk_ms * 1e-3) / 1e9 / hbm_peak if walk_ms > 0 else None,
+                                               traffic=WALK_TRAFFIC_BYTES,
+                                               note="cooperative, all SMs: the sweep as the fixed point of a parallel map "
+                                                    "(a few passes over the cells behind the last settled one); "
+                                                    "latency-bound on grid barriers and gathers")),
+            sweep_split_ms=dict(run=prof[0], prepare=prof[1], walk=prof[3], end_of_sweep=prof[4]),
+            walk=cstats, ranks=ranks, binning=binning, clocks=clocks)
+        if seeds:
+            line["seeds"] = seeds
+        if fixtures:
+            line["fixtures"] = fixtures
+        if kernels:
+            line["kernels"] = kernels
+        if allele:
+            line["allele_sampler"] = allele
+        if config5:
+            line["config5"] = config5
         if conc:
             line["concurrent_chains"] = conc
         if region:
@@ -498,6 +767,10 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=100000)
     ap.add_argument("--cpu-sweeps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-seeds", action="store_true", help="skip the seeds 200..207 leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fixtures / kernels / allele legs")
+    ap.add_argument("--spots", type=int, default=1000000, help="BASELINE config 5: cells sharded over the ranks (0 = skip)")
+    ap.add_argument("--spot-genes", type=int, default=2000, help="mean expressed genes per spot in the config-5 leg")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

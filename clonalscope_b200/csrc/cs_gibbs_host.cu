@@ -3,7 +3,9 @@
 // Reference boundary: BayesNonparCluster, R/BayesNonparCluster.R:21-289.
 #include "cs_gibbs.cuh"
 
+#include <chrono>
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -33,6 +35,10 @@ struct cs_chain {
     DevBuf<long long> u_off;
     DevBuf<uint32_t> mt;
     DevBuf<ChainScal> scal;
+    DevBuf<int> zt;                 // cs_chain_fetch: Zall transposed into R's layout (kept between calls)
+    void *pin[2] = {nullptr, nullptr}; // pinned staging for the device-to-host copies (two halves in flight)
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    static constexpr size_t kPinBytes = 16u << 20;
     // timing of the last cs_chain_run: whole run, and (flags bit 1) per-sweep kernel groups
     cudaEvent_t run_ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> sweep_ev;
@@ -42,9 +48,40 @@ struct cs_chain {
         for (auto e : sweep_ev) cudaEventDestroy(e);
         for (auto e : run_ev)
             if (e) cudaEventDestroy(e);
+        for (auto e : pin_ev)
+            if (e) cudaEventDestroy(e);
+        for (auto p : pin)
+            if (p) cudaFreeHost(p);
         if (st) cudaStreamDestroy(st);
     }
 };
+
+// device -> pageable host memory through two pinned staging buffers: the copy of one piece
+// overlaps the host-side copy-out of the one before (cudaMemcpy into pageable memory stages
+// through one small driver buffer and serialises both)
+static int d2h_staged(cs_chain *c, void *dst, const void *dsrc, size_t bytes)
+{
+    if (bytes == 0) return CS_OK;
+    for (int b = 0; b < 2; b++) {
+        if (!c->pin[b]) CS_CUDA(cudaHostAlloc(&c->pin[b], cs_chain::kPinBytes, cudaHostAllocDefault));
+        if (!c->pin_ev[b]) CS_CUDA(cudaEventCreateWithFlags(&c->pin_ev[b], cudaEventDisableTiming));
+    }
+    const size_t piece = cs_chain::kPinBytes;
+    const size_t np = (bytes + piece - 1) / piece;
+    for (size_t i = 0; i <= np; i++) {
+        if (i < np) {
+            const size_t off = i * piece, len = bytes - off < piece ? bytes - off : piece;
+            CS_CUDA(cudaMemcpyAsync(c->pin[i & 1], static_cast<const char *>(dsrc) + off, len, cudaMemcpyDeviceToHost, c->st));
+            CS_CUDA(cudaEventRecord(c->pin_ev[i & 1], c->st));
+        }
+        if (i > 0) {
+            const size_t off = (i - 1) * piece, len = bytes - off < piece ? bytes - off : piece;
+            CS_CUDA(cudaEventSynchronize(c->pin_ev[(i - 1) & 1]));
+            memcpy(static_cast<char *>(dst) + off, c->pin[(i - 1) & 1], len);
+        }
+    }
+    return CS_OK;
+}
 
 static const int kDefaultKcapPhilox = 256, kDefaultLcapR = 4096;
 static thread_local cs_chain *g_cached = nullptr; // see cs_ncrp_gibbs
@@ -410,12 +447,10 @@ extern "C" int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double 
     if (L0) CS_CUDA(cudaMemcpy(L0, c->L0.p, sizeof(double), cudaMemcpyDeviceToHost));
     if (T == 0) return CS_OK;
     if (Zall) { // device sweep-major T x N (row-major) -> R's column-major T x N (== row-major N x T)
-        DevBuf<int> tmp;
-        CS_CUDA(tmp.alloc((size_t)T * N));
-        rc = cs_transpose<int>(T, N, c->Zall.p, tmp.p, c->st);
+        CS_CUDA(c->zt.reserve((size_t)c->niter_cap * N));
+        rc = cs_transpose<int>(T, N, c->Zall.p, c->zt.p, c->st);
         if (rc) return rc;
-        CS_CUDA(cudaMemcpyAsync(Zall, tmp.p, sizeof(int) * (size_t)T * N, cudaMemcpyDeviceToHost, c->st));
-        CS_CUDA(cudaStreamSynchronize(c->st));
+        if ((rc = d2h_staged(c, Zall, c->zt.p, sizeof(int) * (size_t)T * N))) return rc;
     }
     // sigma_all: device T x R row-major == column-major R x T: column t = sweep t
     if (sigma_all) CS_CUDA(cudaMemcpy(sigma_all, c->sigma_all.p, sizeof(double) * (size_t)T * R, cudaMemcpyDeviceToHost));
@@ -431,7 +466,7 @@ extern "C" int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double 
             return CS_ERR_UCAP;
         }
         if (u_labels && need) CS_CUDA(cudaMemcpy(u_labels, c->u_labels.p, sizeof(int) * (size_t)need, cudaMemcpyDeviceToHost));
-        if (u_rows && need) CS_CUDA(cudaMemcpy(u_rows, c->u_rows.p, sizeof(double) * (size_t)need * R, cudaMemcpyDeviceToHost));
+        if (u_rows && need && (rc = d2h_staged(c, u_rows, c->u_rows.p, sizeof(double) * (size_t)need * R))) return rc;
     }
     return CS_OK;
 }
@@ -493,9 +528,18 @@ extern "C" int cs_ncrp_gibbs(int N, int R, const double *X, int K0, const double
             }
         }
     } guard{c, dev};
+    const bool e2e_prof = getenv("CS_E2E_PROF") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    auto t0 = now();
     if ((rc = cs_chain_init(c, X, K0, U0, Z0, sigmas0, alpha, beta, seed, o.flags))) return rc;
+    const double t_init = ms_since(t0);
+    t0 = now();
     if ((rc = cs_chain_run(c, niter, 1, 1))) return rc;
+    const double t_run = ms_since(t0);
+    t0 = now();
     if ((rc = cs_chain_fetch(c, Zall, sigma_all, LL, L0, kt_all, ucap_rows, u_off, u_labels, u_rows))) return rc;
+    if (e2e_prof) fprintf(stderr, "cs_ncrp_gibbs: init %.1f ms  run %.1f ms  fetch %.1f ms\n", t_init, t_run, ms_since(t0));
     if (n_reject) {
         int64_t sc, ev;
         if ((rc = cs_chain_stats(c, &sc, &ev, n_reject))) return rc;
