@@ -3,20 +3,23 @@
 //
 //   LL[i,k] = sum_r dnorm(X[i,r]; U[k,r], sigma[r], log=TRUE)   (NA segments skipped)
 // reference: R/BayesNonparCluster.R:91-96 (Z0 init), :193 (scoring), R/AssignCluster.R:58.
-// One warp per cell: lanes stride the segments (coalesced 256 B row reads), FP64
-// accumulation, butterfly reduction.  Not a tensor-core workload: the NaN mask and the
+// One warp per cell: lanes stride the segments (coalesced 256 B row reads), the row kept in
+// registers and scored against four clusters per pass, FP64 accumulation, folded warp sums.  Not a tensor-core workload: the NaN mask and the
 // 1e-6 criterion rule out the expanded-square GEMM form.
 #include "cs_common.cuh"
 
+#include <math_constants.h>
 #include <vector>
 
 namespace {
 
 constexpr int LL_THREADS = 256;
+constexpr int LL_KT = 4; // clusters scored per pass over a cell's registers
 
+// any R: a pass over the row per cluster (the row comes from L1 after the first)
 __global__ void __launch_bounds__(LL_THREADS)
-loglik_matrix_kernel(int N, int R, int K, const double *__restrict__ X, const double *__restrict__ U,
-                     const double *__restrict__ sigma, double *__restrict__ LL)
+loglik_matrix_generic_kernel(int N, int R, int K, const double *__restrict__ X, const double *__restrict__ U,
+                             const double *__restrict__ sigma, double *__restrict__ LL)
 {
     extern __shared__ double s_ll[]; // isig[R], cterm[R] = log(sigma)+ln sqrt(2 pi)
     double *s_isig = s_ll, *s_c = s_ll + R;
@@ -51,6 +54,71 @@ loglik_matrix_kernel(int N, int R, int K, const double *__restrict__ X, const do
     }
 }
 
+// R <= 32 * NCH: the cell's row and 1/sigma stay in registers, LL_KT clusters per pass for independent FMA
+// chains, and the LL_KT warp sums are folded together (6 shuffles instead of 5 per cluster).
+template <int NCH>
+__global__ void __launch_bounds__(LL_THREADS)
+loglik_matrix_kernel(int N, int R, int K, const double *__restrict__ X, const double *__restrict__ U,
+                     const double *__restrict__ sigma, double *__restrict__ LL)
+{
+    extern __shared__ double s_ll[];
+    double *s_isig = s_ll, *s_c = s_ll + R;
+    for (int r = threadIdx.x; r < R; r += LL_THREADS) {
+        const double s = sigma[r];
+        s_isig[r] = 1.0 / s;
+        s_c[r] = CS_LN_SQRT_2PI + log(s);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = LL_THREADS / 32;
+    const int kslot = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1); // which of the LL_KT sums this lane ends up with
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < N; i += gridDim.x * warps_per_block) {
+        const double *xrow = X + (size_t)i * R;
+        double x[NCH], is[NCH];
+        double cpart = 0.0;
+        unsigned okmask = 0u; // chunks whose segment exists and is not NA for this cell
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int r = lane + 32 * c;
+            const double xv = (r < R) ? __ldcs(xrow + r) : CUDART_NAN;
+            const bool ok = !cs_isna(xv);
+            x[c] = xv;
+            is[c] = ok ? s_isig[r] : 0.0;
+            if (ok) {
+                cpart += s_c[r];
+                okmask |= 1u << c;
+            }
+        }
+        cpart = cs_warp_sum_bfly(cpart);
+        for (int k0 = 0; k0 < K; k0 += LL_KT) {
+            double q[LL_KT];
+#pragma unroll
+            for (int j = 0; j < LL_KT; j++) q[j] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int r = min(lane + 32 * c, R - 1);
+#pragma unroll
+                for (int j = 0; j < LL_KT; j++) {
+                    const int k = min(k0 + j, K - 1);
+                    const double d = (x[c] - __ldg(U + (size_t)k * R + r)) * is[c];
+                    if (okmask >> c & 1u) q[j] = fma(d, d, q[j]);
+                }
+            }
+            // fold: halves of the warp keep two sums each, then quarters one each
+            const bool up16 = lane & 16, up8 = lane & 8;
+            const double s0 = up16 ? q[0] : q[2], s1 = up16 ? q[1] : q[3]; // what goes to the other half
+            double a0 = (up16 ? q[2] : q[0]) + __shfl_xor_sync(CS_FULL, s0, 16);
+            double a1 = (up16 ? q[3] : q[1]) + __shfl_xor_sync(CS_FULL, s1, 16);
+            double b = (up8 ? a1 : a0) + __shfl_xor_sync(CS_FULL, up8 ? a0 : a1, 8);
+            b += __shfl_xor_sync(CS_FULL, b, 4);
+            b += __shfl_xor_sync(CS_FULL, b, 2);
+            b += __shfl_xor_sync(CS_FULL, b, 1);
+            const int k = k0 + kslot;
+            if ((lane & 7) == 0 && k < K) LL[(size_t)i * K + k] = -(cpart + 0.5 * b);
+        }
+    }
+}
+
 // out[c*rows + r] = in[r*cols + c] : generic tiled transpose (rows x cols row-major in)
 template <typename T>
 __global__ void transpose_kernel(int rows, int cols, const T *__restrict__ in, T *__restrict__ out)
@@ -69,29 +137,62 @@ __global__ void transpose_kernel(int rows, int cols, const T *__restrict__ in, T
 }
 
 // ---- majority vote --------------------------------------------------------
-// one thread per cell; element (t,i) at Z[t*st + i*si].  Fast path: the first label
-// holds a strict majority (the usual state of a converged chain).
-__global__ void majority_vote_kernel(int T, int N, const int *__restrict__ Z, int64_t st, int64_t si,
-                                     int *__restrict__ out)
+// one thread per cell; element (t,i) at Z[t*st + i*si].  One pass over the T labels with the
+// distinct labels seen so far and their counts in MV_SLOTS registers (a converged chain shows
+// two or three per cell); a cell with more distinct labels than that falls back to counting each
+// first occurrence against the whole column.  Most frequent label, ties -> the smallest label
+// (names(table(x))[which.max(table(x))], R/AssignCluster.R:37).
+constexpr int MV_SLOTS = 6;
+
+__global__ void __launch_bounds__(128)
+majority_vote_kernel(int T, int N, const int *__restrict__ Z, int64_t st, int64_t si, int *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int *z = Z + (size_t)i * si;
-    int best = 0, bc = 0;
-    {
-        const int l0 = z[0];
-        int c0 = 0;
-        for (int t = 0; t < T; t++) c0 += (z[(size_t)t * st] == l0);
-        if (2 * c0 > T) {
-            out[i] = l0;
-            return;
-        }
-        best = l0;
-        bc = c0;
+    int lab[MV_SLOTS], cnt[MV_SLOTS];
+#pragma unroll
+    for (int s = 0; s < MV_SLOTS; s++) {
+        lab[s] = 0;
+        cnt[s] = 0;
     }
-    for (int a = 1; a < T; a++) {
+    int used = 0;
+    bool overflow = false;
+#pragma unroll 4
+    for (int t = 0; t < T; t++) {
+        const int l = __ldcs(z + (size_t)t * st);
+        bool hit = false;
+#pragma unroll
+        for (int s = 0; s < MV_SLOTS; s++) {
+            const bool m = s < used && lab[s] == l;
+            cnt[s] += m ? 1 : 0;
+            hit |= m;
+        }
+        if (!hit) {
+#pragma unroll
+            for (int s = 0; s < MV_SLOTS; s++)
+                if (s == used) {
+                    lab[s] = l;
+                    cnt[s] = 1;
+                }
+            overflow |= used >= MV_SLOTS;
+            used = min(used + 1, MV_SLOTS);
+        }
+    }
+    if (!overflow) {
+        int best = lab[0], bc = cnt[0];
+#pragma unroll
+        for (int s = 1; s < MV_SLOTS; s++)
+            if (s < used && (cnt[s] > bc || (cnt[s] == bc && lab[s] < best))) {
+                bc = cnt[s];
+                best = lab[s];
+            }
+        out[i] = best;
+        return;
+    }
+    int best = 0, bc = 0;
+    for (int a = 0; a < T; a++) {
         const int la = z[(size_t)a * st];
-        if (la == best) continue;
         int c = 0;
         bool seen = false;
         for (int t = 0; t < T; t++) {
@@ -131,11 +232,20 @@ extern "C" int cs_loglik_matrix_dev(int N, int R, int K, const double *d_X, cons
     if (N == 0 || K == 0) return CS_OK;
     const size_t smem = sizeof(double) * 2 * (size_t)R;
     CS_REQUIRE(smem <= 200 * 1024, "cs_loglik_matrix: R=%d too large", R);
-    CS_CUDA(cudaFuncSetAttribute(loglik_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (N + LL_THREADS / 32 - 1) / (LL_THREADS / 32);
     const int maxgrid = cs_num_sms() * 8;
     if (grid > maxgrid) grid = maxgrid;
-    loglik_matrix_kernel<<<grid, LL_THREADS, smem, (cudaStream_t)stream>>>(N, R, K, d_X, d_U, d_sigma, d_LL);
+    void (*kern)(int, int, int, const double *, const double *, const double *, double *) = loglik_matrix_generic_kernel;
+    if (R <= 32) kern = loglik_matrix_kernel<1>;
+    else if (R <= 64) kern = loglik_matrix_kernel<2>;
+    else if (R <= 128) kern = loglik_matrix_kernel<4>;
+    else if (R <= 192) kern = loglik_matrix_kernel<6>;
+    else if (R <= 256) kern = loglik_matrix_kernel<8>;
+    else if (R <= 320) kern = loglik_matrix_kernel<10>;
+    else if (R <= 384) kern = loglik_matrix_kernel<12>;
+    else if (R <= 512) kern = loglik_matrix_kernel<16>;
+    CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, LL_THREADS, smem, (cudaStream_t)stream>>>(N, R, K, d_X, d_U, d_sigma, d_LL);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }

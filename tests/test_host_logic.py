@@ -223,3 +223,40 @@ def test_host_r_stream_matches_the_oracle(oracle):
         a = L.cso_sample_int_prob(C.byref(gm), n, p.ctypes.data_as(C.POINTER(C.c_double)),
                                   perm.ctypes.data_as(C.POINTER(C.c_int)))
         assert a == sample_int_prob_one(r, P)
+
+
+def test_r_glue_compiles_against_the_c_abi_and_shims_match_it(tmp_path):
+    """integration/src/cs_glue.c is compiled (not linked) against a declarations-only copy of R's C
+    API, so any drift against include/clonalscope_b200.h is a compile error; every .Call in the R
+    shims must name a registered routine with the registered number of arguments."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    glue = os.path.join(root, "integration", "src", "cs_glue.c")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-c", glue, "-I", os.path.join(root, "integration", "rstub"),
+                           "-I", os.path.join(root, "include"), "-o", str(tmp_path / "cs_glue.o")])
+    src = open(glue).read()
+    registered = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(cs_R_\w+)", \(DL_FUNC\)&\1, (\d+)\}', src)}
+    assert len(registered) >= 8
+    shims = os.path.join(root, "integration", "R")
+    files = sorted(f for f in os.listdir(shims) if f.endswith(".R"))
+    assert {"Gene_bin_cell_rna_filtered.R", "EstRegionCov.R", "BayesNonparCluster.R", "BayesNonparAlleleCluster.R",
+            "AssignCluster.R"} <= set(files)
+    used = set()
+    for f in files:
+        text = open(os.path.join(shims, f)).read()
+        for m in re.finditer(r'\.Call\("(\w+)"', text):
+            name = m.group(1)
+            # count top-level commas up to the matching parenthesis
+            i, depth, nargs = m.end(), 1, 0
+            while depth:
+                ch = text[i]
+                depth += ch in "([{"
+                depth -= ch in ")]}"
+                nargs += depth == 1 and ch == ","
+                i += 1
+            nargs -= 1  # PACKAGE=
+            assert name in registered, f"{f}: .Call to unregistered {name}"
+            assert nargs == registered[name], f"{f}: {name} called with {nargs} arguments, registered with {registered[name]}"
+            used.add(name)
+    assert used == set(registered), f"registered but never called from a shim: {set(registered) - used}"
