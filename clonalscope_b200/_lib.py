@@ -23,6 +23,7 @@ SYMBOLS = [
     "cs_ncrp_gibbs_allele",
     "cs_majority_vote", "cs_majority_vote_dev",
     "cs_cluster_stats_dev", "cs_sigma_stats_dev", "cs_cluster_stats", "cs_sigma_stats", "cs_gene_moments",
+    "cs_rowsum_by_label", "cs_rowsum_by_label_dev", "cs_bin_job_rowsum_by_label", "cs_segment_hmm",
 ]
 
 

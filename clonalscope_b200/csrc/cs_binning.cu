@@ -738,21 +738,25 @@ bin_fill_stream_kernel(int N, int B, const int64_t *__restrict__ colptr,
 // always held by running warps), no CTA barrier anywhere.  A column is traversed twice in tiles
 // of 256 entries (eight consecutive entries per lane, 256-bit loads):
 //   count  row indices only: interval ends, prefix max M across the tile (lane-serial over the
-//          eight entries + one warp scan), number of new bins -> the column's count; published,
-//          and the exclusive prefix over the columns in front is collected (look-back);
-//   fill   row indices again (L2 hits: they were read microseconds ago) + values; the ranks of
-//          new bins are the running count C; sums and bin ids go to a per-warp ring of 512
-//          ranks in shared memory and are flushed to the output in rank order (coalesced) as
-//          soon as no later entry can touch them: every rank below C - (M - f_last).
+//          eight entries + one warp scan), number of new bins -> the column's count; published;
+//   fill   row indices again (L2 hits: they were read microseconds ago) + values.  The ranks a
+//          tile opens are appended to a LINEAR staging buffer of the warp ({sum, bin} pairs in
+//          rank order): a lane walks its eight entries with a running shared-memory address —
+//          new bins are stores at immediate offsets, the old part of an entry is one address
+//          kept for after the stores — no ring arithmetic.  Ranks below C - (M - f_last) can no
+//          longer be touched (first bins do not decrease); when the next tile would not fit they
+//          are written to the output in rank order (coalesced) and the at most OP_MAXNH ranks
+//          behind them move to the front of the buffer.  The exclusive prefix over the columns
+//          in front is collected (look-back) only at the first such write, by which time they
+//          have long published their counts.
 // Exactness as in the other kernels: values must be integers (checked), and a column whose
 // n_entries x 2^bits(max |v|) could overflow an int32 sum raises FLAG_INEXACT (FP64 re-run).
 constexpr int OP_THREADS = 256;
 constexpr int OP_WARPS = OP_THREADS / 32;
-constexpr int OP_RING = 512;
-constexpr int OP_MASK = OP_RING - 1;
+constexpr int OP_CAP = 640;  // ranks a warp stages ({sum, bin}: 8 bytes each)
 constexpr int OP_EPL = 8;
 constexpr int OP_TILE = 32 * OP_EPL;
-constexpr int OP_MAXNH = 32; // widest gene, in bins, this kernel takes (8 x OP_MAXNH + OP_MAXNH ranks must fit the ring)
+constexpr int OP_MAXNH = 32; // widest gene, in bins, this kernel takes
 constexpr unsigned long long OP_FLAG_A = 1ull << 62, OP_FLAG_P = 2ull << 62, OP_VALMASK = (1ull << 62) - 1;
 
 __device__ __forceinline__ void op_load_g8(const int32_t *__restrict__ p, int (&g)[8], bool last_use)
@@ -772,6 +776,7 @@ __device__ __forceinline__ void op_load_x4(const double *__restrict__ p, double 
                  : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
                  : "l"(p));
 }
+__device__ __forceinline__ void op_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned long long op_ld_status(const unsigned long long *p)
 {
     unsigned long long v;
@@ -789,6 +794,13 @@ __device__ __forceinline__ int warp_incl_sum(int v, int lane)
         const int t = __shfl_up_sync(CS_FULL, v, off);
         if (lane >= off) v += t;
     }
+    return v;
+}
+// (shfl.up hands a lane below the offset its own value back: max needs no lane test)
+__device__ __forceinline__ int warp_incl_max_nt(int v)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) v = max(v, __shfl_up_sync(CS_FULL, v, off));
     return v;
 }
 
@@ -812,18 +824,22 @@ __device__ __forceinline__ void op_tile_words(const int32_t *__restrict__ rowidx
     }
 }
 
-// shared-memory accesses of the ring by 32-bit shared address ({sum, bin id} pairs of 8 bytes)
-__device__ __forceinline__ void op_ring_store_if(int cond_gt, int than, unsigned addr, int sum, int bin)
+// the staging buffer by 32-bit shared address ({sum, bin} pairs of 8 bytes)
+__device__ __forceinline__ void op_st_pair_if(int cond_gt, int than, unsigned addr, int sum, int bin)
 {
     asm volatile("{ .reg .pred p; setp.gt.s32 p, %0, %1; @p st.shared.v2.s32 [%2], {%3, %4}; }" ::"r"(cond_gt), "r"(than),
                  "r"(addr), "r"(sum), "r"(bin)
                  : "memory");
 }
-__device__ __forceinline__ void op_ring_add(unsigned addr, int v)
+__device__ __forceinline__ void op_st_pair(unsigned addr, int sum, int bin)
+{
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr), "r"(sum), "r"(bin) : "memory");
+}
+__device__ __forceinline__ void op_red_add(unsigned addr, int v)
 {
     asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void op_ring_load(unsigned addr, int &sum, int &bin)
+__device__ __forceinline__ void op_ld_pair(unsigned addr, int &sum, int &bin)
 {
     asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(sum), "=r"(bin) : "r"(addr) : "memory");
 }
@@ -836,10 +852,9 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
                    int64_t out_cap, int do_fill, unsigned long long *__restrict__ status, int *__restrict__ ticket,
                    int *__restrict__ counts_actual, int *__restrict__ flags)
 {
-    __shared__ int2 s_ring_all[OP_WARPS][OP_RING];
+    __shared__ int2 s_buf_all[OP_WARPS][OP_CAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring_all[wid][0]);
-    constexpr unsigned RB = OP_MASK * 8u; // byte mask of a ring offset
+    const unsigned buf = (unsigned)__cvta_generic_to_shared(&s_buf_all[wid][0]);
     bool inexact = false, irregular = false;
 
     for (;;) {
@@ -856,6 +871,7 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
             for (int64_t t0 = tb; t0 < e1; t0 += OP_TILE) {
                 int g[OP_EPL];
                 uint32_t w[OP_EPL];
+                if (lane < 8 && t0 + OP_TILE + 32 * lane < e1) op_prefetch_l2(rowidx + t0 + OP_TILE + 32 * lane);
                 op_tile_words(rowidx, gmap, t0 + OP_EPL * lane, e0, e1, !do_fill, g, w);
                 int before = __shfl_up_sync(CS_FULL, g[OP_EPL - 1], 1);
                 if (lane == 0) before = carryG;
@@ -868,7 +884,7 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
                 }
                 irregular |= bad;
                 carryG = __shfl_sync(CS_FULL, g[OP_EPL - 1], 31);
-                const int incl = warp_incl_max(lmax, lane);
+                const int incl = warp_incl_max_nt(lmax);
                 int m = __shfl_up_sync(CS_FULL, incl, 1);
                 if (lane == 0) m = 0;
                 m = max(m, carryM);
@@ -895,7 +911,7 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
                 if (idx >= 0) {
                     sv = op_ld_status(status + idx);
                     while ((sv >> 62) == 0ull) {
-                        __nanosleep(100);
+                        __nanosleep(200);
                         sv = op_ld_status(status + idx);
                     }
                 }
@@ -920,14 +936,49 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
         }
         // ---------------- fill
         bool have_excl = false, skip = false;
-        int32_t *__restrict__ ocol_i = out_rowidx;
+        int32_t *__restrict__ ocol_i = out_rowidx; // (advance with every write-out)
         double *__restrict__ ocol_x = out_x;
-        int carryM = 0, carryC = 0, carryF = 0, flushed = 0, nz = 0;
+        int carryM = 0, carryF = 0, held = 0, written = 0, nz = 0;
         unsigned orbits = 0;
+        // ranks [0, nfin) of the buffer go to the output; the rest moves to the front
+        auto write_out = [&](int nfin) {
+            if (!have_excl) {
+                look_back();
+                have_excl = true;
+                if (excl + cnt > out_cap) { // caller's buffers too small: report, write nothing
+                    if (lane == 0) flags[FLAG_CAP] = 1;
+                    skip = true;
+                    return;
+                }
+                ocol_i += excl;
+                ocol_x += excl;
+            }
+            for (int r = lane; r < nfin; r += 32) {
+                int sv, bv;
+                op_ld_pair(buf + 8u * r, sv, bv);
+                __stcs(ocol_x + r, (double)sv);
+                __stcs(ocol_i + r, bv);
+                nz += (sv != 0) ? 1 : 0;
+            }
+            ocol_i += nfin;
+            ocol_x += nfin;
+            written += nfin;
+            const int rem = held - nfin; // (<= OP_MAXNH)
+            __syncwarp();
+            for (int r0 = 0; r0 < rem; r0 += 32) {
+                int sv = 0, bv = 0;
+                if (r0 + lane < rem) op_ld_pair(buf + 8u * (nfin + r0 + lane), sv, bv);
+                __syncwarp();
+                if (r0 + lane < rem) op_st_pair(buf + 8u * (r0 + lane), sv, bv);
+            }
+            __syncwarp();
+            held = rem;
+        };
         for (int64_t t0 = tb; t0 < e1 && !skip; t0 += OP_TILE) {
             const int64_t gb = t0 + OP_EPL * lane;
             int g[OP_EPL], iv[OP_EPL];
             uint32_t w[OP_EPL];
+            if (lane < 16 && t0 + OP_TILE + 16 * lane < e1) op_prefetch_l2(x + t0 + OP_TILE + 16 * lane);
             op_tile_words(rowidx, gmap, gb, e0, e1, true, g, w);
             if (gb >= e0 && gb + OP_EPL <= e1) {
                 double v[OP_EPL];
@@ -951,104 +1002,86 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
                     }
                 }
             }
-            // a tile goes through the ring in one round unless its new bins do not fit (then lane by lane)
-            for (;;) {
-                int lmax = 0, lf = 0;
+            // interval ends, first bins, the prefix max M in front of this lane's entries
+            int lmax = 0, lf = 0;
+#pragma unroll
+            for (int i = 0; i < OP_EPL; i++) {
+                lmax = max(lmax, (int)(w[i] & 0xFFFFF) + (int)(w[i] >> 20));
+                lf = max(lf, (int)(w[i] & 0xFFFFF)); // (starts do not decrease: the last one with a bin is the largest)
+            }
+            const int incl = warp_incl_max_nt(lmax);
+            int m0 = __shfl_up_sync(CS_FULL, incl, 1);
+            if (lane == 0) m0 = 0;
+            m0 = max(m0, carryM);
+            int ln = 0; // bins this lane's entries open
+            {
+                int m = m0;
 #pragma unroll
                 for (int i = 0; i < OP_EPL; i++) {
-                    lmax = max(lmax, (int)(w[i] & 0xFFFFF) + (int)(w[i] >> 20));
-                    lf = max(lf, (int)(w[i] & 0xFFFFF)); // (starts do not decrease: the last one with a bin is the largest)
+                    const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
+                    ln += max(0, e - max(f, m));
+                    m = max(m, e);
                 }
-                const int incl = warp_incl_max(lmax, lane);
-                int m0 = __shfl_up_sync(CS_FULL, incl, 1);
-                if (lane == 0) m0 = 0;
-                m0 = max(m0, carryM);
-                int ln = 0;
-                {
-                    int m = m0;
-#pragma unroll
-                    for (int i = 0; i < OP_EPL; i++) {
-                        const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
-                        ln += max(0, e - max(f, m));
-                        m = max(m, e);
-                    }
-                }
-                const int cincl = warp_incl_sum(ln, lane);
-                const int room = OP_RING - (carryC - flushed);
-                const int hi = __popc(__ballot_sync(CS_FULL, cincl <= room)); // lanes [0, hi) fit (cincl is non-decreasing)
-                const bool act = lane < hi;
-                unsigned oi[OP_EPL]; // old part of entry i: ring offset (bytes) of its first bin | number of bins << 16
-                {
-                    int m = m0, cr = act ? carryC + cincl - ln : 0;
-#pragma unroll
-                    for (int i = 0; i < OP_EPL; i++) {
-                        const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
-                        const int s = max(f, m);
-                        const int nn = act ? e - s : 0, old = act ? min(e, m) - f : 0;
-                        oi[i] = old > 0 ? ((((unsigned)(cr - m + f)) << 3) & RB) | ((unsigned)old << 16) : 0u;
-                        op_ring_store_if(nn, 0, ring + (((unsigned)cr << 3) & RB), iv[i], s);
-                        op_ring_store_if(nn, 1, ring + (((unsigned)(cr + 1) << 3) & RB), iv[i], s + 1);
-                        if (nn > 2) {
-#pragma unroll 1
-                            for (int k = 2; k < nn; k++)
-                                op_ring_store_if(1, 0, ring + (((unsigned)(cr + k) << 3) & RB), iv[i], s + k);
-                        }
-                        cr += max(nn, 0);
-                        m = max(m, e);
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < OP_EPL; i++) {
-                    if (oi[i]) {
-                        const unsigned base = oi[i] & 0xFFFFu;
-                        const int n = (int)(oi[i] >> 16);
-#pragma unroll 1
-                        for (int k = 0; k < n; k++) op_ring_add(ring + ((base + 8u * k) & RB), iv[i]);
-                    }
-                }
-                __syncwarp();
-                const int src = (hi > 0 ? hi : 1) - 1;
-                carryM = max(carryM, __shfl_sync(CS_FULL, incl, src));
-                carryC += __shfl_sync(CS_FULL, cincl, src);
-                carryF = max(carryF, __reduce_max_sync(CS_FULL, act ? lf : 0));
-                if (carryC > cnt) { // (cannot happen for ascending rows: the count pass saw the same entries)
+            }
+            const int cincl = warp_incl_sum(ln, lane);
+            const int need = __shfl_sync(CS_FULL, cincl, 31);
+            if (held + need > OP_CAP) { // make room: everything no later entry can touch goes out
+                write_out(held - max(0, carryM - carryF));
+                if (skip) break;
+                if (held + need > OP_CAP) { // (a tile of very wide genes: not this kernel's case)
                     irregular = true;
                     skip = true;
                     break;
                 }
-                // every rank below the bins the last start can still reach is final: flush them
-                const bool done = hi == 32 && t0 + OP_TILE >= e1;
-                const int frontier = done ? carryC : carryC - max(0, carryM - carryF);
-                if (frontier > flushed) {
-                    if (!have_excl) {
-                        look_back();
-                        have_excl = true;
-                        if (excl + cnt > out_cap) { // caller's buffers too small: report, write nothing
-                            if (lane == 0) flags[FLAG_CAP] = 1;
-                            skip = true;
-                            break;
-                        }
-                        ocol_i = out_rowidx + excl;
-                        ocol_x = out_x + excl;
-                    }
-                    for (int r = flushed + lane; r < frontier; r += 32) {
-                        int sv, bv;
-                        op_ring_load(ring + (((unsigned)r << 3) & RB), sv, bv);
-                        __stcs(ocol_x + r, (double)sv);
-                        __stcs(ocol_i + r, bv);
-                        nz += (sv != 0) ? 1 : 0;
-                    }
-                    flushed = frontier;
-                    __syncwarp();
-                }
-                if (hi == 32) break;
-                if (act) { // (these lanes are done: neutral from here on)
+            }
+            // placement: new bins are stores at the lane's running address, the old part of an entry
+            // (bins an earlier entry opened: ranks just below the running one) is remembered
+            unsigned oa[OP_EPL];
+            bool multi = false;
+            {
+                int m = m0;
+                unsigned addr = buf + 8u * (unsigned)(held + cincl - ln);
 #pragma unroll
-                    for (int i = 0; i < OP_EPL; i++) w[i] = 0u;
+                for (int i = 0; i < OP_EPL; i++) {
+                    const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
+                    const int s = max(f, m), nn = e - s, old = min(e, m) - f;
+                    op_st_pair_if(nn, 0, addr, iv[i], s);
+                    op_st_pair_if(nn, 1, addr + 8u, iv[i], s + 1);
+                    if (nn > 2) {
+#pragma unroll 1
+                        for (int k = 2; k < nn; k++) op_st_pair(addr + 8u * k, iv[i], s + k);
+                    }
+                    oa[i] = old > 0 ? addr - 8u * (unsigned)(m - f) : 0u;
+                    multi |= old > 1;
+                    addr += 8u * (unsigned)max(nn, 0);
+                    m = max(m, e);
                 }
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < OP_EPL; i++)
+                if (oa[i]) op_red_add(oa[i], iv[i]);
+            if (__any_sync(CS_FULL, multi)) { // entries that reach over two or more old bins (rare)
+                int m = m0;
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) {
+                    const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
+                    const int old = min(e, m) - f;
+#pragma unroll 1
+                    for (int k = 1; k < old; k++) op_red_add(oa[i] + 8u * k, iv[i]);
+                    m = max(m, e);
+                }
+            }
+            __syncwarp();
+            held += need;
+            carryM = max(carryM, __shfl_sync(CS_FULL, incl, 31));
+            carryF = max(carryF, (int)__reduce_max_sync(CS_FULL, (unsigned)lf));
+            if (written + held > cnt) { // (cannot happen for ascending rows: the count pass saw the same entries)
+                irregular = true;
+                skip = true;
+            }
         }
+        if (!skip) write_out(held);
         if (!have_excl) look_back(); // (empty columns, or columns given up on)
         nz = (int)__reduce_add_sync(CS_FULL, (unsigned)nz);
         orbits = __reduce_or_sync(CS_FULL, orbits);
@@ -1405,8 +1438,19 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
 }
 
 // ------------------------------------------------------- host (R-layout) form
+// the position of some row index outside [0, G) (-1 as an unsigned maximum when there is none)
+__global__ void validate_rows_kernel(int64_t nnz, const int32_t *__restrict__ rowidx, int G, long long *__restrict__ bad)
+{
+    long long mine = -1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        const int g = rowidx[e];
+        if ((g < 0 || g >= G) && mine < 0) mine = e;
+    }
+    if (mine >= 0) atomicMin(reinterpret_cast<unsigned long long *>(bad), (unsigned long long)mine);
+}
+
 struct cs_bin_job {
-    int N = 0;
+    int N = 0, B = 0;
     int64_t nnz = 0;
     DevBuf<int64_t> out_colptr;
     DevBuf<int32_t> out_rowidx;
@@ -1423,8 +1467,6 @@ extern "C" int cs_bin_counts_begin(int G, int N, int B, const int32_t *colptr, c
     CS_REQUIRE(colptr[0] == 0, "cs_bin_counts_begin: colptr[0] must be 0");
     const int64_t nnz = colptr[N];
     for (int c = 0; c < N; c++) CS_REQUIRE(colptr[c] <= colptr[c + 1], "colptr not monotone at column %d", c);
-    for (int64_t e = 0; e < nnz; e++)
-        CS_REQUIRE(rowidx[e] >= 0 && rowidx[e] < G, "rowidx[%lld]=%d outside [0,%d)", (long long)e, rowidx[e], G);
     cs_bin_plan *plan = nullptr;
     int rc = cs_bin_plan_create(G, B, map_ptr, map_bin, &plan);
     if (rc) return rc;
@@ -1443,14 +1485,22 @@ extern "C" int cs_bin_counts_begin(int G, int N, int B, const int32_t *colptr, c
         ~JobGuard() { delete j; }
     } jguard{job};
     job->N = N;
+    job->B = B;
     CS_CUDA(d_colptr.alloc((size_t)N + 1));
     CS_CUDA(d_rowidx.alloc((size_t)nnz));
     CS_CUDA(d_x.alloc((size_t)nnz));
     CS_CUDA(job->out_colptr.alloc((size_t)N + 1));
     CS_CUDA(cudaMemcpy(d_colptr.p, cp64.data(), sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice));
     if (nnz) {
-        CS_CUDA(cudaMemcpy(d_rowidx.p, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
-        CS_CUDA(cudaMemcpy(d_x.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+        if ((rc = cs_h2d_staged(d_rowidx.p, rowidx, sizeof(int32_t) * (size_t)nnz))) return rc;
+        if ((rc = cs_h2d_staged(d_x.p, x, sizeof(double) * (size_t)nnz))) return rc;
+        // row indices are validated on the device (a host loop over them costs as much as the copy)
+        long long *d_bad = reinterpret_cast<long long *>(job->out_colptr.p); // (free until the count runs)
+        CS_CUDA(cudaMemset(d_bad, 0xFF, sizeof(long long)));
+        validate_rows_kernel<<<cs_num_sms() * 8, 256>>>(nnz, d_rowidx.p, G, d_bad);
+        long long bad = -1;
+        CS_CUDA(cudaMemcpy(&bad, d_bad, sizeof(long long), cudaMemcpyDeviceToHost));
+        CS_REQUIRE(bad < 0, "rowidx[%lld]=%d outside [0,%d)", bad, rowidx[bad], G);
     }
     int64_t need = 0;
     rc = cs_bin_counts_dev(plan, N, d_colptr.p, d_rowidx.p, d_x.p, job->out_colptr.p, nullptr, nullptr, 0, &need, nullptr);
@@ -1487,10 +1537,28 @@ extern "C" int cs_bin_counts_fetch(cs_bin_job *job, int32_t *out_colptr, int32_t
     for (size_t c = 0; c < cp64.size(); c++) out_colptr[c] = (int32_t)cp64[c];
     if (job->nnz) {
         CS_REQUIRE(out_rowidx && out_x, "cs_bin_counts_fetch: NULL output slots");
-        CS_CUDA(cudaMemcpy(out_rowidx, job->out_rowidx.p, sizeof(int32_t) * (size_t)job->nnz, cudaMemcpyDeviceToHost));
-        CS_CUDA(cudaMemcpy(out_x, job->out_x.p, sizeof(double) * (size_t)job->nnz, cudaMemcpyDeviceToHost));
+        int rc;
+        if ((rc = cs_d2h_staged(out_rowidx, job->out_rowidx.p, sizeof(int32_t) * (size_t)job->nnz))) return rc;
+        if ((rc = cs_d2h_staged(out_x, job->out_x.p, sizeof(double) * (size_t)job->nnz))) return rc;
     }
     return CS_OK;
 }
 
 extern "C" void cs_bin_counts_free(cs_bin_job *job) { delete job; }
+
+// bin x cluster pooling of a job's bin x cell counts where they lie on the device (the job stays
+// valid): out is B x K column-major, see cs_rowsum_by_label
+extern "C" int cs_bin_job_rowsum_by_label(cs_bin_job *job, const int *label, int K, double *out)
+{
+    CS_REQUIRE(job && label && out && K >= 1, "cs_bin_job_rowsum_by_label: bad arguments");
+    DevBuf<int> d_l;
+    DevBuf<double> d_o;
+    CS_CUDA(d_l.alloc((size_t)job->N));
+    CS_CUDA(d_o.alloc((size_t)job->B * K));
+    if (job->N) CS_CUDA(cudaMemcpy(d_l.p, label, sizeof(int) * (size_t)job->N, cudaMemcpyHostToDevice));
+    int rc = cs_rowsum_by_label_dev(job->B, job->N, job->out_colptr.p, job->out_rowidx.p, job->out_x.p, d_l.p, K,
+                                    d_o.p, nullptr);
+    if (rc) return rc;
+    CS_CUDA(cudaMemcpy(out, d_o.p, sizeof(double) * (size_t)job->B * K, cudaMemcpyDeviceToHost));
+    return CS_OK;
+}

@@ -59,6 +59,11 @@ struct DevBuf {
 
 int cs_num_sms();
 
+// pageable host memory <-> device through pinned slots and a few copy threads (cs_stage.cu);
+// both return after the copy has completed
+int cs_h2d_staged(void *d_dst, const void *h_src, size_t bytes);
+int cs_d2h_staged(void *h_dst, const void *d_src, size_t bytes);
+
 // -------------------------------------------------------------- device side
 #define CS_LN_SQRT_2PI 0.918938533204672741780329736406
 #define CS_FULL 0xffffffffu

@@ -36,9 +36,6 @@ struct cs_chain {
     DevBuf<uint32_t> mt;
     DevBuf<ChainScal> scal;
     DevBuf<int> zt;                 // cs_chain_fetch: Zall transposed into R's layout (kept between calls)
-    void *pin[2] = {nullptr, nullptr}; // pinned staging for the device-to-host copies (two halves in flight)
-    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
-    static constexpr size_t kPinBytes = 16u << 20;
     // timing of the last cs_chain_run: whole run, and (flags bit 1) per-sweep kernel groups
     cudaEvent_t run_ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> sweep_ev;
@@ -48,40 +45,9 @@ struct cs_chain {
         for (auto e : sweep_ev) cudaEventDestroy(e);
         for (auto e : run_ev)
             if (e) cudaEventDestroy(e);
-        for (auto e : pin_ev)
-            if (e) cudaEventDestroy(e);
-        for (auto p : pin)
-            if (p) cudaFreeHost(p);
         if (st) cudaStreamDestroy(st);
     }
 };
-
-// device -> pageable host memory through two pinned staging buffers: the copy of one piece
-// overlaps the host-side copy-out of the one before (cudaMemcpy into pageable memory stages
-// through one small driver buffer and serialises both)
-static int d2h_staged(cs_chain *c, void *dst, const void *dsrc, size_t bytes)
-{
-    if (bytes == 0) return CS_OK;
-    for (int b = 0; b < 2; b++) {
-        if (!c->pin[b]) CS_CUDA(cudaHostAlloc(&c->pin[b], cs_chain::kPinBytes, cudaHostAllocDefault));
-        if (!c->pin_ev[b]) CS_CUDA(cudaEventCreateWithFlags(&c->pin_ev[b], cudaEventDisableTiming));
-    }
-    const size_t piece = cs_chain::kPinBytes;
-    const size_t np = (bytes + piece - 1) / piece;
-    for (size_t i = 0; i <= np; i++) {
-        if (i < np) {
-            const size_t off = i * piece, len = bytes - off < piece ? bytes - off : piece;
-            CS_CUDA(cudaMemcpyAsync(c->pin[i & 1], static_cast<const char *>(dsrc) + off, len, cudaMemcpyDeviceToHost, c->st));
-            CS_CUDA(cudaEventRecord(c->pin_ev[i & 1], c->st));
-        }
-        if (i > 0) {
-            const size_t off = (i - 1) * piece, len = bytes - off < piece ? bytes - off : piece;
-            CS_CUDA(cudaEventSynchronize(c->pin_ev[(i - 1) & 1]));
-            memcpy(static_cast<char *>(dst) + off, c->pin[(i - 1) & 1], len);
-        }
-    }
-    return CS_OK;
-}
 
 static const int kDefaultKcapPhilox = 256, kDefaultLcapR = 4096;
 static thread_local cs_chain *g_cached = nullptr; // see cs_ncrp_gibbs
@@ -250,8 +216,10 @@ extern "C" int cs_chain_init(cs_chain *c, const double *X, int K0, const double 
     c->flags = flags;
     c->sweeps_done = 0;
     // X: column-major N x R (== row-major R x N) -> cell-major
-    CS_CUDA(cudaMemcpyAsync(c->Xc.p, X, sizeof(double) * (size_t)N * R, cudaMemcpyHostToDevice, st));
-    int rc = cs_transpose<double>(R, N, c->Xc.p, c->X.p, st);
+    CS_CUDA(cudaStreamSynchronize(st));
+    int rc = cs_h2d_staged(c->Xc.p, X, sizeof(double) * (size_t)N * R);
+    if (rc) return rc;
+    rc = cs_transpose<double>(R, N, c->Xc.p, c->X.p, st);
     if (rc) return rc;
     // U0: column-major K0 x R -> rows (Philox: the non-NA rows, in label order, one slot each)
     const int nrows_up = ph ? nrows_live : K0;
@@ -450,7 +418,8 @@ extern "C" int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double 
         CS_CUDA(c->zt.reserve((size_t)c->niter_cap * N));
         rc = cs_transpose<int>(T, N, c->Zall.p, c->zt.p, c->st);
         if (rc) return rc;
-        if ((rc = d2h_staged(c, Zall, c->zt.p, sizeof(int) * (size_t)T * N))) return rc;
+        CS_CUDA(cudaStreamSynchronize(c->st));
+        if ((rc = cs_d2h_staged(Zall, c->zt.p, sizeof(int) * (size_t)T * N))) return rc;
     }
     // sigma_all: device T x R row-major == column-major R x T: column t = sweep t
     if (sigma_all) CS_CUDA(cudaMemcpy(sigma_all, c->sigma_all.p, sizeof(double) * (size_t)T * R, cudaMemcpyDeviceToHost));
@@ -466,7 +435,7 @@ extern "C" int cs_chain_fetch(cs_chain *c, int *Zall, double *sigma_all, double 
             return CS_ERR_UCAP;
         }
         if (u_labels && need) CS_CUDA(cudaMemcpy(u_labels, c->u_labels.p, sizeof(int) * (size_t)need, cudaMemcpyDeviceToHost));
-        if (u_rows && need && (rc = d2h_staged(c, u_rows, c->u_rows.p, sizeof(double) * (size_t)need * R))) return rc;
+        if (u_rows && need && (rc = cs_d2h_staged(u_rows, c->u_rows.p, sizeof(double) * (size_t)need * R))) return rc;
     }
     return CS_OK;
 }

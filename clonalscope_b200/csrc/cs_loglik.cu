@@ -265,7 +265,7 @@ extern "C" int cs_loglik_matrix(int N, int R, int K, const double *X, const doub
     CS_CUDA(dS.alloc(R));
     CS_CUDA(dL.alloc(nl));
     CS_CUDA(dLc.alloc(nl));
-    CS_CUDA(cudaMemcpy(dXc.p, X, sizeof(double) * nx, cudaMemcpyHostToDevice));
+    if (int rc0 = cs_h2d_staged(dXc.p, X, sizeof(double) * nx)) return rc0;
     CS_CUDA(cudaMemcpy(dUc.p, U, sizeof(double) * nu, cudaMemcpyHostToDevice));
     CS_CUDA(cudaMemcpy(dS.p, sigma, sizeof(double) * R, cudaMemcpyHostToDevice));
     int rc;
@@ -275,7 +275,8 @@ extern "C" int cs_loglik_matrix(int N, int R, int K, const double *X, const doub
     if ((rc = cs_loglik_matrix_dev(N, R, K, dX.p, dU.p, dS.p, dL.p, nullptr))) return rc;
     // row-major N x K -> column-major N x K (== row-major K x N)
     if ((rc = cs_transpose<double>(N, K, dL.p, dLc.p, 0))) return rc;
-    CS_CUDA(cudaMemcpy(LL, dLc.p, sizeof(double) * nl, cudaMemcpyDeviceToHost));
+    CS_CUDA(cudaDeviceSynchronize());
+    if ((rc = cs_d2h_staged(LL, dLc.p, sizeof(double) * nl))) return rc;
     return CS_OK;
 }
 
@@ -298,7 +299,7 @@ extern "C" int cs_majority_vote(int T, int N, const int *Zall, int *zmaj)
     CS_CUDA(dZ.alloc(n));
     CS_CUDA(dZt.alloc(n));
     CS_CUDA(dO.alloc(N));
-    CS_CUDA(cudaMemcpy(dZ.p, Zall, sizeof(int) * n, cudaMemcpyHostToDevice));
+    if (int rc0 = cs_h2d_staged(dZ.p, Zall, sizeof(int) * n)) return rc0;
     // T x N column-major == row-major N x T; transpose to sweep-major (T x N row-major)
     // so that consecutive threads (cells) read consecutive addresses
     int rc = cs_transpose<int>(N, T, dZ.p, dZt.p, 0);

@@ -102,8 +102,8 @@ extern "C" int cs_gene_moments(int G, int64_t nnz, const int32_t *rowidx, const 
     CS_CUDA(cudaMemset(d_s.p, 0, sizeof(double) * (size_t)(G > 0 ? G : 1)));
     CS_CUDA(cudaMemset(d_q.p, 0, sizeof(double) * (size_t)(G > 0 ? G : 1)));
     if (nnz) {
-        CS_CUDA(cudaMemcpy(d_i.p, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
-        CS_CUDA(cudaMemcpy(d_x.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+        if (int rc = cs_h2d_staged(d_i.p, rowidx, sizeof(int32_t) * (size_t)nnz)) return rc;
+        if (int rc = cs_h2d_staged(d_x.p, x, sizeof(double) * (size_t)nnz)) return rc;
         gene_moments_kernel<<<cs_num_sms() * 8, 256>>>(nnz, d_i.p, d_x.p, d_s.p, d_q.p);
         CS_CUDA(cudaGetLastError());
     }
@@ -169,7 +169,7 @@ extern "C" int cs_cluster_stats(int N, int R, int K, const double *X, const int 
     CS_CUDA(dN.alloc(K));
     int rc;
     if (N) {
-        CS_CUDA(cudaMemcpy(dXc.p, X, sizeof(double) * nx, cudaMemcpyHostToDevice));
+        if (int rc0 = cs_h2d_staged(dXc.p, X, sizeof(double) * nx)) return rc0;
         CS_CUDA(cudaMemcpy(dZ.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
         if ((rc = cs_transpose<double>(R, N, dXc.p, dX.p, 0))) return rc; // column-major N x R -> cell-major
     }
@@ -201,7 +201,7 @@ extern "C" int cs_sigma_stats(int N, int R, int K, const double *X, const int *Z
     CS_CUDA(dC.alloc(R));
     int rc;
     if (N) {
-        CS_CUDA(cudaMemcpy(dXc.p, X, sizeof(double) * nx, cudaMemcpyHostToDevice));
+        if (int rc0 = cs_h2d_staged(dXc.p, X, sizeof(double) * nx)) return rc0;
         CS_CUDA(cudaMemcpy(dZ.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
         if ((rc = cs_transpose<double>(R, N, dXc.p, dX.p, 0))) return rc;
     }

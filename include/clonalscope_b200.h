@@ -227,6 +227,30 @@ int cs_sigma_stats(int N, int R, int K, const double *X, const int *Z, const dou
  * ---------------------------------------------------------------------- */
 int cs_gene_moments(int G, int64_t nnz, const int32_t *rowidx, const double *x, double *sum, double *sumsq);
 
+/* ------------------------------------------------------------------------
+ * the caller side of the gene -> bin aggregation (CreateSegtableNoWGS + Segmentation_bulk)
+ *
+ * cs_rowsum_by_label: bin x cluster pooling of a bin x cell dgCMatrix (slots as above, B bins,
+ *   N cells): out[b + k*B] = sum over the cells with label[c] == k of counts[b, c]; labels
+ *   outside [0, K) are skipped.  Replaces bin_by_cluster[, k] = rowSums(bin_mtx[, Zest == k])
+ *   of R/CreateSegtableNoWGS.R:62-69 and ref_counts = rowSums(bin_mtx[, normal]) of :77.
+ *   _dev: device pointers (int64 colptr), e.g. the output of cs_bin_counts_dev as it lies.
+ * cs_segment_hmm: nseq sequences stored back to back (sequence s = val[off[s] .. off[s+1])), one
+ *   per chromosome and pooled profile: centred running mean of width nmean with shrinking ends
+ *   (caTools::runmean(x, k), R/Segmentation_bulk.R:152) and the Viterbi path of the 4-state
+ *   Gaussian HMM (HiddenMarkov::dthmm + Viterbi, :154-166; means / sds per state, initial
+ *   distribution delta, transition matrix Pi row-major).  state[i] is 0-based.  Host pointers.
+ * ---------------------------------------------------------------------- */
+int cs_rowsum_by_label(int B, int N, const int32_t *colptr, const int32_t *rowidx, const double *x,
+                       const int *label, int K, double *out);
+int cs_rowsum_by_label_dev(int B, int N, const int64_t *d_colptr, const int32_t *d_rowidx, const double *d_x,
+                           const int *d_label, int K, double *d_out, void *stream);
+/* the same pooling on the device-resident result of cs_bin_counts_begin (before or instead of
+ * cs_bin_counts_fetch; the job stays valid and is released by fetch or free as before) */
+int cs_bin_job_rowsum_by_label(cs_bin_job *job, const int *label, int K, double *out);
+int cs_segment_hmm(int nseq, const int64_t *off, const double *val, int nmean, const double *means,
+                   const double *sds, const double *delta, const double *Pi, double *smooth, int *state);
+
 #ifdef __cplusplus
 }
 #endif

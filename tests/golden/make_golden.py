@@ -122,8 +122,31 @@ def geometry_fixture():
     print("geometry", len(chrom), "bins", len(g["V1"].data), "genes", os.path.getsize(fn) // 1024, "KiB")
 
 
+def segtable_fixture():
+    """CreateSegtableNoWGS on P5847: the per-cluster seg tables (Obj_all_cluster.rds, the input of the
+    breakpoint union) and the merged table the reference saved (seg_filtered_from_cluster.rds)."""
+    base = "samples/P5847/scRNA/noWGS_output"
+    obj = read_rds(os.path.join(REF, base, "Obj_all_cluster.rds"))
+    out = {"clusters": np.array(obj.names)}
+    for name in obj.names:
+        st = obj[name]["seg_table"]
+        for col in ("chr", "start", "end", "states", "length", "mean", "var", "chrr"):
+            out[f"{name}_{col}"] = np.array([str(v) for v in st[col].data])
+        # the table Segmentation_bulk saved on its own for the same cluster must be the same object
+        alone = read_rds(os.path.join(REF, base, "rds", f"seg_table_all_{name}_qt95_rm2_nmean500.rds"))
+        for col in ("chr", "start", "end", "states"):
+            assert [str(v) for v in alone[col].data] == list(out[f"{name}_{col}"]), (name, col)
+    merged = read_rds(os.path.join(REF, base, "seg_filtered_from_cluster.rds"))
+    nr, nc = (int(v) for v in merged.attrs["dim"].data)
+    out["seg_filtered"] = np.array([str(v) for v in merged.data]).reshape(nc, nr).T  # column-major
+    fn = os.path.join(HERE, "segtable_P5847.npz")
+    np.savez_compressed(fn, **out)
+    print("segtable", list(obj.names), out["seg_filtered"].shape, os.path.getsize(fn) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     geometry_fixture()
+    segtable_fixture()
     for k, v in SAMPLER.items():
         sampler_fixture(k, v)
     for k, v in DELTAS.items():

@@ -835,3 +835,156 @@ def test_assign_cluster_on_the_reference_chains(cs, name, mincell, labels):
     before = {int(l): int(c) for l, c in zip(zl, zc)}
     assert all(c >= before[int(l)] for l, c in zip(lab, cnt)) and cnt.sum() == g["X"].shape[0]
     assert set(np.unique(out["annot"])) <= {"T", "N"} and np.all(np.isfinite(out["sigmas_est"]))
+
+
+# ------------------------------------------------------------------ f3: CreateSegtableNoWGS + Segmentation_bulk
+def _planted_profile(rng, bins, depth=40.0):
+    """Pooled tumour / normal counts over the synthetic tiles with a few planted gains and losses."""
+    B = len(bins["chr"])
+    cn = np.ones(B)
+    for chrom, lo, hi, v in ((1, 0.10, 0.35, 1.5), (3, 0.5, 1.0, 0.5), (7, 0.0, 1.0, 1.5), (8, 0.2, 0.4, 1.8),
+                             (13, 0.3, 0.9, 0.5), (20, 0.0, 0.5, 1.5)):
+        idx = np.nonzero(bins["chr"] == chrom)[0]
+        cn[idx[int(lo * len(idx)):int(hi * len(idx))]] = v
+    base = rng.gamma(4.0, depth / 4.0, size=B)
+    base[rng.random(B) < 0.03] = 0.0                                    # dead bins: 0/0 and x/0
+    ref = rng.poisson(base).astype(np.float64)
+    raw = rng.poisson(base * cn).astype(np.float64)
+    return raw, ref
+
+
+@pytest.mark.gpu
+def test_segment_hmm_vs_oracle(cs, oracle):
+    """cs_segment_hmm (running mean + 4-state Viterbi, all sequences in one launch) against the
+    restated caTools::runmean / HiddenMarkov::Viterbi: same states everywhere, smoothed values to 1e-12."""
+    import segmentation as sg
+    from clonalscope_b200.segtable import segment_hmm
+    rng = np.random.default_rng(21)
+    means, sds, delta = [1.8, 1.5, 1.0, 0.5], [0.2] * 4, [0.1, 0.2, 0.5, 0.2]
+    t = 1e-6
+    Pi = [[1 - 3 * t if a == b else t for b in range(4)] for a in range(4)]
+    for nmean in (1, 4, 100, 500):
+        seqs = []
+        for n in (1, 2, 3, 9, 250, 1245, 640):
+            lv = np.repeat(rng.choice(means, size=n // 40 + 1), 40)[:n]
+            seqs.append(lv + rng.normal(0, 0.3, size=n))
+        sm, st = segment_hmm(seqs, nmean, means, sds, delta, Pi)
+        for x, a, b in zip(seqs, sm, st):
+            want = sg.runmean(x, nmean)
+            np.testing.assert_allclose(a, want, rtol=1e-12, atol=1e-14)
+            assert np.array_equal(b + 1, sg.viterbi(want, means, sds, delta, Pi))
+    # underflow is the reference's error, not a silent path
+    with pytest.raises(cs.ClonalscopeError, match="Underflow"):
+        segment_hmm([np.array([1.0, 1e200, 1.0])], 1, means, sds, delta, Pi)
+
+
+@pytest.mark.gpu
+def test_rowsum_by_label_exact(cs, oracle):
+    import scipy.sparse as sp
+    import segmentation as sg
+    from clonalscope_b200.segtable import rowsum_by_label
+    rng = np.random.default_rng(22)
+    B, N, K = 700, 900, 5
+    colptr, rowidx, x = _random_csc(rng, B, N, 0.2)
+    label = rng.integers(-1, K + 1, size=N)                            # -1 and K: cells outside every pool
+    got = rowsum_by_label(sp.csc_matrix((x, rowidx, colptr), shape=(B, N)), label, K)
+    assert np.array_equal(got, sg.pool_by_label(B, colptr, rowidx, x, label, K))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rm_extreme,assay,nmean", [(1, "WGS", 100), (2, "WGS", 500), (2, "scRNA", 30)])
+def test_segmentation_bulk_vs_oracle(cs, oracle, rm_extreme, assay, nmean):
+    """Segmentation_bulk through the host API against the line-by-line restatement: the same segments
+    (chr / start / end / states / length strings), means and variances to 1e-12."""
+    import segmentation as sg
+    from clonalscope_b200 import synth
+    from clonalscope_b200.api import NamedMatrix
+    from clonalscope_b200.segtable import Createobj_bulk, Segmentation_bulk
+    rng = np.random.default_rng(23 + rm_extreme)
+    bins, _ = synth.geometry(G=10)
+    raw, ref = _planted_profile(rng, bins)
+    names = [f"chr{c}-{s + 1}-{e}" for c, s, e in zip(bins["chr"], bins["start"], bins["end"])]
+    size = {f"chr{i + 1}": v for i, v in enumerate(synth.CHR_SIZES)}
+    obj = Createobj_bulk(NamedMatrix(raw.reshape(-1, 1), names, ["V1"]), NamedMatrix(ref.reshape(-1, 1), names, ["V1"]),
+                         size=size)
+    out = Segmentation_bulk(obj, hmm_states=(0.5, 1.5, 1.8), nmean=nmean, plot_seg=False, max_qt=0.95,
+                            rm_extreme=rm_extreme, adj=-0.5 if assay == "scRNA" else 0, assay=assay)
+    want, annot = sg.segmentation_bulk(list(bins["chr"]), list(bins["start"] + 1), list(bins["end"]), raw, ref,
+                                       {i + 1: float(v) for i, v in enumerate(synth.CHR_SIZES)}, nmean=nmean,
+                                       max_qt=0.95, rm_extreme=rm_extreme, adj=-0.5 if assay == "scRNA" else 0.0,
+                                       assay=assay)
+    got = out["seg_table"]
+    assert out["annot"] == annot
+    assert len(got["chr"]) > 22                                        # the planted events were found
+    for col in ("chr", "start", "end", "states", "length", "chrr"):
+        assert list(got[col]) == list(want[col]), col
+    for col in ("mean", "var"):
+        a = np.array([float(v) if v != "NA" else np.nan for v in got[col]])
+        b = np.array([float(v) if v != "NA" else np.nan for v in want[col]])
+        np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_create_segtable_nowgs_end_to_end(cs, oracle):
+    """CreateSegtableNoWGS from the gene x cell counts: device binning -> pooling on the device-resident
+    result -> HMM per cluster -> breakpoint union, against the restated chain on the same inputs."""
+    import scipy.sparse as sp
+    import segmentation as sg
+    from clonalscope_b200 import synth
+    from clonalscope_b200.segtable import CreateSegtableNoWGS
+    G, N = 3000, 600
+    rng = np.random.default_rng(29)
+    bins, genes = synth.geometry(G=G, seed=31)
+    B = len(bins["chr"])
+    colptr, rowidx, x = synth.counts_csc(N, G=G, seed=30, mean_genes=900)
+    z = rng.integers(1, 4, size=N)                                      # clusters 1..3, cluster 1 = the normal cells
+    # plant copy-number changes per cluster by scaling the counts of the genes of some chromosomes
+    gchr = genes["chr"][rowidx]
+    cell = np.repeat(np.arange(N), np.diff(colptr))
+    scale = np.ones(len(x))
+    scale[(z[cell] == 2) & (gchr == 5)] = 1.5
+    scale[(z[cell] == 2) & (gchr == 9)] = 0.5
+    scale[(z[cell] == 3) & (gchr == 5)] = 1.5
+    scale[(z[cell] == 3) & (gchr == 17)] = 1.8
+    x = np.maximum(1.0, np.rint(x * 4 * scale))
+    m = sp.csc_matrix((x, rowidx, colptr), shape=(G, N))
+    ids = [f"ENSG{i:08d}" for i in range(G)]
+    gtf = dict(V1=np.array([f"chr{c}" for c in genes["chr"]]), V3=np.array(["gene"] * G), V4=genes["start"],
+               V5=genes["end"], V9=np.array([f'gene_id {i}; gene_name x' for i in ids]))
+    features = np.array(ids, dtype=object).reshape(-1, 1)
+    barcodes = np.array([f"c{i}" for i in range(N)], dtype=object).reshape(-1, 1)
+    perm = rng.permutation(N)                                           # celltype0 lists the cells in another order
+    celltype0 = np.array([[f"c{i}", "normal" if z[i] == 1 else "tumor"] for i in perm], dtype=object)
+    bed = np.stack([np.array([f"chr{c}" for c in bins["chr"]], dtype=object), bins["start"].astype(object),
+                    bins["end"].astype(object)], axis=1)
+    size = np.array([[f"chr{i + 1}", v] for i, v in enumerate(synth.CHR_SIZES)], dtype=object)
+    kw = dict(hmm_states=(0.5, 1.5, 1.8), max_qt=0.95, nmean=40, rm_extreme=2, adj=0, plot_seg=False)
+    seg, obj_all, bbc = CreateSegtableNoWGS(mtx=m, barcodes=barcodes, features=features, Zest=z[perm], bin_bed=bed,
+                                            celltype0=celltype0, gtf=gtf, size=size, merge=True, return_obj=True, **kw)
+    # the restated chain
+    mp, mb = synth.geometry_map(bins, genes)
+    mm = m[:, perm].tocsc()
+    mm.sort_indices()
+    ocp, ori, ox = oracle.bin_counts(G, N, B, mm.indptr, mm.indices, mm.data, mp, mb)
+    pooled = sg.pool_by_label(B, ocp, ori, ox, z[perm] - 1, 3)
+    refsum = sg.pool_by_label(B, ocp, ori, ox, np.where(z[perm] == 1, 0, -1), 1)[:, 0]
+    assert np.array_equal(bbc.values, pooled) and bbc.colnames == ["C1", "C2", "C3"]
+    tabs = []
+    for k in range(3):
+        tab, _ = sg.segmentation_bulk(list(bins["chr"]), list(bins["start"] + 1), list(bins["end"]), pooled[:, k], refsum,
+                                      {i + 1: float(v) for i, v in enumerate(synth.CHR_SIZES)}, nmean=40, max_qt=0.95,
+                                      rm_extreme=2, adj=0.0)
+        for col in ("chr", "start", "end", "states", "length"):
+            assert list(obj_all[f"C{k + 1}"]["seg_table"][col]) == list(tab[col]), (k, col)
+        tabs.append(tab)
+    want = np.array(sg.merge_segments(tabs, merge=True))
+    assert np.array_equal(seg.astype(str), want)
+    assert len(want) > 22                                               # breakpoints from the planted events
+    # a precomputed bin matrix gives the same answer (the reference's bin_mtx= argument)
+    from clonalscope_b200.api import NamedMatrix
+    bm = sp.csc_matrix((ox, ori, ocp), shape=(B, N))
+    seg2 = CreateSegtableNoWGS(bin_mtx=NamedMatrix(bm, [""] * B, [""] * N), Zest=z[perm], bin_bed=bed, celltype0=celltype0,
+                               size=size, merge=True, **kw)
+    assert np.array_equal(seg2.astype(str), want)
+    with pytest.raises(ValueError, match="three HMM numeric states"):   # the reference's own default fails its check
+        CreateSegtableNoWGS(bin_mtx=bm, Zest=z[perm], bin_bed=bed, celltype0=celltype0, size=size)

@@ -260,3 +260,28 @@ def test_r_glue_compiles_against_the_c_abi_and_shims_match_it(tmp_path):
             assert nargs == registered[name], f"{f}: {name} called with {nargs} arguments, registered with {registered[name]}"
             used.add(name)
     assert used == set(registered), f"registered but never called from a shim: {set(registered) - used}"
+
+
+def test_merge_segment_tables_reproduces_shipped_seg_filtered():
+    """The product's host-side breakpoint union (segtable.merge_segment_tables, no device work) on the
+    reference's shipped per-cluster tables == its shipped seg_filtered_from_cluster.rds."""
+    from clonalscope_b200.segtable import merge_segment_tables
+    d = load_golden("segtable_P5847.npz")
+    tabs = [{c: [str(v) for v in d[f"{n}_{c}"]] for c in ("chr", "start", "end", "states")} for n in d["clusters"]]
+    out = merge_segment_tables(tabs, merge=True)
+    assert np.array_equal(out.astype(str), d["seg_filtered"])
+
+
+def test_segmentation_argument_errors():
+    from clonalscope_b200.segtable import Segmentation_bulk, Createobj_bulk
+    with pytest.raises(ValueError, match="valid Alleloscope object"):
+        Segmentation_bulk(None)
+    with pytest.raises(ValueError, match="two columns"):
+        Createobj_bulk(raw_counts=None, ref_counts=None, size=None)
+    from clonalscope_b200.api import NamedMatrix
+    names = [f"chr1-{1 + 200000 * i}-{200000 * (i + 1)}" for i in range(5)]
+    obj = Createobj_bulk(NamedMatrix(np.ones((5, 1)), names, ["V1"]), NamedMatrix(np.ones((5, 1)), names, ["V1"]),
+                         size={"chr1": 1000000, "chr2": 5})
+    assert obj["size"] == {"1": 1000000.0}
+    with pytest.raises(ValueError, match="three HMM numeric states"):
+        Segmentation_bulk(obj, hmm_states=(0.5, 1, 1.5, 2))

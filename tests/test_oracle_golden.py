@@ -125,3 +125,66 @@ def test_est_region_cov_restatement_small_case(oracle):
     assert name == "pt1_tumor_alphaallchr1_0_250" and cells == ["d", "a"]
     np.testing.assert_allclose(vals, want, rtol=1e-15)
     assert res["ngenes"] == [(name, 2)] and res["barcodes_normal"] == ["c", "b"]
+
+
+# ------------------------------------------------------------------ segmentation (f3)
+def test_breakpoint_union_reproduces_shipped_seg_filtered():
+    """CreateSegtableNoWGS.R:107-166 restated: the four per-cluster seg tables the reference ships for
+    P5847 (Obj_all_cluster.rds) -> its shipped seg_filtered_from_cluster.rds, string for string
+    (the tutorial ran with merge = T)."""
+    import segmentation as sg
+    d = load_golden("segtable_P5847.npz")
+    tabs = [{c: [str(v) for v in d[f"{n}_{c}"]] for c in ("chr", "start", "end", "states")} for n in d["clusters"]]
+    out = sg.merge_segments(tabs, merge=True)
+    assert np.array_equal(np.array(out), d["seg_filtered"])
+    assert len(sg.merge_segments(tabs, merge=False)) > len(out)
+
+
+def test_seg_table_number_strings_match_r():
+    """Every number the shipped seg tables hold as a string round-trips through the restated
+    as.character() (start/end/length up to 2.5e8 incl. '6e+05', states, 15-digit means)."""
+    import segmentation as sg
+    d = load_golden("segtable_P5847.npz")
+    n = 0
+    for name in d["clusters"]:
+        for col in ("start", "end", "states", "length", "mean", "var"):
+            for v in d[f"{name}_{col}"]:
+                if str(v) == "NA":
+                    continue
+                assert sg.r_chr(float(v)) == str(v), (name, col, v)
+                n += 1
+    assert n > 400
+
+
+def test_runmean_and_viterbi_restatements_against_definitions():
+    """caTools::runmean and HiddenMarkov::Viterbi are third-party: pin the restatements by their
+    definitions — window means with shrinking ends, and the arg-max path by exhaustive search."""
+    import itertools
+    import math
+    import segmentation as sg
+    rng = np.random.default_rng(11)
+    for n, k in ((1, 5), (7, 3), (10, 4), (23, 10), (40, 500), (12, 1)):
+        x = rng.normal(1, 0.3, size=n)
+        got = sg.runmean(x, k)
+        kk = min(k, n)
+        k2 = kk // 2
+        k1 = kk - k2 - 1
+        want = [x[max(0, i - k1):min(n, i + k2 + 1)].mean() for i in range(n)] if kk > 1 else list(x)
+        np.testing.assert_allclose(got, want, rtol=1e-13)
+    means, sds, delta = [1.8, 1.5, 1.0, 0.5], [0.2] * 4, [0.1, 0.2, 0.5, 0.2]
+    t = 0.01
+    Pi = [[1 - 3 * t if a == b else t for b in range(4)] for a in range(4)]
+    for trial in range(6):
+        x = rng.choice(means, size=7) + rng.normal(0, 0.25, size=7)
+        got = sg.viterbi(list(x), means, sds, delta, Pi)
+        best, arg = -math.inf, None
+        for path in itertools.product(range(4), repeat=7):
+            lp = math.log(delta[path[0]])
+            for i, a in enumerate(path):
+                z = (x[i] - means[a]) / sds[a]
+                lp += -(sg.LN_SQRT_2PI + 0.5 * z * z + math.log(sds[a]))
+                if i:
+                    lp += math.log(Pi[path[i - 1]][a])
+            if lp > best:
+                best, arg = lp, path
+        assert [a + 1 for a in arg] == got
