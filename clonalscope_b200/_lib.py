@@ -24,6 +24,7 @@ SYMBOLS = [
     "cs_majority_vote", "cs_majority_vote_dev",
     "cs_cluster_stats_dev", "cs_sigma_stats_dev", "cs_cluster_stats", "cs_sigma_stats", "cs_gene_moments",
     "cs_rowsum_by_label", "cs_rowsum_by_label_dev", "cs_bin_job_rowsum_by_label", "cs_segment_hmm",
+    "cs_csc_upload", "cs_csc_free", "cs_csc_gene_moments", "cs_csc_region_cov",
 ]
 
 
@@ -56,6 +57,7 @@ def lib():
         L = C.CDLL(_SO)
         L.cs_last_error.restype = C.c_char_p
         L.cs_bin_counts_free.restype = None
+        L.cs_csc_free.restype = None
         L.cs_bin_plan_destroy.restype = None
         L.cs_chain_destroy.restype = None
         L.cs_release_cached.restype = None

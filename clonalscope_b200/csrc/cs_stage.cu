@@ -122,6 +122,9 @@ int staged(void *dev_ptr, void *host_ptr, size_t bytes, bool to_device)
     if (bytes < kSmall) {
         CS_CUDA(cudaMemcpy(to_device ? dev_ptr : host_ptr, to_device ? host_ptr : dev_ptr, bytes,
                            to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+        // cudaMemcpy from pageable memory returns once the data is in the driver's staging buffer; the
+        // DMA runs on the legacy stream, which the callers' non-blocking streams do not wait for
+        if (to_device) CS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
         return CS_OK;
     }
     int dev = 0;

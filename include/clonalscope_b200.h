@@ -228,6 +228,30 @@ int cs_sigma_stats(int N, int R, int K, const double *X, const int *Z, const dou
 int cs_gene_moments(int G, int64_t nnz, const int32_t *rowidx, const double *x, double *sum, double *sumsq);
 
 /* ------------------------------------------------------------------------
+ * EstRegionCov on a device-resident copy of the gene x cell matrix (uploaded once)
+ *
+ * cs_csc_upload: dgCMatrix slots (G genes x N cells, 0-based) -> handle.  With col_sel != NULL the
+ *   handle holds the Nsel columns col_sel[0..Nsel) in that order (gathered on the device): the
+ *   mtx[, match(celltype0[, 1], barcodes[, 1])] of R/EstRegionCov.R:40.
+ * cs_csc_gene_moments: per-gene sum and sum of squares over the handle's cells (:42-48).
+ * cs_csc_region_cov: R/EstRegionCov.R:88-159 for S segments at once.  map_ptr[G+1] / map_seg: the
+ *   genes of every segment as a CSR map gene -> segments (findOverlaps on the host); lib_flag[G]:
+ *   1 for the genes whose counts make up the library size (:131-139); celltype[N]: 0 normal,
+ *   1 tumor, other = neither; include: 0 tumor, 1 control, 2 all.  Outputs, N x S column-major:
+ *   sums (may be NULL) = per-segment column sums; deltas = the coverage change of the cells the
+ *   segment reports (positive sum and of the included type), NaN elsewhere; alpha[N] = library
+ *   sizes; nsel[S] = cells with a positive sum.  The medians (:141,:153) are exact.
+ * ---------------------------------------------------------------------- */
+typedef struct cs_csc cs_csc;
+int cs_csc_upload(int G, int N, const int32_t *colptr, const int32_t *rowidx, const double *x, int Nsel,
+                  const int32_t *col_sel, cs_csc **out);
+void cs_csc_free(cs_csc *m);
+int cs_csc_gene_moments(cs_csc *m, double *sum, double *sumsq);
+int cs_csc_region_cov(cs_csc *m, int S, const int32_t *map_ptr, const int32_t *map_seg,
+                      const unsigned char *lib_flag, const int *celltype, int include, double *deltas,
+                      double *sums, double *alpha, int *nsel);
+
+/* ------------------------------------------------------------------------
  * the caller side of the gene -> bin aggregation (CreateSegtableNoWGS + Segmentation_bulk)
  *
  * cs_rowsum_by_label: bin x cluster pooling of a bin x cell dgCMatrix (slots as above, B bins,

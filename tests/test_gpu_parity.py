@@ -934,7 +934,7 @@ def test_create_segtable_nowgs_end_to_end(cs, oracle):
     from clonalscope_b200.segtable import CreateSegtableNoWGS
     G, N = 3000, 600
     rng = np.random.default_rng(29)
-    bins, genes = synth.geometry(G=G, seed=31)
+    bins, genes = synth.geometry(G=G, bin_size=2000000, seed=31)       # ~1450 tiles of 2 Mb: two genes per tile
     B = len(bins["chr"])
     colptr, rowidx, x = synth.counts_csc(N, G=G, seed=30, mean_genes=900)
     z = rng.integers(1, 4, size=N)                                      # clusters 1..3, cluster 1 = the normal cells
@@ -942,9 +942,10 @@ def test_create_segtable_nowgs_end_to_end(cs, oracle):
     gchr = genes["chr"][rowidx]
     cell = np.repeat(np.arange(N), np.diff(colptr))
     scale = np.ones(len(x))
-    scale[(z[cell] == 2) & (gchr == 5)] = 1.5
+    gpos = genes["start"][rowidx]
+    scale[(z[cell] == 2) & (gchr == 5) & (gpos > 90e6)] = 1.5
     scale[(z[cell] == 2) & (gchr == 9)] = 0.5
-    scale[(z[cell] == 3) & (gchr == 5)] = 1.5
+    scale[(z[cell] == 3) & (gchr == 5) & (gpos < 60e6)] = 1.5
     scale[(z[cell] == 3) & (gchr == 17)] = 1.8
     x = np.maximum(1.0, np.rint(x * 4 * scale))
     m = sp.csc_matrix((x, rowidx, colptr), shape=(G, N))
@@ -958,7 +959,7 @@ def test_create_segtable_nowgs_end_to_end(cs, oracle):
     bed = np.stack([np.array([f"chr{c}" for c in bins["chr"]], dtype=object), bins["start"].astype(object),
                     bins["end"].astype(object)], axis=1)
     size = np.array([[f"chr{i + 1}", v] for i, v in enumerate(synth.CHR_SIZES)], dtype=object)
-    kw = dict(hmm_states=(0.5, 1.5, 1.8), max_qt=0.95, nmean=40, rm_extreme=2, adj=0, plot_seg=False)
+    kw = dict(hmm_states=(0.5, 1.5, 1.8), max_qt=0.95, nmean=10, rm_extreme=2, adj=0, plot_seg=False)
     seg, obj_all, bbc = CreateSegtableNoWGS(mtx=m, barcodes=barcodes, features=features, Zest=z[perm], bin_bed=bed,
                                             celltype0=celltype0, gtf=gtf, size=size, merge=True, return_obj=True, **kw)
     # the restated chain
@@ -972,7 +973,7 @@ def test_create_segtable_nowgs_end_to_end(cs, oracle):
     tabs = []
     for k in range(3):
         tab, _ = sg.segmentation_bulk(list(bins["chr"]), list(bins["start"] + 1), list(bins["end"]), pooled[:, k], refsum,
-                                      {i + 1: float(v) for i, v in enumerate(synth.CHR_SIZES)}, nmean=40, max_qt=0.95,
+                                      {i + 1: float(v) for i, v in enumerate(synth.CHR_SIZES)}, nmean=10, max_qt=0.95,
                                       rm_extreme=2, adj=0.0)
         for col in ("chr", "start", "end", "states", "length"):
             assert list(obj_all[f"C{k + 1}"]["seg_table"][col]) == list(tab[col]), (k, col)
