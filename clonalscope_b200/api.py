@@ -714,6 +714,129 @@ def _label_stats(Xd, z, K, U=None):
     return sq.cpu().numpy()
 
 
+def _genotype_grid(maxcp=6):
+    """The (rho, theta) grid of R/genotype_neighbor.R:9-13 (rows in the reference's order)."""
+    rows = []
+    for ii in range(1, maxcp + 1):
+        rho = [0.5 * ii] * (ii + 1)
+        theta = [0.0] + [j / ii for j in range(1, ii + 1)]
+        rows.extend(zip(rho, theta))
+    return np.asarray(rows, dtype=np.float64)
+
+
+def _genotype_neighbor(cov, allele, maxcp=6):
+    """1-based index of the nearest grid state of every (cov, allele) pair (first minimum)."""
+    mu = _genotype_grid(maxcp)
+    d = np.sqrt((np.asarray(cov)[:, None] - mu[None, :, 0]) ** 2 + (np.asarray(allele)[:, None] - mu[None, :, 1]) ** 2)
+    return np.argmin(d, axis=1) + 1
+
+
+def _km_cutoff(stream, corrs):
+    """cutoff = 'km' (R/AssignCluster.R:191-194): kmeans(annot[annot != 100], 2) on R's stream."""
+    from .rrng import kmeans_hartigan_wong
+    vals = [float(v) for v in corrs if v != 100]
+    try:
+        cen = kmeans_hartigan_wong(stream, vals, 2)
+    except ValueError as e:
+        raise ClonalscopeError(_lib.CS_ERR_ARG, str(e)) from None
+    return float((np.longdouble(cen[0]) + np.longdouble(cen[1])) / 2)
+
+
+def _assign_cluster_allele(cluster_obj, mincell, cutoff, cna_states_WGS, rm_extreme, cap_corr):
+    """The allele branch (reference R/AssignCluster.R:216-414): as the coverage branch on both
+    modalities, orphans scored on coverage + allele, final means with the coverage capped at 3,
+    the genotype of every (cluster, region) from the nearest grid state."""
+    import torch
+    from .rrng import RStream, sample_int_prob_one
+    res, priors, data = cluster_obj["results"], cluster_obj["priors"], cluster_obj["data"]
+    Xc_v, _, colnames = _values(data["Xir_cov"])
+    Xa_v, _, _ = _values(data["Xir_allele"])
+    Xc = np.ascontiguousarray(Xc_v, dtype=np.float64)
+    Xa = np.ascontiguousarray(Xa_v, dtype=np.float64)
+    N, R = Xc.shape
+    Zall = np.asarray(res["Zall"], dtype=np.int32)
+    kt = int(np.asarray(res["Uall"][-1]).shape[0])
+    stream = RStream(100)                                                # :231
+    zmaj = majority_vote(Zall)                                           # :232
+    labs, cnts = np.unique(zmaj, return_counts=True)
+    ind_clusters = labs[cnts > mincell].astype(np.int64)                 # :236
+    orphan = ~np.isin(zmaj, ind_clusters)
+    ind_cell = np.nonzero(orphan)[0]
+    if len(ind_clusters) == 0:
+        raise ClonalscopeError("no cluster has more than mincell cells")
+    Xcd, Xad = torch.as_tensor(Xc, device="cuda"), torch.as_tensor(Xa, device="cuda")
+    z = np.where(orphan, 0, zmaj).astype(np.int32)
+    zkeep = z.copy()                                                     # labels of the cells outside ind_cell
+
+    def means(Xd, zz):                                                   # colMeans(na.rm = T), NA -> 0; counts per cluster
+        sx, c = _label_stats(Xd, zz, kt)
+        U = np.full((kt, R), np.nan)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mm = np.where(c > 0, sx / np.maximum(c, 1), 0.0)
+        U[ind_clusters - 1] = mm[ind_clusters - 1]
+        return U, c
+
+    def sigma(Xd, U, n):
+        # colSums((X[-ind_cell,] - U[Zest[-ind_cell],])^2): x[-integer(0), ] selects NO row in R, so
+        # without orphans the reference's sums are empty (sigma 0); reproduced as it stands
+        if len(ind_cell) == 0:
+            sq = np.zeros(R)
+        else:
+            zz = np.where(orphan, 0, z).astype(np.int32)
+            sq = _label_stats(Xd, zz, kt, np.where(np.isnan(U), 0.0, U))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.sqrt(1.0 / n * sq)
+
+    Usubc, cc = means(Xcd, z)                                            # :240-250
+    Usuba, ca = means(Xad, z)
+    ncov, nallele = cc[ind_clusters - 1].sum(axis=0), ca[ind_clusters - 1].sum(axis=0)      # :252-256
+    sig_c, sig_a = sigma(Xcd, Usubc, ncov), sigma(Xad, Usuba, nallele)  # :258-259
+    if len(ind_cell):                                                    # :265-275
+        LLo = loglik_matrix(Xc[ind_cell], Usubc[ind_clusters - 1], sig_c) + \
+            loglik_matrix(Xa[ind_cell], Usuba[ind_clusters - 1], sig_a)
+        for row, ii in zip(LLo, ind_cell):
+            P = np.full(kt, np.nan)
+            P[ind_clusters - 1] = row - np.max(row)
+            P[np.isnan(P)] = np.nanmin(P) - 100
+            z[ii] = sample_int_prob_one(stream, np.exp(P))
+    Xc2d = torch.clamp(Xcd, max=3.0)                                     # :281 pmin(x, 3) keeps NA
+    Usubc, _ = means(Xc2d, z)                                            # :282-294
+    Usuba, _ = means(Xad, z)
+    Usub = np.full((kt, R), np.nan)
+    for kk in ind_clusters:
+        Usub[kk - 1] = _genotype_neighbor(Usubc[kk - 1], Usuba[kk - 1], 6)
+    ncov, nallele = (~np.isnan(Xc)).sum(axis=0), (~np.isnan(Xa)).sum(axis=0)               # :302-303
+    sigmas_cov, sigmas_allele = sigma(Xcd, Usubc, ncov), sigma(Xad, Usuba, nallele)         # :305-306
+    pri = priors.get("cna_states_WGS") if cna_states_WGS is None else cna_states_WGS        # :311-315
+    pri = np.asarray(pri, dtype=np.float64).ravel()
+    if np.all(pri == 4):                                                 # :317-320
+        pri = np.full(R, 8.0)
+    priorsc = _genotype_grid(6)[pri.astype(np.int64) - 1, 0]             # :333
+    U2 = np.maximum(np.minimum(Usubc, cap_corr), 0.5)                    # :339-340
+    corrs = np.zeros(kt)
+    for k in range(kt):                                                  # :342-353
+        tmp = (U2[k] - 1) * (priorsc - 1)
+        tmp = np.sort(tmp[~np.isnan(tmp)])
+        if len(tmp) == 0:
+            continue                                                     # NA -> 0 (:357)
+        if rm_extreme:
+            tmp = tmp[1:len(tmp) - 1] if len(tmp) > 2 else (tmp[[1, 0]] if len(tmp) == 2 else np.array([tmp[0], np.nan]))
+        corrs[k] = float(np.sum(tmp.astype(np.longdouble)))
+    corrs = np.where(np.isnan(corrs), 0.0, corrs)
+    corrs = corrs / corrs.max()                                          # :358
+    if isinstance(cutoff, str):
+        if cutoff != "km":
+            raise ClonalscopeError(_lib.CS_ERR_ARG, "cutoff must be a number or 'km'")
+        cutoff = _km_cutoff(stream, corrs)
+    annot = np.where(corrs > cutoff, "T", "N")                           # :401-402
+    print("Succeed!")
+    rn = [f"Cluster{k + 1}" for k in range(kt)]
+    wrap = (lambda M: NamedMatrix(M, rn, colnames)) if colnames is not None else (lambda M: M)
+    return dict(Zest=z.astype(np.int32), corrs=corrs[z - 1], annot=annot[z - 1], Uest=wrap(Usub), Ucest=wrap(Usubc),
+                Uaest=wrap(Usuba), sigmas_cov_est=sigmas_cov, sigmas_allele_est=sigmas_allele, Zmaj=zmaj, cutoff=cutoff,
+                U0=priors.get("U0"), wU0=priors.get("wU0"))
+
+
 def AssignCluster(cluster_obj=None, mincell=20, cutoff=0.2, allele=False, cna_states_WGS=None, rm_extreme=False,
                   cap_corr=1.5):
     """Assign a subclone to every cell (reference R/AssignCluster.R:20-208, coverage branch):
@@ -723,12 +846,13 @@ def AssignCluster(cluster_obj=None, mincell=20, cutoff=0.2, allele=False, cna_st
 
     Device: the tally, the per-cluster sums and squared residuals, the orphans' log-likelihoods.
     Host: counting, R's stream (one uniform per orphan), the K x R index arithmetic of :106-150.
-    `allele=TRUE` (:210-) and `cutoff='km'` (k-means on R's stream, :191-194) are not built."""
+    `allele=TRUE` takes the allele branch (:216-414, _assign_cluster_allele); `cutoff='km'` is R's
+    kmeans on the same stream (:191-194, rrng.kmeans_hartigan_wong)."""
     import torch
     if allele:
-        raise ClonalscopeError("AssignCluster(allele=TRUE) is not built in this path")
-    if isinstance(cutoff, str):
-        raise ClonalscopeError("AssignCluster(cutoff='km') is not built in this path")
+        return _assign_cluster_allele(cluster_obj, mincell, cutoff, cna_states_WGS, rm_extreme, cap_corr)
+    if isinstance(cutoff, str) and cutoff != "km":
+        raise ClonalscopeError(_lib.CS_ERR_ARG, "cutoff must be a number or 'km'")
     if rm_extreme:
         raise ClonalscopeError("rm_extreme=TRUE returns NULL indices in the reference (:139-144); not supported")
     from .rrng import RStream, sample_int_prob_one
@@ -787,6 +911,8 @@ def AssignCluster(cluster_obj=None, mincell=20, cutoff=0.2, allele=False, cna_st
     if corrs.max() < 0.5:                                                # :154-156
         import warnings
         warnings.warn("WGS and scRNA do not match well. annot might not be accurate!")
+    if isinstance(cutoff, str):                                          # :191-194
+        cutoff = _km_cutoff(stream, corrs)
     annot = np.where(corrs > cutoff, "T", "N")                           # :196-197
     print("Succeed!")
     Uest = NamedMatrix(Usub, [f"Cluster{k + 1}" for k in range(kt)], colnames) if colnames is not None else Usub

@@ -409,3 +409,90 @@ def assign_cluster(Zall, kt_last, X, cna_states_WGS, mincell=20, cutoff=0.2, cap
         corrs[k] = float(s) if len(tmp) and not np.any(np.isnan(x)) else 0.0
     annot = np.where(corrs > cutoff, "T", "N")
     return dict(Zest=z, corrs=corrs[z - 1], annot=annot[z - 1], Uest=Usub, sigmas_est=sig, Zmaj=zmaj, cutoff=cutoff)
+
+
+def assign_cluster_allele(Zall, kt_last, Xcov, Xall, cna_states_WGS, mincell=20, cutoff=0.2, cap_corr=1.5,
+                          rm_extreme=False):
+    """Restatement of AssignCluster, allele branch (reference R/AssignCluster.R:216-414); test
+    infrastructure only.  PARITY UNPINNED: the reference ships no AssignCluster(allele=TRUE) output.
+    R's `x[-ind_cell, ]` with an empty `ind_cell` selects no row, so without dissolved clusters the
+    returned sigmas are 0 — kept as the reference behaves."""
+    L = lib()
+    Zall = np.asarray(Zall)
+    Xcov, Xall = np.asarray(Xcov, dtype=np.float64), np.asarray(Xall, dtype=np.float64)
+    N, R = Xcov.shape
+    g = MT()
+    L.cso_set_seed(C.byref(g), C.c_uint32(100))                          # :231
+    zmaj = majority_vote(Zall)
+    Zest = zmaj.astype(np.float64)
+    labs, cnts = np.unique(zmaj, return_counts=True)
+    ind_clusters = labs[cnts > mincell]                                  # :236
+    ind_cell = np.nonzero(~np.isin(zmaj, ind_clusters))[0]
+    Zest[ind_cell] = np.nan
+    kept = np.setdiff1d(np.arange(N), ind_cell) if len(ind_cell) else np.zeros(0, dtype=int)   # x[-integer(0)] is empty
+
+    def means(X):
+        U = np.full((kt_last, R), np.nan)
+        for kk in ind_clusters:
+            rows = X[Zest == kk].astype(np.longdouble)
+            ok = ~np.isnan(rows)
+            cnt = ok.sum(axis=0)
+            s = np.where(ok, rows, 0).sum(axis=0)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                m = np.asarray(s / cnt, dtype=np.float64)
+            m[cnt == 0] = 0.0
+            U[kk - 1] = m
+        return U
+
+    def sigma(X, U, n):
+        d = (X[kept] - U[Zest[kept].astype(int) - 1]).astype(np.longdouble) ** 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.sqrt(1.0 / n * np.asarray(np.where(np.isnan(d), 0, d).sum(axis=0), dtype=np.float64))
+
+    Uc, Ua = means(Xcov), means(Xall)                                    # :240-250
+    notorph = np.ones(N, dtype=bool)
+    notorph[ind_cell] = False
+    ncov = (~np.isnan(Xcov) & notorph[:, None]).sum(axis=0)              # :252-256
+    nall = (~np.isnan(Xall) & notorph[:, None]).sum(axis=0)
+    sc, sa = sigma(Xcov, Uc, ncov), sigma(Xall, Ua, nall)                # :258-259
+    one = np.array([1], dtype=np.int32)
+    for ii in ind_cell:                                                  # :265-275
+        P = np.full(kt_last, np.nan)
+        for kk in ind_clusters:
+            P[kk - 1] = total_loglik(Xcov[ii:ii + 1], Uc[kk - 1:kk], one, sc) + \
+                total_loglik(Xall[ii:ii + 1], Ua[kk - 1:kk], one, sa)
+        P[ind_clusters - 1] -= np.max(P[ind_clusters - 1])
+        P[np.isnan(P)] = np.nanmin(P) - 100
+        p = np.ascontiguousarray(np.exp(P), dtype=np.float64)
+        perm = np.zeros(kt_last, dtype=np.int32)
+        Zest[ii] = L.cso_sample_int_prob(C.byref(g), kt_last, _p(p, C.c_double), _p(perm, C.c_int))
+    Uc, Ua = means(np.minimum(Xcov, 3.0)), means(Xall)                   # :281-294 (pmin keeps NA)
+    Ug = np.full((kt_last, R), np.nan)
+    for kk in ind_clusters:
+        for r in range(R):
+            Ug[kk - 1, r] = genotype_neighbor(Uc[kk - 1, r], Ua[kk - 1, r], 6)
+    ncov, nall = (~np.isnan(Xcov)).sum(axis=0), (~np.isnan(Xall)).sum(axis=0)               # :302-303
+    sc, sa = sigma(Xcov, Uc, ncov), sigma(Xall, Ua, nall)                # :305-306
+    priors = np.asarray(cna_states_WGS, dtype=np.float64)
+    if np.all(priors == 4):
+        priors = np.full(R, 8.0)
+    priorsc = genotype_grid(6)[priors.astype(int) - 1, 0]                # :333
+    U2 = np.maximum(np.minimum(Uc, cap_corr), 0.5)
+    corrs = np.zeros(kt_last)
+    for k in range(kt_last):                                             # :342-353
+        tmp = (U2[k] - 1) * (priorsc - 1)
+        tmp = sorted(v for v in tmp if v == v)
+        if not tmp:
+            continue
+        if rm_extreme:
+            idx = list(range(2, len(tmp))) if len(tmp) >= 3 else list(range(2, len(tmp) - 2, -1))   # 2:(n-1), 1-based
+            tmp = [tmp[i - 1] if 1 <= i <= len(tmp) else np.nan for i in idx if i != 0]
+        s = np.longdouble(0)
+        for v in tmp:
+            s += v
+        corrs[k] = 0.0 if s != s else float(s)
+    corrs = corrs / corrs.max()                                          # :358
+    z = Zest.astype(int)
+    annot = np.where(corrs > cutoff, "T", "N")
+    return dict(Zest=z, corrs=corrs[z - 1], annot=annot[z - 1], Uest=Ug, Ucest=Uc, Uaest=Ua, sigmas_cov_est=sc,
+                sigmas_allele_est=sa, Zmaj=zmaj, cutoff=cutoff)

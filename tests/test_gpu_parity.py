@@ -837,6 +837,65 @@ def test_assign_cluster_on_the_reference_chains(cs, name, mincell, labels):
     assert set(np.unique(out["annot"])) <= {"T", "N"} and np.all(np.isfinite(out["sigmas_est"]))
 
 
+@pytest.mark.parametrize("mincell,na,rm_extreme", [(81, 0.0, False), (81, 0.05, True), (5, 0.0, False)])
+def test_assign_cluster_allele_branch_vs_oracle(cs, oracle, mincell, na, rm_extreme):
+    """AssignCluster(allele=TRUE) after BayesNonparAlleleCluster + MCMCtrim against the restated
+    R/AssignCluster.R:216-414 (no reference output exists: parity unpinned): the same orphans re-drawn
+    to the same clusters under set.seed(100), genotype states identical, means / sigmas / index 1e-10.
+    With mincell=5 no cluster is dissolved and the reference's sigmas come out 0 (x[-integer(0), ])."""
+    Xc, Xa, true, z = _allele_data(oracle, na=na)
+    chain = cs.BayesNonparAlleleCluster(Xc, Xa, cna_states_WGS=true[1], niter=30, seed=200, rng="R")
+    tr = cs.MCMCtrim(chain, burnin=10, allele=True)
+    got = cs.AssignCluster(tr, mincell=mincell, allele=True, rm_extreme=rm_extreme)
+    kt = tr["results"]["Uall"][-1].shape[0]
+    want = oracle.assign_cluster_allele(tr["results"]["Zall"], kt, Xc, Xa, true[1], mincell=mincell,
+                                        rm_extreme=rm_extreme)
+    assert np.array_equal(got["Zmaj"], want["Zmaj"])
+    assert np.array_equal(got["Zest"], want["Zest"])
+    if mincell == 81:                                                  # the 80-cell cluster is dissolved
+        assert (got["Zest"] != got["Zmaj"]).sum() >= 80               # and its cells re-drawn
+    else:
+        assert np.array_equal(got["Zest"], got["Zmaj"]) and not got["sigmas_cov_est"].any()
+    val = lambda m: m.values if hasattr(m, "values") else m            # noqa: E731
+    assert np.array_equal(np.nan_to_num(val(got["Uest"]), nan=-1), np.nan_to_num(want["Uest"], nan=-1))
+    np.testing.assert_allclose(val(got["Ucest"]), want["Ucest"], rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(val(got["Uaest"]), want["Uaest"], rtol=1e-10, atol=1e-14, equal_nan=True)
+    np.testing.assert_allclose(got["sigmas_cov_est"], want["sigmas_cov_est"], rtol=1e-10)
+    np.testing.assert_allclose(got["sigmas_allele_est"], want["sigmas_allele_est"], rtol=1e-10)
+    np.testing.assert_allclose(got["corrs"], want["corrs"], rtol=1e-10, atol=1e-12)
+    assert np.array_equal(got["annot"], want["annot"]) and np.nanmax(got["corrs"]) == 1.0
+
+
+def test_assign_cluster_km_cutoff(cs, oracle):
+    """cutoff='km' (R/AssignCluster.R:191-194): kmeans on R's stream after the orphans' draws.  The
+    cutoff must be the midpoint of a 2-means partition of the per-cluster indices that no single
+    transfer improves (Hartigan-Wong's stopping rule), and the labels must follow it."""
+    g = load_golden("sampler_P5931.npz")
+    R = g["X"].shape[1]
+    obj = dict(results=dict(Zall=g["Zall"][100:].astype(np.int32), Uall=[np.zeros((int(g["kt"][-1]), R))]),
+               priors=dict(U0=g["U0"], cna_states_WGS=g["cna_states_WGS"], wU0=True), data=g["X"])
+    fixed = cs.AssignCluster(obj, mincell=13, cutoff=0.2)
+    km = cs.AssignCluster(obj, mincell=13, cutoff="km")
+    assert np.array_equal(km["Zest"], fixed["Zest"]) and np.array_equal(km["corrs"], fixed["corrs"])
+    # per-cluster indices: zeros for the dissolved clusters included, as the reference passes them
+    kt = int(g["kt"][-1])
+    per = np.zeros(kt)
+    per[km["Zest"] - 1] = km["corrs"]
+    c = km["cutoff"]
+    lo, hi = per[per <= c], per[per > c]
+    assert len(lo) and len(hi) and abs(c - (lo.mean() + hi.mean()) / 2) < 1e-12
+    def wss(a, b):
+        return ((a - a.mean()) ** 2).sum() + ((b - b.mean()) ** 2).sum()
+    base = wss(lo, hi)
+    for i in range(len(lo)):
+        if len(lo) > 1:
+            assert wss(np.delete(lo, i), np.append(hi, lo[i])) >= base - 1e-12
+    for i in range(len(hi)):
+        if len(hi) > 1:
+            assert wss(np.append(lo, hi[i]), np.delete(hi, i)) >= base - 1e-12
+    assert np.array_equal(km["annot"], np.where(km["corrs"] > c, "T", "N"))
+
+
 # ------------------------------------------------------------------ f3: CreateSegtableNoWGS + Segmentation_bulk
 def _planted_profile(rng, bins, depth=40.0):
     """Pooled tumour / normal counts over the synthetic tiles with a few planted gains and losses."""
