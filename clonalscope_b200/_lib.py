@@ -25,6 +25,7 @@ SYMBOLS = [
     "cs_cluster_stats_dev", "cs_sigma_stats_dev", "cs_cluster_stats", "cs_sigma_stats", "cs_gene_moments",
     "cs_rowsum_by_label", "cs_rowsum_by_label_dev", "cs_bin_job_rowsum_by_label", "cs_segment_hmm",
     "cs_csc_upload", "cs_csc_free", "cs_csc_gene_moments", "cs_csc_region_cov",
+    "cs_mm_read_begin", "cs_mm_read_fetch", "cs_mm_read_free",
 ]
 
 
@@ -58,6 +59,7 @@ def lib():
         L.cs_last_error.restype = C.c_char_p
         L.cs_bin_counts_free.restype = None
         L.cs_csc_free.restype = None
+        L.cs_mm_read_free.restype = None
         L.cs_bin_plan_destroy.restype = None
         L.cs_chain_destroy.restype = None
         L.cs_release_cached.restype = None

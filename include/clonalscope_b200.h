@@ -275,6 +275,18 @@ int cs_bin_job_rowsum_by_label(cs_bin_job *job, const int *label, int K, double 
 int cs_segment_hmm(int nseq, const int64_t *off, const double *val, int nmean, const double *means,
                    const double *sds, const double *delta, const double *Pi, double *smooth, int *state);
 
+/* ------------------------------------------------------------------------
+ * MatrixMarket ingest: Matrix::readMM + as(., "dgCMatrix") of the tutorials
+ * (samples/P5931/scRNA/README.md:72; R/Gene_bin_cell_rna_filtered.R:23).  `path`: a coordinate
+ * real / integer / pattern general file, plain or .gz.  begin() parses the text on host threads,
+ * builds the compressed columns on the device (duplicates summed, rows ascending) and reports
+ * dims = {rows, cols, nnz}; fetch() copies into caller-allocated dgCMatrix slots and frees the job.
+ * ---------------------------------------------------------------------- */
+typedef struct cs_mm_job cs_mm_job;
+int cs_mm_read_begin(const char *path, cs_mm_job **job, int64_t *dims);
+int cs_mm_read_fetch(cs_mm_job *job, int32_t *colptr, int32_t *rowidx, double *x);
+void cs_mm_read_free(cs_mm_job *job);
+
 #ifdef __cplusplus
 }
 #endif

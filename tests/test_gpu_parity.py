@@ -1048,3 +1048,72 @@ def test_create_segtable_nowgs_end_to_end(cs, oracle):
     assert np.array_equal(seg2.astype(str), want)
     with pytest.raises(ValueError, match="three HMM numeric states"):   # the reference's own default fails its check
         CreateSegtableNoWGS(bin_mtx=bm, Zest=z[perm], bin_bed=bed, celltype0=celltype0, size=size)
+
+
+# ------------------------------------------------------------------ f4: MatrixMarket ingest
+def test_readmm_matches_scipy(cs, tmp_path):
+    """cs_mm_read_*: cellranger-style files (column-major, ascending rows — the fast path), a shuffled
+    file with duplicated coordinates (sort + segmented sum), pattern and real-valued files, .gz."""
+    import gzip
+    import scipy.io
+    import scipy.sparse as sp
+    from clonalscope_b200.rio import readMM
+    rng = np.random.default_rng(41)
+    G, N = 5000, 700
+    m = sp.random(G, N, density=0.08, random_state=7, format="csc", data_rvs=lambda k: rng.integers(1, 50, k).astype(float))
+    m.sort_indices()
+    coo = m.tocoo()                                                    # column-major, rows ascending
+    def write(path, rows, cols, vals, field="integer", opener=open):
+        with opener(path, "wt") as f:
+            f.write(f"%%MatrixMarket matrix coordinate {field} general\n%metadata_json: {{}}\n")
+            f.write(f"{G} {N} {len(rows)}\n")
+            if vals is None:
+                f.write("".join(f"{r + 1} {c + 1}\n" for r, c in zip(rows, cols)))
+            else:
+                f.write("".join(f"{r + 1} {c + 1} {v}\n" for r, c, v in zip(rows, cols, vals)))
+    ints = coo.data.astype(np.int64)
+    write(tmp_path / "a.mtx", coo.row, coo.col, ints)
+    got = readMM(tmp_path / "a.mtx")
+    assert got.shape == (G, N) and (got != m).nnz == 0 and got.has_sorted_indices
+    assert np.array_equal(got.indptr, m.indptr) and np.array_equal(got.indices, m.indices)
+    assert (tmp_path / "a.mtx").stat().st_size > (1 << 20)              # several parser threads took part
+    write(tmp_path / "a.mtx.gz", coo.row, coo.col, ints, opener=gzip.open)
+    gz = readMM(tmp_path / "a.mtx.gz")
+    assert np.array_equal(gz.indptr, m.indptr) and np.array_equal(gz.indices, m.indices) and np.array_equal(gz.data, m.data)
+    # shuffled, with every 10th entry split in two: duplicates are summed, like readMM + dgCMatrix
+    rows, cols = list(coo.row), list(coo.col)
+    vals = list(ints)
+    for e in range(0, len(vals), 10):
+        if vals[e] > 1:
+            rows.append(rows[e]), cols.append(cols[e]), vals.append(1)
+            vals[e] -= 1
+    perm = rng.permutation(len(vals))
+    write(tmp_path / "b.mtx", np.array(rows)[perm], np.array(cols)[perm], np.array(vals)[perm])
+    got = readMM(tmp_path / "b.mtx")
+    assert np.array_equal(got.indptr, m.indptr) and np.array_equal(got.indices, m.indices) and np.array_equal(got.data, m.data)
+    # pattern and real fields against scipy's reader
+    write(tmp_path / "p.mtx", coo.row[:500], coo.col[:500], None, field="pattern")
+    want = sp.csc_matrix(scipy.io.mmread(str(tmp_path / "p.mtx")))
+    got = readMM(tmp_path / "p.mtx")
+    assert (got != want).nnz == 0
+    real = rng.normal(size=300)
+    write(tmp_path / "r.mtx", coo.row[:300], coo.col[:300], [repr(float(v)) for v in real], field="real")
+    got = readMM(tmp_path / "r.mtx")
+    want = sp.csc_matrix(scipy.io.mmread(str(tmp_path / "r.mtx")))
+    assert abs(got - want).max() == 0.0
+    # loud failures
+    with open(tmp_path / "bad.mtx", "w") as f:
+        f.write("%%MatrixMarket matrix coordinate integer general\n3 3 2\n1 1 5\n4 1 2\n")
+    with pytest.raises(cs.ClonalscopeError, match="outside"):
+        readMM(tmp_path / "bad.mtx")
+    with open(tmp_path / "short.mtx", "w") as f:
+        f.write("%%MatrixMarket matrix coordinate integer general\n3 3 5\n1 1 5\n")
+    with pytest.raises(cs.ClonalscopeError, match="announces"):
+        readMM(tmp_path / "short.mtx")
+    with pytest.raises(cs.ClonalscopeError, match="cannot open"):
+        readMM(tmp_path / "missing.mtx")
+    # empty matrix
+    with open(tmp_path / "empty.mtx", "w") as f:
+        f.write("%%MatrixMarket matrix coordinate integer general\n4 3 0\n")
+    e = readMM(tmp_path / "empty.mtx")
+    assert e.shape == (4, 3) and e.nnz == 0

@@ -285,3 +285,40 @@ def test_segmentation_argument_errors():
     assert obj["size"] == {"1": 1000000.0}
     with pytest.raises(ValueError, match="three HMM numeric states"):
         Segmentation_bulk(obj, hmm_states=(0.5, 1, 1.5, 2))
+
+
+def test_saverds_known_bytes_and_round_trip(tmp_path):
+    """saveRDS: the byte stream of R's serialize(c(1, 2), NULL, version = 2) is a known answer, and the
+    objects of the path (named list, matrices with dimnames, named numeric vectors, data.frame, NA
+    strings) read back through the RDS reader that is pinned by the reference's own .rds files."""
+    import rds_reader as rr
+    from clonalscope_b200.api import NamedMatrix
+    from clonalscope_b200.rio import RDataFrame, saveRDS, serialize
+    assert serialize(np.array([1.0, 2.0])) == bytes.fromhex(
+        "580a" "00000002" "00030600" "00020300" "0000000e" "00000002" "3ff0000000000000" "4000000000000000")
+    assert serialize(None)[-4:] == bytes.fromhex("000000fe")
+    clustering = dict(
+        data=NamedMatrix(np.array([[1.0, np.nan], [0.5, 2.0], [1.5, 1.0]]), ["c1", "c2", "c3"], ["chr1-0-5", "chr2-0-9"]),
+        results=dict(Zall=np.array([[1, 2, 2], [1, 1, 2]], dtype=np.int32), Likelihood=np.array([-3.5, -2.25]),
+                     Uall=[np.ones((2, 2)), np.full((3, 2), 0.5)]),
+        priors=dict(alpha=2.0, seed=np.int32(200), U0=None, names=["a", None, "é"]),
+        deltas_all={"pt0.99_tumor_alphaallchr1": (["c1", "c3"], np.array([1.1, 0.9]))},
+        seg=RDataFrame(chr=["1", "2"], start=np.array([0.0, 6e5]), Var1=np.array([1, 2], dtype=np.int32)))
+    fn = str(tmp_path / "nonpara_clustering.rds")
+    saveRDS(clustering, fn)
+    r = rr.read_rds(fn)
+    assert r.names == ["data", "results", "priors", "deltas_all", "seg"]
+    d = r["data"]
+    assert list(d.attrs["dim"].data) == [3, 2] and list(d.attrs["dimnames"][1].data) == ["chr1-0-5", "chr2-0-9"]
+    np.testing.assert_array_equal(d.data.reshape(2, 3).T, clustering["data"].values)
+    assert np.array_equal(r["results"]["Zall"].data.reshape(3, 2).T, clustering["results"]["Zall"])
+    assert r["results"]["Zall"].data.dtype.kind == "i" and len(r["results"]["Uall"]) == 2
+    assert list(r["results"]["Uall"][1].attrs["dim"].data) == [3, 2]
+    assert r["priors"]["U0"] is None and list(r["priors"]["names"].data) == ["a", None, "é"]
+    assert float(r["priors"]["alpha"].data[0]) == 2.0 and int(r["priors"]["seed"].data[0]) == 200
+    nv = r["deltas_all"]["pt0.99_tumor_alphaallchr1"]
+    assert nv.names == ["c1", "c3"] and list(nv.data) == [1.1, 0.9]
+    assert list(r["seg"].attrs["class"].data) == ["data.frame"] and list(r["seg"].attrs["row.names"].data) == [-2147483648, -2]
+    assert list(r["seg"]["chr"].data) == ["1", "2"] and list(r["seg"]["start"].data) == [0.0, 6e5]
+    saveRDS(np.arange(3.0), str(tmp_path / "plain.rds"), compress=False)
+    assert list(rr.read_rds(str(tmp_path / "plain.rds")).data) == [0.0, 1.0, 2.0]
