@@ -1,9 +1,10 @@
-## Drop-in body for R/EstRegionCov.R of the reference: same signature and return list.  What ran
-## over the dense gene x cell matrix there runs on the device here, on the dgCMatrix slots:
-##   apply(mtx,1,var) / rowSums (:42-43)            -> cs_R_gene_moments  (per-gene sum, sum of squares)
-##   colSums(rna[gene_ind,]) per segment (:88-93)   -> cs_R_bin_counts    (gene -> segment map)
-##   colSums(rna_control) library sizes (:131-137)  -> cs_R_bin_counts    (every control gene -> one bin)
-## Overlaps, quantiles, medians, ratios, names and the optional histograms stay in R.
+## Drop-in body for R/EstRegionCov.R of the reference: same signature and return list.  The matrix is
+## uploaded once and everything that ran over the dense gene x cell matrix runs on that device copy:
+##   mtx[, match(celltype0[,1], barcodes[,1])] (:40)          -> cs_R_csc_upload      (column gather on the device)
+##   apply(mtx,1,var) / rowSums (:42-43)                       -> cs_R_csc_gene_moments
+##   per segment: colSums, sel_cell, library sizes, both medians, ratios (:88-159), all segments at once
+##                                                             -> cs_R_csc_region_cov
+## Overlaps, the quantile of the variance filter, names and the optional histograms stay in R.
 EstRegionCov=function(mtx=NULL, barcodes=NULL, features=NULL, bed=NULL, celltype0=NULL, var_pt=0.99, var_pt_ctrl=0.99,ngene_filter=0, include='tumor',
                       alpha_source='all', ctrl_region=NULL, seg_table_filtered=NULL,size=NULL, plot_path=NULL, breaks=30){
   if(!include %in% c('tumor','control','all')) stop("include variable is not valid!")
@@ -11,9 +12,9 @@ EstRegionCov=function(mtx=NULL, barcodes=NULL, features=NULL, bed=NULL, celltype
   if(!grepl("chr",bed[1,1])) bed[,1]=paste0('chr', bed[,1])
   if(is.null(celltype0)) celltype0=cbind(barcodes[,1], rep("normal", nrow(barcodes)))
   M=as(mtx, "CsparseMatrix")
-  M=M[,match(celltype0[,1], barcodes[,1]), drop=FALSE]                                     # :36-40
-  G=nrow(M); N=ncol(M); cells=celltype0[,1]
-  mom=.Call("cs_R_gene_moments", M@i, as.numeric(M@x), as.integer(G), PACKAGE="Clonalscope")
+  G=nrow(M); cells=celltype0[,1]; N=length(cells)
+  h=.Call("cs_R_csc_upload", M@p, M@i, as.numeric(M@x), as.integer(G), as.integer(match(celltype0[,1], barcodes[,1])-1L), PACKAGE="Clonalscope")  # :36-40
+  mom=.Call("cs_R_csc_gene_moments", h, as.integer(G), PACKAGE="Clonalscope")
   ngenes_g=mom[[1]]; rna_var=pmax(mom[[2]]-mom[[1]]^2/N, 0)/(N-1)                          # :42-43
   keep  =which(rna_var<quantile(rna_var,var_pt)      & (rna_var!=0) & ngenes_g>ngene_filter)  # :47
   keep_c=which(rna_var<quantile(rna_var,var_pt_ctrl) & (rna_var!=0) & ngenes_g>ngene_filter)  # :48
@@ -33,31 +34,26 @@ EstRegionCov=function(mtx=NULL, barcodes=NULL, features=NULL, bed=NULL, celltype
   ov=cbind(match(paste0(seg_table_filtered$chrr)[ov[,1]], regs), keep[ov[,2]])             # (segment, gene row)
   ov=ov[order(ov[,2], ov[,1]),,drop=FALSE]
   seg_ngene=tabulate(ov[,1], nbins=S)
-  seg=.Call("cs_R_bin_counts", M@p, M@i, as.numeric(M@x), as.integer(G), as.integer(c(0L,cumsum(tabulate(ov[,2], nbins=G)))),
-            as.integer(ov[,1]-1L), as.integer(S), PACKAGE="Clonalscope")
-  segsum=as.matrix(new("dgCMatrix", p=seg[[1]], i=seg[[2]], x=seg[[3]], Dim=c(S, N)))     # S x N, small
   libg=if(alpha_source=='all') keep_c else keep[which(bed_sub[,1] %in% ctrl_region)]
-  flag=integer(G); flag[libg]=1L
-  lib=.Call("cs_R_bin_counts", M@p, M@i, as.numeric(M@x), as.integer(G), as.integer(c(0L,cumsum(flag))),
-            integer(sum(flag)), 1L, PACKAGE="Clonalscope")
-  alpha_all=numeric(N); alpha_all[which(diff(lib[[1]])>0)]=lib[[3]]
+  flag=raw(G); flag[libg]=as.raw(1L)
+  code=ifelse(celltype0[,2]=='normal', 0L, ifelse(celltype0[,2]=='tumor', 1L, 2L))
+  rc=.Call("cs_R_csc_region_cov", h, as.integer(N), as.integer(S), as.integer(c(0L,cumsum(tabulate(ov[,2], nbins=G)))),
+           as.integer(ov[,1]-1L), flag, as.integer(code), match(include, c('tumor','control','all'))-1L, PACKAGE="Clonalscope")
+  out_type=switch(include, tumor=celltype0[,2]=='tumor', control=celltype0[,2]=='normal', all=rep(TRUE, N))
   deltas_all=list(); ngenes=c(); sel_ind=c(); alphas=NULL; barcodes_normal=NULL
   if(!is.null(plot_path)){ pdf(plot_path, width = 8, height = 6); par(mfrow=c(2,3)) }
   for(si in seq_len(S)){
     chrr=regs[si]
-    sel_cell=which(segsum[si,]>0)                                                          # :93
-    if(length(sel_cell)==0) next
+    if(rc$nsel[si]==0) next                                                                # :93 no cell with a positive sum
     sel_ind=c(sel_ind, chrr)
-    types=celltype0[sel_cell,2]
-    normal=which(types=='normal')
-    tsel=switch(include, tumor=which(types=='tumor'), control=normal, all=seq_along(sel_cell))
-    barcodes_normal=cells[sel_cell][normal]
-    alphas=alpha_all[sel_cell]; names(alphas)=cells[sel_cell]                              # :131-137
-    alpha_controls=alphas[normal]/median(alphas); alpha_tests=alphas[tsel]/median(alphas)  # :141-148
-    deltas=(segsum[si,sel_cell][tsel]/alpha_tests)/median(segsum[si,sel_cell][normal]/alpha_controls)  # :153-159
-    names(deltas)=cells[sel_cell][tsel]
+    sel=rc$sums[,si]>0
+    tsel=which(sel & out_type)
+    types=celltype0[sel,2]
+    barcodes_normal=cells[sel & celltype0[,2]=='normal']
+    alphas=rc$alpha[sel]; names(alphas)=cells[sel]                                         # :131-137
+    deltas=rc$deltas[tsel,si]; names(deltas)=cells[tsel]                                   # :141-159 (device)
     if(!is.null(plot_path)){
-      tp=types[tsel]
+      tp=celltype0[tsel,2]
       if(sum(tp=='tumor')>1 & sum(tp=='normal')>1){
         plot(hist(deltas[tp=='tumor'],breaks=breaks,plot=FALSE), xlim=c(0,3), col=rgb(239,90,155,max=255,alpha=50),
              main=paste0(chrr, ":", seg_ngene[si], " genes; ", length(deltas), " cells"))

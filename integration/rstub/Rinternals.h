@@ -27,4 +27,17 @@ double *REAL(SEXP);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 SEXP R_do_slot(SEXP, SEXP);
 SEXP Rf_install(const char *);
+#define RAWSXP 24
+typedef unsigned char Rbyte;
+Rbyte *RAW(SEXP);
+extern SEXP R_NilValue;
+SEXP STRING_ELT(SEXP, R_xlen_t);
+const char *R_CHAR(SEXP);
+#define CHAR(x) R_CHAR(x)
+typedef void (*R_CFinalizer_t)(SEXP);
+SEXP R_MakeExternalPtr(void *, SEXP, SEXP);
+void *R_ExternalPtrAddr(SEXP);
+void R_ClearExternalPtr(SEXP);
+void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, int);
+SEXP Rf_ScalarInteger(int);
 #endif

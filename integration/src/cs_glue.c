@@ -155,20 +155,6 @@ SEXP cs_R_majority_vote(SEXP Zall)
     return z;
 }
 
-/* .Call("cs_R_gene_moments", i, x, G): list(sum, sumsq), one entry per gene (R/EstRegionCov.R:42-43) */
-SEXP cs_R_gene_moments(SEXP i, SEXP x, SEXP G)
-{
-    const int g = Rf_asInteger(G);
-    SEXP s = PROTECT(Rf_allocVector(REALSXP, g)), q = PROTECT(Rf_allocVector(REALSXP, g));
-    int rc = cs_gene_moments(g, (int64_t)XLENGTH(x), INTEGER(i), REAL(x), REAL(s), REAL(q));
-    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
-    SET_VECTOR_ELT(out, 0, s);
-    SET_VECTOR_ELT(out, 1, q);
-    UNPROTECT(3);
-    check(rc);
-    return out;
-}
-
 /* .Call("cs_R_cluster_stats", X, Z, K): list(sum, count, n) — K x R sums and non-NA counts of the
  * cells of each label, and the cluster sizes (R/AssignCluster.R:46-51, :67-72; labels NA / outside
  * 1..K are skipped: NA_integer_ is INT_MIN) */
@@ -204,15 +190,138 @@ SEXP cs_R_sigma_stats(SEXP X, SEXP Z, SEXP U)
     return out;
 }
 
+/* ---- EstRegionCov on a device-resident matrix (R/EstRegionCov.R:36-48, :80-159) */
+static void csc_finalizer(SEXP ptr)
+{
+    cs_csc *m = (cs_csc *)R_ExternalPtrAddr(ptr);
+    if (m) cs_csc_free(m);
+    R_ClearExternalPtr(ptr);
+}
+
+/* .Call("cs_R_csc_upload", p, i, x, G, col_sel): external pointer to the uploaded matrix; col_sel =
+ * match(celltype0[,1], barcodes[,1]) - 1L (or integer(0) for all columns in order) */
+SEXP cs_R_csc_upload(SEXP p, SEXP i, SEXP x, SEXP G, SEXP col_sel)
+{
+    cs_csc *m = NULL;
+    const int nsel = LENGTH(col_sel);
+    check(cs_csc_upload(Rf_asInteger(G), LENGTH(p) - 1, INTEGER(p), INTEGER(i), REAL(x), nsel,
+                        nsel ? INTEGER(col_sel) : NULL, &m));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(m, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, csc_finalizer, 1);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* .Call("cs_R_csc_gene_moments", handle, G): list(sum, sumsq) (:42-43) */
+SEXP cs_R_csc_gene_moments(SEXP handle, SEXP G)
+{
+    const int g = Rf_asInteger(G);
+    SEXP s = PROTECT(Rf_allocVector(REALSXP, g)), q = PROTECT(Rf_allocVector(REALSXP, g));
+    int rc = cs_csc_gene_moments((cs_csc *)R_ExternalPtrAddr(handle), REAL(s), REAL(q));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, s);
+    SET_VECTOR_ELT(out, 1, q);
+    UNPROTECT(3);
+    check(rc);
+    return out;
+}
+
+/* .Call("cs_R_csc_region_cov", handle, N, S, map_ptr, map_seg, lib_flag (raw), celltype, include)
+ * -> list(deltas N x S, sums N x S, alpha, nsel) (:88-159 for every segment at once) */
+SEXP cs_R_csc_region_cov(SEXP handle, SEXP N_, SEXP S_, SEXP map_ptr, SEXP map_seg, SEXP lib_flag, SEXP celltype,
+                         SEXP include)
+{
+    const int N = Rf_asInteger(N_), S = Rf_asInteger(S_);
+    SEXP d = PROTECT(Rf_allocMatrix(REALSXP, N, S)), s = PROTECT(Rf_allocMatrix(REALSXP, N, S));
+    SEXP a = PROTECT(Rf_allocVector(REALSXP, N)), n = PROTECT(Rf_allocVector(INTSXP, S));
+    int rc = cs_csc_region_cov((cs_csc *)R_ExternalPtrAddr(handle), S, INTEGER(map_ptr), INTEGER(map_seg), RAW(lib_flag),
+                               INTEGER(celltype), Rf_asInteger(include), REAL(d), REAL(s), REAL(a), INTEGER(n));
+    const char *names[] = {"deltas", "sums", "alpha", "nsel", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, d);
+    SET_VECTOR_ELT(out, 1, s);
+    SET_VECTOR_ELT(out, 2, a);
+    SET_VECTOR_ELT(out, 3, n);
+    UNPROTECT(5);
+    check(rc);
+    return out;
+}
+
+/* .Call("cs_R_rowsum_by_label", p, i, x, B, label, K): B x K matrix, column k = rowSums over the
+ * cells with label k (0-based; others skipped) (R/CreateSegtableNoWGS.R:62-69, :77) */
+SEXP cs_R_rowsum_by_label(SEXP p, SEXP i, SEXP x, SEXP B_, SEXP label, SEXP K_)
+{
+    const int B = Rf_asInteger(B_), K = Rf_asInteger(K_);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, B, K));
+    int rc = cs_rowsum_by_label(B, LENGTH(p) - 1, INTEGER(p), INTEGER(i), REAL(x), INTEGER(label), K, REAL(out));
+    UNPROTECT(1);
+    check(rc);
+    return out;
+}
+
+/* .Call("cs_R_segment_hmm", off, val, nmean, means, sds, delta, Pi): list(smooth, state) for the
+ * sequences val[off[s] .. off[s+1]) (R/Segmentation_bulk.R:152-166: runmean + dthmm + Viterbi);
+ * off is a double vector (R has no 64-bit integers), Pi row-major, state 1-based like Viterbi() */
+SEXP cs_R_segment_hmm(SEXP off, SEXP val, SEXP nmean, SEXP means, SEXP sds, SEXP delta, SEXP Pi)
+{
+    const int nseq = LENGTH(off) - 1;
+    const R_xlen_t total = XLENGTH(val);
+    int64_t off64[1024];
+    if (nseq > 1023) Rf_error("cs_R_segment_hmm: at most 1023 sequences per call");
+    for (int s = 0; s <= nseq; s++) off64[s] = (int64_t)REAL(off)[s];
+    SEXP sm = PROTECT(Rf_allocVector(REALSXP, total)), st = PROTECT(Rf_allocVector(INTSXP, total));
+    int rc = cs_segment_hmm(nseq, off64, REAL(val), Rf_asInteger(nmean), REAL(means), REAL(sds), REAL(delta), REAL(Pi),
+                            REAL(sm), INTEGER(st));
+    if (rc == CS_OK)
+        for (R_xlen_t e = 0; e < total; e++) INTEGER(st)[e] += 1;
+    const char *names[] = {"smooth", "state", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, sm);
+    SET_VECTOR_ELT(out, 1, st);
+    UNPROTECT(3);
+    check(rc);
+    return out;
+}
+
+/* .Call("cs_R_read_mm", path): list(Dim, p, i, x) of the dgCMatrix (Matrix::readMM + as(., "dgCMatrix"),
+ * samples/P5931/scRNA/README.md:72) */
+SEXP cs_R_read_mm(SEXP path)
+{
+    cs_mm_job *job = NULL;
+    int64_t dims[3] = {0, 0, 0};
+    check(cs_mm_read_begin(CHAR(STRING_ELT(path, 0)), &job, dims));
+    SEXP dim = PROTECT(Rf_allocVector(INTSXP, 2));
+    INTEGER(dim)[0] = (int)dims[0];
+    INTEGER(dim)[1] = (int)dims[1];
+    SEXP op = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)dims[1] + 1));
+    SEXP oi = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)dims[2]));
+    SEXP ox = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)dims[2]));
+    int rc = cs_mm_read_fetch(job, INTEGER(op), INTEGER(oi), REAL(ox)); /* frees the job */
+    const char *names[] = {"Dim", "p", "i", "x", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, dim);
+    SET_VECTOR_ELT(out, 1, op);
+    SET_VECTOR_ELT(out, 2, oi);
+    SET_VECTOR_ELT(out, 3, ox);
+    UNPROTECT(5);
+    check(rc);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
     {"cs_R_loglik_matrix", (DL_FUNC)&cs_R_loglik_matrix, 3},
     {"cs_R_bin_counts", (DL_FUNC)&cs_R_bin_counts, 7},
     {"cs_R_ncrp_gibbs", (DL_FUNC)&cs_R_ncrp_gibbs, 10},
     {"cs_R_ncrp_gibbs_allele", (DL_FUNC)&cs_R_ncrp_gibbs_allele, 13},
     {"cs_R_majority_vote", (DL_FUNC)&cs_R_majority_vote, 1},
-    {"cs_R_gene_moments", (DL_FUNC)&cs_R_gene_moments, 3},
     {"cs_R_cluster_stats", (DL_FUNC)&cs_R_cluster_stats, 3},
     {"cs_R_sigma_stats", (DL_FUNC)&cs_R_sigma_stats, 3},
+    {"cs_R_csc_upload", (DL_FUNC)&cs_R_csc_upload, 5},
+    {"cs_R_csc_gene_moments", (DL_FUNC)&cs_R_csc_gene_moments, 2},
+    {"cs_R_csc_region_cov", (DL_FUNC)&cs_R_csc_region_cov, 8},
+    {"cs_R_rowsum_by_label", (DL_FUNC)&cs_R_rowsum_by_label, 6},
+    {"cs_R_segment_hmm", (DL_FUNC)&cs_R_segment_hmm, 7},
+    {"cs_R_read_mm", (DL_FUNC)&cs_R_read_mm, 1},
     {NULL, NULL, 0}};
 
 void R_init_Clonalscope(DllInfo *dll)
