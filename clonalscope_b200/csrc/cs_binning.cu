@@ -31,6 +31,8 @@
 // as Matrix(sparse=TRUE) does; that rare case triggers a compaction pass.
 #include "cs_common.cuh"
 
+#include <utility>
+
 #include <limits.h>
 #include <stdlib.h>
 #include <vector>
@@ -753,6 +755,7 @@ bin_fill_stream_kernel(int N, int B, const int64_t *__restrict__ colptr,
 // n_entries x 2^bits(max |v|) could overflow an int32 sum raises FLAG_INEXACT (FP64 re-run).
 constexpr int OP_THREADS = 256;
 constexpr int OP_WARPS = OP_THREADS / 32;
+constexpr int OP_SMAP_THREADS = 512; // one CTA per SM: 16 warps' buffers (80 KB) + the map table (120 KB for 30k genes), 128 registers
 constexpr int OP_CAP = 640;  // ranks a warp stages ({sum, bin}: 8 bytes each)
 constexpr int OP_EPL = 8;
 constexpr int OP_TILE = 32 * OP_EPL;
@@ -806,24 +809,38 @@ __device__ __forceinline__ int warp_incl_max_nt(int v)
 
 // row indices of this lane's eight entries and their packed map words.  Outside the column:
 // -1 in front of it, INT_MAX behind it (so that "ascending" can be tested on all eight), word 0.
-__device__ __forceinline__ void op_tile_words(const int32_t *__restrict__ rowidx, const uint32_t *__restrict__ gmap,
-                                              int64_t gb, int64_t e0, int64_t e1, bool last_use, int (&g)[8],
-                                              uint32_t (&w)[8])
+// row indices of this lane's eight entries: -1 in front of the column, INT_MAX behind it.  A group
+// that straddles an end of the column is still one 256-bit load when it lies inside the array
+// (`total` entries): the neighbours' entries it brings along are masked out.
+template <bool EDGE>
+__device__ __forceinline__ void op_load_rows(const int32_t *__restrict__ rowidx, int64_t gb, int64_t e0, int64_t e1,
+                                             int64_t total, bool last_use, int (&g)[8])
 {
     if (gb >= e0 && gb + OP_EPL <= e1) {
         op_load_g8(rowidx + gb, g, last_use);
+    } else if (EDGE && gb < e1 && gb + OP_EPL > e0 && gb + OP_EPL <= total) {
+        op_load_g8(rowidx + gb, g, false);
 #pragma unroll
-        for (int i = 0; i < OP_EPL; i++) w[i] = __ldg(gmap + g[i]);
+        for (int i = 0; i < OP_EPL; i++) g[i] = gb + i < e0 ? -1 : (gb + i >= e1 ? INT_MAX : g[i]);
     } else {
 #pragma unroll
         for (int i = 0; i < OP_EPL; i++) {
             const bool in = gb + i >= e0 && gb + i < e1;
             g[i] = in ? __ldg(rowidx + gb + i) : (gb + i < e0 ? -1 : INT_MAX);
-            w[i] = in ? __ldg(gmap + g[i]) : 0u;
         }
     }
 }
-
+__device__ __forceinline__ void op_load_x4_keep(const double *__restrict__ p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// SMAP: the map words come from the CTA's shared-memory copy of the table (no L1 / L2 round trip)
+template <bool SMAP>
+__device__ __forceinline__ uint32_t op_map_word(const uint32_t *__restrict__ gmap, const uint32_t *s_gmap, int g)
+{
+    if (SMAP) return s_gmap[g];
+    return __ldg(gmap + g);
+}
 // the staging buffer by 32-bit shared address ({sum, bin} pairs of 8 bytes)
 __device__ __forceinline__ void op_st_pair_if(int cond_gt, int than, unsigned addr, int sum, int bin)
 {
@@ -844,64 +861,120 @@ __device__ __forceinline__ void op_ld_pair(unsigned addr, int &sum, int &bin)
     asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(sum), "=r"(bin) : "r"(addr) : "memory");
 }
 
-template <int CTAS_PER_SM>
-__global__ void __launch_bounds__(OP_THREADS, CTAS_PER_SM)
-bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+// the packed map words of eight rows (0 for the sentinels outside the column and for rows outside the table)
+template <bool SMAP>
+__device__ __forceinline__ void op_words_of(const uint32_t *__restrict__ gmap, const uint32_t *s_gmap, int G,
+                                            const int (&g)[8], uint32_t (&w)[8])
+{
+#pragma unroll
+    for (int i = 0; i < OP_EPL; i++) w[i] = ((unsigned)g[i] < (unsigned)G) ? op_map_word<SMAP>(gmap, s_gmap, g[i]) : 0u;
+}
+
+// THREADS x CTAS_PER_SM: 256 x {2,3,4} with the map read through L1, or — SMAP — one CTA of
+// OP_SMAP_THREADS per SM that holds the whole map table in shared memory next to its warps' buffers
+// OPT: 1 = count the next column before filling this one, 2 = rows of the next tile in flight during
+// the fill, 4 = 256-bit loads on tiles that straddle a column end, 8 = four predicated stores per
+// entry, 16 = rows two tiles ahead in the count pass
+template <int THREADS, int CTAS_PER_SM, bool SMAP, int OPT>
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
+bin_onepass_kernel(int N, int G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                    const double *__restrict__ x, const uint32_t *__restrict__ gmap,
                    int64_t *__restrict__ out_colptr, int32_t *__restrict__ out_rowidx, double *__restrict__ out_x,
                    int64_t out_cap, int do_fill, unsigned long long *__restrict__ status, int *__restrict__ ticket,
                    int *__restrict__ counts_actual, int *__restrict__ flags)
 {
-    __shared__ int2 s_buf_all[OP_WARPS][OP_CAP];
+    extern __shared__ __align__(16) unsigned char s_op_raw[];
+    int2 *s_buf_all = reinterpret_cast<int2 *>(s_op_raw);
+    const uint32_t *s_gmap = reinterpret_cast<const uint32_t *>(s_op_raw + (size_t)(THREADS / 32) * OP_CAP * sizeof(int2));
+    if (SMAP) {
+        uint32_t *dst = const_cast<uint32_t *>(s_gmap);
+        for (int i = threadIdx.x; i < G; i += THREADS) dst[i] = __ldg(gmap + i);
+        __syncthreads();
+    }
+    constexpr bool PIPE = (OPT & 1) != 0, FILLPF = (OPT & 2) != 0, EDGE = (OPT & 4) != 0, ST4 = (OPT & 8) != 0,
+                   DEPTH2 = (OPT & 16) != 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned buf = (unsigned)__cvta_generic_to_shared(&s_buf_all[wid][0]);
+    const unsigned buf = (unsigned)__cvta_generic_to_shared(s_buf_all + (size_t)wid * OP_CAP);
+    __shared__ long long s_total; // entries in the whole matrix (read back where a tile straddles a column end)
+    if (threadIdx.x == 0) s_total = colptr[N];
+    __syncthreads();
+#define total ((int64_t)s_total)
     bool inexact = false, irregular = false;
 
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(ticket, 1);
-        c = __shfl_sync(CS_FULL, c, 0);
-        if (c >= N) break;
-        const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+    auto take_ticket = [&]() {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1);
+        return __shfl_sync(CS_FULL, t, 0);
+    };
+    // ---------------- count: number of distinct bins column [e0, e1) touches; published at once
+    // (rows two tiles ahead are in flight in registers, three tiles ahead on their way into L2)
+    auto count_column = [&](int col, int64_t e0, int64_t e1) {
         const int64_t tb = e0 & ~(int64_t)(OP_EPL - 1);
-        // ---------------- count: number of distinct bins the column touches
-        int cnt = 0;
-        {
-            int carryM = 0, carryG = -1;
-            for (int64_t t0 = tb; t0 < e1; t0 += OP_TILE) {
-                int g[OP_EPL];
-                uint32_t w[OP_EPL];
-                if (lane < 8 && t0 + OP_TILE + 32 * lane < e1) op_prefetch_l2(rowidx + t0 + OP_TILE + 32 * lane);
-                op_tile_words(rowidx, gmap, t0 + OP_EPL * lane, e0, e1, !do_fill, g, w);
-                int before = __shfl_up_sync(CS_FULL, g[OP_EPL - 1], 1);
-                if (lane == 0) before = carryG;
-                bool bad = g[0] < before; // (row indices must ascend)
-                int lmax = 0;
+        int cnt = 0, carryM = 0, carryG = -1;
+        int gn[OP_EPL], gn2[OP_EPL];
+        op_load_rows<EDGE>(rowidx, tb + OP_EPL * lane, e0, e1, total, !do_fill, gn);
+        if (DEPTH2 && tb + OP_TILE < e1) op_load_rows<EDGE>(rowidx, tb + OP_TILE + OP_EPL * lane, e0, e1, total, !do_fill, gn2);
+        for (int64_t t0 = tb; t0 < e1; t0 += OP_TILE) {
+            int g[OP_EPL];
+            uint32_t w[OP_EPL];
 #pragma unroll
-                for (int i = 0; i < OP_EPL; i++) {
-                    lmax = max(lmax, (int)(w[i] & 0xFFFFF) + (int)(w[i] >> 20));
-                    if (i) bad |= g[i] < g[i - 1];
-                }
-                irregular |= bad;
-                carryG = __shfl_sync(CS_FULL, g[OP_EPL - 1], 31);
-                const int incl = warp_incl_max_nt(lmax);
-                int m = __shfl_up_sync(CS_FULL, incl, 1);
-                if (lane == 0) m = 0;
-                m = max(m, carryM);
-#pragma unroll
-                for (int i = 0; i < OP_EPL; i++) {
-                    const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
-                    cnt += max(0, e - max(f, m));
-                    m = max(m, e);
-                }
-                carryM = max(carryM, __shfl_sync(CS_FULL, incl, 31));
+            for (int i = 0; i < OP_EPL; i++) {
+                g[i] = gn[i];
+                if (DEPTH2) gn[i] = gn2[i];
             }
-            cnt = (int)__reduce_add_sync(CS_FULL, (unsigned)cnt);
+            if (lane < 8 && t0 + 3 * OP_TILE + 32 * lane < e1) op_prefetch_l2(rowidx + t0 + 3 * OP_TILE + 32 * lane);
+            if (DEPTH2) {
+                if (t0 + 2 * OP_TILE < e1) op_load_rows<EDGE>(rowidx, t0 + 2 * OP_TILE + OP_EPL * lane, e0, e1, total, !do_fill, gn2);
+            } else {
+                if (t0 + OP_TILE < e1) op_load_rows<EDGE>(rowidx, t0 + OP_TILE + OP_EPL * lane, e0, e1, total, !do_fill, gn);
+            }
+            op_words_of<SMAP>(gmap, s_gmap, G, g, w);
+            int before = __shfl_up_sync(CS_FULL, g[OP_EPL - 1], 1);
+            if (lane == 0) before = carryG;
+            bool bad = g[0] < before; // (row indices must ascend)
+            int lmax = 0;
+#pragma unroll
+            for (int i = 0; i < OP_EPL; i++) {
+                lmax = max(lmax, (int)(w[i] & 0xFFFFF) + (int)(w[i] >> 20));
+                if (i) bad |= g[i] < g[i - 1];
+            }
+            irregular |= bad;
+            carryG = __shfl_sync(CS_FULL, g[OP_EPL - 1], 31);
+            const int incl = warp_incl_max_nt(lmax);
+            int m = __shfl_up_sync(CS_FULL, incl, 1);
+            if (lane == 0) m = 0;
+            m = max(m, carryM);
+#pragma unroll
+            for (int i = 0; i < OP_EPL; i++) {
+                const int f = (int)(w[i] & 0xFFFFF), e = f + (int)(w[i] >> 20);
+                cnt += max(0, e - max(f, m));
+                m = max(m, e);
+            }
+            carryM = max(carryM, __shfl_sync(CS_FULL, incl, 31));
         }
-        // ---------------- the column's offset: publish the count now; the prefix over the columns in
-        // front is collected (look-back) only when the first ranks are about to be written, by
-        // which time the columns handed out just before this one have published theirs as well
-        if (lane == 0) op_st_status(status + c, OP_FLAG_A | (unsigned long long)cnt);
+        cnt = (int)__reduce_add_sync(CS_FULL, (unsigned)cnt);
+        if (lane == 0) op_st_status(status + col, OP_FLAG_A | (unsigned long long)cnt);
+        return cnt;
+    };
+
+    // Columns are handed out by a ticket.  A warp counts (and publishes) its NEXT column before it
+    // fills the current one: by the time the fill needs the prefix over the columns in front
+    // (look-back, at its first write-out) every warp that holds one of them has long published it.
+    int c = take_ticket();
+    int64_t e0 = 0, e1 = 0;
+    int cnt = 0;
+    if (c < N) {
+        e0 = colptr[c];
+        e1 = colptr[c + 1];
+        cnt = count_column(c, e0, e1);
+    }
+    while (c < N) {
+        int cn = N, ncnt = 0; // (only these two stay live across the fill: the bounds are read again)
+        if (PIPE && do_fill) {
+            cn = take_ticket();
+            if (cn < N) ncnt = count_column(cn, colptr[cn], colptr[cn + 1]);
+        }
+        const int64_t tb = e0 & ~(int64_t)(OP_EPL - 1);
         long long excl = 0;
         auto look_back = [&]() {
             int j = c - 1;
@@ -932,6 +1005,12 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
         };
         if (!do_fill) {
             look_back();
+            c = take_ticket();
+            if (c < N) {
+                e0 = colptr[c];
+                e1 = colptr[c + 1];
+                cnt = count_column(c, e0, e1);
+            }
             continue;
         }
         // ---------------- fill
@@ -974,34 +1053,36 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
             __syncwarp();
             held = rem;
         };
+        int gn[OP_EPL]; // the next tile's rows, in flight while this one is worked on
+        if (FILLPF) op_load_rows<EDGE>(rowidx, tb + OP_EPL * lane, e0, e1, total, true, gn);
         for (int64_t t0 = tb; t0 < e1 && !skip; t0 += OP_TILE) {
             const int64_t gb = t0 + OP_EPL * lane;
             int g[OP_EPL], iv[OP_EPL];
             uint32_t w[OP_EPL];
-            if (lane < 16 && t0 + OP_TILE + 16 * lane < e1) op_prefetch_l2(x + t0 + OP_TILE + 16 * lane);
-            op_tile_words(rowidx, gmap, gb, e0, e1, true, g, w);
-            if (gb >= e0 && gb + OP_EPL <= e1) {
-                double v[OP_EPL];
+            double v[OP_EPL];
+            if (FILLPF) {
+#pragma unroll
+                for (int i = 0; i < OP_EPL; i++) g[i] = gn[i];
+            } else {
+                op_load_rows<EDGE>(rowidx, gb, e0, e1, total, true, g);
+            }
+            // this tile's values are asked for now and converted only when the placement needs them
+            const bool full = gb >= e0 && gb + OP_EPL <= e1;
+            if (full) {
                 op_load_x4(x + gb, v[0], v[1], v[2], v[3]);
                 op_load_x4(x + gb + 4, v[4], v[5], v[6], v[7]);
+            } else if (EDGE && gb < e1 && gb + OP_EPL > e0 && gb + OP_EPL <= total) { // (the neighbours' values are masked out)
+                op_load_x4_keep(x + gb, v[0], v[1], v[2], v[3]);
+                op_load_x4_keep(x + gb + 4, v[4], v[5], v[6], v[7]);
 #pragma unroll
-                for (int i = 0; i < OP_EPL; i++) {
-                    iv[i] = __double2int_rz(v[i]);
-                    inexact |= __int2double_rn(iv[i]) != v[i];
-                    orbits |= (unsigned)abs(iv[i]);
-                }
+                for (int i = 0; i < OP_EPL; i++) v[i] = (gb + i >= e0 && gb + i < e1) ? v[i] : 0.0;
             } else {
 #pragma unroll
-                for (int i = 0; i < OP_EPL; i++) {
-                    iv[i] = 0;
-                    if (gb + i >= e0 && gb + i < e1) {
-                        const double v = __ldcs(x + gb + i);
-                        iv[i] = __double2int_rz(v);
-                        inexact |= __int2double_rn(iv[i]) != v;
-                        orbits |= (unsigned)abs(iv[i]);
-                    }
-                }
+                for (int i = 0; i < OP_EPL; i++) v[i] = (gb + i >= e0 && gb + i < e1) ? __ldcs(x + gb + i) : 0.0;
             }
+            if (lane < 16 && t0 + 2 * OP_TILE + 16 * lane < e1) op_prefetch_l2(x + t0 + 2 * OP_TILE + 16 * lane);
+            if (FILLPF && t0 + OP_TILE < e1) op_load_rows<EDGE>(rowidx, gb + OP_TILE, e0, e1, total, true, gn);
+            op_words_of<SMAP>(gmap, s_gmap, G, g, w);
             // interval ends, first bins, the prefix max M in front of this lane's entries
             int lmax = 0, lf = 0;
 #pragma unroll
@@ -1034,6 +1115,12 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
                     break;
                 }
             }
+#pragma unroll
+            for (int i = 0; i < OP_EPL; i++) {
+                iv[i] = __double2int_rz(v[i]);
+                inexact |= __int2double_rn(iv[i]) != v[i];
+                orbits |= (unsigned)abs(iv[i]);
+            }
             // placement: new bins are stores at the lane's running address, the old part of an entry
             // (bins an earlier entry opened: ranks just below the running one) is remembered
             unsigned oa[OP_EPL];
@@ -1047,9 +1134,13 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
                     const int s = max(f, m), nn = e - s, old = min(e, m) - f;
                     op_st_pair_if(nn, 0, addr, iv[i], s);
                     op_st_pair_if(nn, 1, addr + 8u, iv[i], s + 1);
-                    if (nn > 2) {
+                    if (ST4) {
+                        op_st_pair_if(nn, 2, addr + 16u, iv[i], s + 2);
+                        op_st_pair_if(nn, 3, addr + 24u, iv[i], s + 3);
+                    }
+                    if (nn > (ST4 ? 4 : 2)) {
 #pragma unroll 1
-                        for (int k = 2; k < nn; k++) op_st_pair(addr + 8u * k, iv[i], s + k);
+                        for (int k = (ST4 ? 4 : 2); k < nn; k++) op_st_pair(addr + 8u * k, iv[i], s + k);
                     }
                     oa[i] = old > 0 ? addr - 8u * (unsigned)(m - f) : 0u;
                     multi |= old > 1;
@@ -1092,9 +1183,29 @@ bin_onepass_kernel(int N, const int64_t *__restrict__ colptr, const int32_t *__r
             const int bits = 32 - __clz(orbits);
             if (bits >= 31 || ((unsigned long long)(e1 - e0) << bits) > 2147483647ull) flags[FLAG_INEXACT] = 1;
         }
+        if (!PIPE) {
+            cn = take_ticket();
+            if (cn < N) ncnt = count_column(cn, colptr[cn], colptr[cn + 1]);
+        }
+        c = cn;
+        cnt = ncnt;
+        if (c < N) {
+            e0 = colptr[c];
+            e1 = colptr[c + 1];
+        }
     }
     if (inexact) flags[FLAG_INEXACT] = 1;
     if (irregular) flags[FLAG_IRREG] = 1;
+#undef total
+}
+
+constexpr int OP_DEFAULT_OPT = 11; // (measured: tools/sweep_binning.py)
+using op_kernel_t = decltype(&bin_onepass_kernel<OP_SMAP_THREADS, 1, true, 0>);
+template <int T, int... I>
+static op_kernel_t op_pick(int opt, std::integer_sequence<int, I...>)
+{
+    static const op_kernel_t table[] = {&bin_onepass_kernel<T, 1, true, I>...};
+    return table[opt];
 }
 
 // closes the gaps left by dropped zero sums: column c's first nwritten entries (all of its
@@ -1337,18 +1448,29 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         CS_CUDA(cudaMemsetAsync(p->status.p, 0, sizeof(unsigned long long) * (size_t)N, st));
         CS_CUDA(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
         // (CS_BIN_OP_CTAS = 2 | 3 | 4 CTAs per SM: registers per thread against warps in flight)
+        // (CS_BIN_OP_SMAP=0: the 256-thread CTAs that read the map through L1)
         int ctas = getenv("CS_BIN_OP_CTAS") ? atoi(getenv("CS_BIN_OP_CTAS")) : 3;
-        auto kern = ctas == 4 ? bin_onepass_kernel<4> : (ctas == 2 ? bin_onepass_kernel<2> : bin_onepass_kernel<3>);
+        int sthreads = getenv("CS_BIN_OP_SMAP_THREADS") ? atoi(getenv("CS_BIN_OP_SMAP_THREADS")) : OP_SMAP_THREADS;
+        if (sthreads != 384) sthreads = OP_SMAP_THREADS;
+        const size_t smap_bytes = (size_t)(sthreads / 32) * OP_CAP * sizeof(int2) + sizeof(uint32_t) * (size_t)p->G;
+        const bool smap = smap_bytes <= 227u * 1024u && !(getenv("CS_BIN_OP_SMAP") && atoi(getenv("CS_BIN_OP_SMAP")) == 0);
+        int opt = getenv("CS_BIN_OP_OPT") ? (atoi(getenv("CS_BIN_OP_OPT")) & 31) : OP_DEFAULT_OPT;
+        auto kern = smap ? (sthreads == 384 ? op_pick<384>(opt, std::make_integer_sequence<int, 32>{})
+                                            : op_pick<OP_SMAP_THREADS>(opt, std::make_integer_sequence<int, 32>{}))
+                         : (ctas == 2 ? bin_onepass_kernel<OP_THREADS, 2, false, 2> : bin_onepass_kernel<OP_THREADS, 3, false, 2>);
+        const int threads = smap ? sthreads : OP_THREADS;
+        const size_t smem = smap ? smap_bytes : (size_t)OP_WARPS * OP_CAP * sizeof(int2);
+        CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OP_THREADS, 0));
+        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         if (per_sm < 1) per_sm = 1;
         int grid = cs_num_sms() * per_sm;
-        if (grid > (N + OP_WARPS - 1) / OP_WARPS) grid = (N + OP_WARPS - 1) / OP_WARPS;
+        if (grid > (N + threads / 32 - 1) / (threads / 32)) grid = (N + threads / 32 - 1) / (threads / 32);
         p->timed = false;
         CS_CUDA(cudaEventRecord(p->ev[0], st));
         CS_CUDA(cudaEventRecord(p->ev[1], st));
         CS_CUDA(cudaEventRecord(p->ev[2], st));
-        kern<<<grid, OP_THREADS, 0, st>>>(N, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr, d_out_rowidx, d_out_x, out_cap,
+        kern<<<grid, threads, smem, st>>>(N, p->G, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr, d_out_rowidx, d_out_x, out_cap,
                                           d_out_rowidx ? 1 : 0, p->status.p, p->ticket.p, p->counts2.p, p->flags.p);
         CS_CUDA(cudaGetLastError());
         CS_CUDA(cudaEventRecord(p->ev[3], st));
