@@ -768,8 +768,8 @@ __device__ __forceinline__ void op_load_g8(const int32_t *__restrict__ p, int (&
         asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]), "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7])
                      : "l"(p));
-    else
-        asm volatile("ld.global.nc.L1::no_allocate.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    else // (read again by the fill a column later: keep the line in L2)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]), "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7])
                      : "l"(p));
 }
@@ -823,10 +823,12 @@ __device__ __forceinline__ void op_load_rows(const int32_t *__restrict__ rowidx,
 #pragma unroll
         for (int i = 0; i < OP_EPL; i++) g[i] = gb + i < e0 ? -1 : (gb + i >= e1 ? INT_MAX : g[i]);
     } else {
+        // (predicated loads straight into the registers: nothing waits for them here)
 #pragma unroll
         for (int i = 0; i < OP_EPL; i++) {
-            const bool in = gb + i >= e0 && gb + i < e1;
-            g[i] = in ? __ldg(rowidx + gb + i) : (gb + i < e0 ? -1 : INT_MAX);
+            g[i] = gb + i < e0 ? -1 : INT_MAX;
+            if (gb + i >= e0 && gb + i < e1)
+                asm volatile("ld.global.nc.s32 %0, [%1];" : "+r"(g[i]) : "l"(rowidx + gb + i));
         }
     }
 }
@@ -874,7 +876,7 @@ __device__ __forceinline__ void op_words_of(const uint32_t *__restrict__ gmap, c
 // OP_SMAP_THREADS per SM that holds the whole map table in shared memory next to its warps' buffers
 // OPT: 1 = count the next column before filling this one, 2 = rows of the next tile in flight during
 // the fill, 4 = 256-bit loads on tiles that straddle a column end, 8 = four predicated stores per
-// entry, 16 = rows two tiles ahead in the count pass
+// entry, 16 = the next tile's values prefetched into L1 (instead of two tiles ahead into L2)
 template <int THREADS, int CTAS_PER_SM, bool SMAP, int OPT>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 bin_onepass_kernel(int N, int G, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
@@ -892,7 +894,7 @@ bin_onepass_kernel(int N, int G, const int64_t *__restrict__ colptr, const int32
         __syncthreads();
     }
     constexpr bool PIPE = (OPT & 1) != 0, FILLPF = (OPT & 2) != 0, EDGE = (OPT & 4) != 0, ST4 = (OPT & 8) != 0,
-                   DEPTH2 = (OPT & 16) != 0;
+                   XL1 = (OPT & 16) != 0, DEPTH2 = false;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned buf = (unsigned)__cvta_generic_to_shared(s_buf_all + (size_t)wid * OP_CAP);
     __shared__ long long s_total; // entries in the whole matrix (read back where a tile straddles a column end)
@@ -1078,9 +1080,16 @@ bin_onepass_kernel(int N, int G, const int64_t *__restrict__ colptr, const int32
                 for (int i = 0; i < OP_EPL; i++) v[i] = (gb + i >= e0 && gb + i < e1) ? v[i] : 0.0;
             } else {
 #pragma unroll
-                for (int i = 0; i < OP_EPL; i++) v[i] = (gb + i >= e0 && gb + i < e1) ? __ldcs(x + gb + i) : 0.0;
+                for (int i = 0; i < OP_EPL; i++) {
+                    v[i] = 0.0;
+                    if (gb + i >= e0 && gb + i < e1) asm volatile("ld.global.cs.f64 %0, [%1];" : "+d"(v[i]) : "l"(x + gb + i));
+                }
             }
-            if (lane < 16 && t0 + 2 * OP_TILE + 16 * lane < e1) op_prefetch_l2(x + t0 + 2 * OP_TILE + 16 * lane);
+            if (XL1) {
+                if (lane < 16 && t0 + OP_TILE + 16 * lane < e1) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + t0 + OP_TILE + 16 * lane));
+            } else {
+                if (lane < 16 && t0 + 2 * OP_TILE + 16 * lane < e1) op_prefetch_l2(x + t0 + 2 * OP_TILE + 16 * lane);
+            }
             if (FILLPF && t0 + OP_TILE < e1) op_load_rows<EDGE>(rowidx, gb + OP_TILE, e0, e1, total, true, gn);
             op_words_of<SMAP>(gmap, s_gmap, G, g, w);
             // interval ends, first bins, the prefix max M in front of this lane's entries

@@ -19,6 +19,8 @@
 #include "cs_gibbs.cuh"
 #include "cs_rstream.cuh"
 
+#include <math_constants.h>
+
 namespace {
 
 constexpr int RT = 256; // threads of the persistent CTA
@@ -53,11 +55,58 @@ __device__ double cell_loglik(int R, const double *x, const double *u, const dou
     return s;
 }
 
+// ---- the pooled stream (POOL): the uniforms of the current and of the next Mersenne-Twister block
+// (624 each) lie tempered in shared memory, so that any thread can read the k-th upcoming draw
+// (k < 624).  The stream is still consumed in base R's order: only WHO reads a draw changes.
+struct RPool {
+    uint32_t *raw[2]; // raw[cur]: the state R would hold now; raw[cur ^ 1]: after its next refill
+    double *uu[2];    // their tempered outputs as unif_rand() returns them
+};
+
+__device__ __forceinline__ double mt_temper(uint32_t y)
+{
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    const double v = (double)y * 2.3283064365386963e-10;
+    if (v <= 0.0) return 0.5 * 2.328306437080797e-10;
+    if (1.0 - v <= 0.0) return 1.0 - 0.5 * 2.328306437080797e-10;
+    return v;
+}
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t m)
+{
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// B = refill(A) by all threads (three dependent phases of <= 227 words), then both blocks tempered
+__device__ void pool_build(const RPool &P, int cur, bool temper_cur)
+{
+    const uint32_t *A = P.raw[cur];
+    uint32_t *B = P.raw[cur ^ 1];
+    const int tid = threadIdx.x;
+    if (temper_cur)
+        for (int k = tid; k < 624; k += RT) P.uu[cur][k] = mt_temper(A[k]);
+    for (int k = tid; k < 227; k += RT) B[k] = mt_twist(A[k], A[k + 1], A[k + 397]);
+    __syncthreads();
+    for (int k = 227 + tid; k < 454; k += RT) B[k] = mt_twist(A[k], A[k + 1], B[k - 227]);
+    __syncthreads();
+    for (int k = 454 + tid; k < 623; k += RT) B[k] = mt_twist(A[k], A[k + 1], B[k - 227]);
+    if (tid == 0) B[623] = mt_twist(A[623], B[0], B[396]);
+    __syncthreads();
+    for (int k = tid; k < 624; k += RT) P.uu[cur ^ 1][k] = mt_temper(B[k]);
+    __syncthreads();
+}
+
+template <bool POOL>
 __global__ void __launch_bounds__(RT)
 gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__restrict__ scratch)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     RShared S;
+    RPool P;
+    double *s_logsig, *s_term; // POOL: log(sigma) per segment; one row of terms per warp
+    int *s_ind;
     {
         double *d = reinterpret_cast<double *>(s_raw);
         S.cumc = d; d += lcap + 1;
@@ -65,13 +114,21 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
         S.xrow = d; d += D.R;
         S.mu = d; d += D.R;
         S.sig = d; d += D.R;
+        s_logsig = d; d += POOL ? D.R : 0;
+        s_term = d; d += POOL ? (RT / 32) * D.R : 0;
+        P.uu[0] = d; d += POOL ? 624 : 0;
+        P.uu[1] = d; d += POOL ? 624 : 0;
         int *p = reinterpret_cast<int *>(d);
         S.permc = p; p += lcap + 1;
         S.perm = p; p += lcap + 1;
         S.np = p; p += lcap;
         S.occ = p; p += lcap;
+        s_ind = p; p += POOL ? D.R : 0;
         S.mt = reinterpret_cast<uint32_t *>(p);
+        P.raw[0] = S.mt;
+        P.raw[1] = S.mt + 624;
     }
+    __shared__ int s_cur, s_flip;
     __shared__ int s_kt, s_nocc, s_pos, s_prop_valid, s_err, s_z, s_new;
     __shared__ long long s_rej, s_uused;
     __shared__ double s_red[RT];
@@ -87,6 +144,8 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
         s_err = 0;
         s_rej = 0;
         s_uused = D.scal->u_used;
+        s_cur = 0;
+        s_flip = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -95,7 +154,30 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
             if (S.np[k] > 0) S.occ[n++] = k;
         s_nocc = n;
     }
+    if (POOL) {
+        for (int r = tid; r < R; r += RT) s_logsig[r] = log(S.sig[r]);
+        pool_build(P, 0, true);
+    }
     __syncthreads();
+    // the k-th upcoming uniform (k < 624) and the uniform advance of the stream by n draws
+    auto upcoming = [&](int k) {
+        const int idx = s_pos + k;
+        return idx < 624 ? P.uu[s_cur][idx] : P.uu[s_cur ^ 1][idx - 624];
+    };
+    auto advance = [&](int n) { // (called by all threads, between barriers)
+        __syncthreads();
+        if (tid == 0) {
+            s_pos += n;
+            s_flip = 0;
+            if (s_pos > 624) { // the current block is used up: the next one becomes current
+                s_pos -= 624;
+                s_cur ^= 1;
+                s_flip = 1;
+            }
+        }
+        __syncthreads();
+        if (s_flip) pool_build(P, s_cur, false);
+    };
 
     for (int tt = t0; tt < t1 && !s_err; tt++) {
         const bool reject_live = D.single && tt == 0;
@@ -119,6 +201,24 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
                         for (int k = 1; k <= kt; k++) S.cumc[k] += S.cumc[k - 1];
                         s_prop_valid = 1;
                     }
+                }
+                if (POOL) {
+                    // draws 2r and 2r + 1 of this attempt belong to segment r: every segment at once
+                    __syncthreads();
+                    for (int r = tid; r < R; r += RT) {
+                        const double tmpr = 0.3 + (2.5 - 0.3) * upcoming(2 * r);
+                        const double u = upcoming(2 * r + 1);
+                        int lo = 0, hi = kt; // first j with u <= cumc[j] (cumc does not decrease), else kt
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (u > S.cumc[mid]) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        const int indr = S.permc[lo];
+                        S.mu[r] = (indr <= kt) ? D.U[(size_t)(indr - 1) * R + r] : tmpr;
+                    }
+                    advance(2 * R);
+                } else if (tid == 0) {
                     int pos = s_pos;
                     for (int r = 0; r < R; r++) {
                         const double tmpr = 0.3 + (2.5 - 0.3) * unif_rand(S.mt, pos);
@@ -150,32 +250,98 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
             if (tid == 0) S.np[zold] -= 1;
             __syncthreads();
             const int nocc = s_nocc;
-            for (int e = tid; e <= nocc; e += RT) {
-                if (e < nocc) {
-                    const int k = S.occ[e];
-                    const int n = S.np[k];
-                    S.prob[e] = (n != 0) ? cell_loglik(R, S.xrow, D.U + (size_t)k * R, S.sig) + log((double)n)
-                                         : -INFINITY;
-                } else {
-                    S.prob[e] = cell_loglik(R, S.xrow, S.mu, S.sig) + log(D.beta);
+            if (POOL) {
+                // a warp per candidate: the terms of all segments at once, then their sum in segment
+                // order by one lane (the order the serial code adds them in)
+                const int lane = tid & 31, wid = tid >> 5;
+                double *term = s_term + (size_t)wid * R;
+                for (int e = wid; e <= nocc; e += RT / 32) {
+                    const int k = e < nocc ? S.occ[e] : -1;
+                    const int n = e < nocc ? S.np[k] : 1;
+                    if (n != 0) {
+                        const double *u = e < nocc ? D.U + (size_t)k * R : S.mu;
+                        for (int r = lane; r < R; r += 32) {
+                            const double xv = S.xrow[r];
+                            double t = CUDART_NAN;
+                            if (!cs_isna(xv)) {
+                                const double z = fabs((xv - u[r]) / S.sig[r]);
+                                t = -(CS_LN_SQRT_2PI + 0.5 * z * z + s_logsig[r]);
+                            }
+                            term[r] = t;
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            double acc = 0.0;
+                            for (int r = 0; r < R; r++) {
+                                const double t = term[r];
+                                if (!cs_isna(t)) acc += t;
+                            }
+                            S.prob[e] = acc + log(e < nocc ? (double)n : D.beta);
+                        }
+                        __syncwarp();
+                    } else if (lane == 0) {
+                        S.prob[e] = -INFINITY;
+                    }
+                }
+            } else {
+                for (int e = tid; e <= nocc; e += RT) {
+                    if (e < nocc) {
+                        const int k = S.occ[e];
+                        const int n = S.np[k];
+                        S.prob[e] = (n != 0) ? cell_loglik(R, S.xrow, D.U + (size_t)k * R, S.sig) + log((double)n)
+                                             : -INFINITY;
+                    } else {
+                        S.prob[e] = cell_loglik(R, S.xrow, S.mu, S.sig) + log(D.beta);
+                    }
                 }
             }
             __syncthreads();
-            // ---- :200-207 categorical draw (thread 0)
+            // ---- :200-207 categorical draw
+            if (POOL) { // the maximum and the exponentials by all threads; the sum in order by thread 0 below
+                double mx = -INFINITY;
+                for (int e = tid; e <= nocc; e += RT)
+                    if (e == nocc || S.np[S.occ[e]] != 0) mx = fmax(mx, S.prob[e]);
+                s_red[tid] = mx;
+                __syncthreads();
+                for (int off = RT / 2; off >= 1; off >>= 1) {
+                    if (tid < off) s_red[tid] = fmax(s_red[tid], s_red[tid + off]);
+                    __syncthreads();
+                }
+                mx = s_red[0];
+                __syncthreads();
+                for (int e = tid; e <= nocc; e += RT)
+                    S.prob[e] = (e == nocc || S.np[S.occ[e]] != 0) ? exp(S.prob[e] - mx) : 0.0;
+                __syncthreads();
+                if (tid == 0) {
+                    double sum = 0.0;
+                    for (int e = 0; e <= nocc; e++)
+                        if (S.prob[e] > 0) sum += S.prob[e];
+                    s_red[0] = sum;
+                }
+                __syncthreads();
+                const double sum = s_red[0];
+                for (int e = tid; e <= nocc; e += RT) S.prob[e] /= sum;
+                __syncthreads();
+            }
             if (tid == 0) {
                 int pos = s_pos;
-                double mx = -INFINITY;
-                for (int e = 0; e <= nocc; e++)
-                    if (e == nocc || S.np[S.occ[e]] != 0) mx = fmax(mx, S.prob[e]);
-                double sum = 0.0;
-                for (int e = 0; e <= nocc; e++) {
-                    const double p = (e == nocc || S.np[S.occ[e]] != 0) ? exp(S.prob[e] - mx) : 0.0;
-                    S.prob[e] = p;
-                    if (p > 0) sum += p;
+                double u;
+                if (POOL) {
+                    u = upcoming(0);
+                } else {
+                    double mx = -INFINITY;
+                    for (int e = 0; e <= nocc; e++)
+                        if (e == nocc || S.np[S.occ[e]] != 0) mx = fmax(mx, S.prob[e]);
+                    double sum = 0.0;
+                    for (int e = 0; e <= nocc; e++) {
+                        const double p = (e == nocc || S.np[S.occ[e]] != 0) ? exp(S.prob[e] - mx) : 0.0;
+                        S.prob[e] = p;
+                        if (p > 0) sum += p;
+                    }
+                    for (int e = 0; e <= nocc; e++) S.prob[e] /= sum;
+                    u = unif_rand(S.mt, pos);
+                    s_pos = pos;
                 }
-                for (int e = 0; e <= nocc; e++) S.prob[e] /= sum;
-                const double u = unif_rand(S.mt, pos);
-                s_pos = pos;
                 // walk candidates in descending order; perm[] marks the ones already taken
                 int z = -1;
                 {
@@ -245,6 +411,7 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
                 D.Zs[ii] = z;
                 s_z = z;
             }
+            if (POOL) advance(1);
             __syncthreads();
             if (s_new) {
                 double *urow = D.U + (size_t)(s_z - 1) * R;
@@ -292,13 +459,14 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
                     }
                     const double sq = sqrt((double)S.np[k]);
                     for (int r = 0; r < R; r++) {
-                        const double v = rnorm_r(S.mt, pos, m[r], S.sig[r] / sq);
+                        const double v = rnorm_r(POOL ? P.raw[s_cur] : S.mt, pos, m[r], S.sig[r] / sq);
                         u[r] = (v < 0.0) ? 0.0 : v;
                     }
                 }
                 s_pos = pos;
             }
             __syncthreads();
+            if (POOL && pass == 0) pool_build(P, s_cur, true); // (the serial draws above moved the raw state)
             if (pass == 0 && last) continue;
             // sigmas (:234 / :269)
             for (int r = tid; r < R; r += RT) {
@@ -312,6 +480,7 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
                     if (!cs_isna(d)) s += d * d;
                 }
                 S.sig[r] = sqrt((1.0 / (double)c) * s);
+                if (POOL) s_logsig[r] = log(S.sig[r]);
             }
             __syncthreads();
         }
@@ -350,7 +519,7 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
         D.sig[r] = S.sig[r];
         D.isig[r] = 1.0 / S.sig[r];
     }
-    for (int k = tid; k < 624; k += RT) D.mt[k] = S.mt[k];
+    for (int k = tid; k < 624; k += RT) D.mt[k] = POOL ? P.raw[s_cur][k] : S.mt[k];
     if (tid == 0) {
         D.scal->kt = s_kt;
         D.scal->mt_pos = s_pos;
@@ -362,22 +531,30 @@ gibbs_r_kernel(ChainDev D, int lcap, int t0, int t1, int last_sweep, double *__r
 
 } // namespace
 
-size_t cs_rmode_smem_bytes(int lcap, int R)
+static size_t rmode_smem(int lcap, int R, bool pool)
 {
-    return sizeof(double) * (2 * ((size_t)lcap + 1) + 3 * (size_t)R) + sizeof(int) * (2 * ((size_t)lcap + 1) + 2 * (size_t)lcap) +
-           sizeof(uint32_t) * 624 + 64;
+    size_t b = sizeof(double) * (2 * ((size_t)lcap + 1) + 3 * (size_t)R) + sizeof(int) * (2 * ((size_t)lcap + 1) + 2 * (size_t)lcap) +
+               sizeof(uint32_t) * 624 + 64;
+    if (pool) b += sizeof(double) * ((size_t)R + (size_t)(RT / 32) * R + 2 * 624) + sizeof(int) * (size_t)R + sizeof(uint32_t) * 624;
+    return b;
 }
+size_t cs_rmode_smem_bytes(int lcap, int R) { return rmode_smem(lcap, R, false); }
 
-// sweeps [t0, t1) of the R-compatible chain; last_sweep = index of the run's final sweep
+// sweeps [t0, t1) of the R-compatible chain; last_sweep = index of the run's final sweep.  The pooled
+// kernel needs the 2R + 1 draws of a cell inside two Mersenne-Twister blocks (R <= 311) and room in
+// shared memory; otherwise (or with CS_RMODE_POOL=0) thread 0 walks the stream draw by draw.
 int cs_rmode_run(const ChainDev &D, int lcap, int t0, int t1, int last_sweep, double *scratch, cudaStream_t st)
 {
-    const size_t smem = cs_rmode_smem_bytes(lcap, D.R);
+    const bool want_pool = !(getenv("CS_RMODE_POOL") && atoi(getenv("CS_RMODE_POOL")) == 0);
+    const bool pool = want_pool && 2 * D.R + 1 < 624 && rmode_smem(lcap, D.R, true) <= 227 * 1024;
+    const size_t smem = rmode_smem(lcap, D.R, pool);
     if (smem > 227 * 1024) {
         cs_set_error("R-compatible sampler: label capacity %d with R=%d needs %zu B of shared memory", lcap, D.R, smem);
         return CS_ERR_UNSUPPORTED;
     }
-    CS_CUDA(cudaFuncSetAttribute(gibbs_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gibbs_r_kernel<<<1, RT, smem, st>>>(D, lcap, t0, t1, last_sweep, scratch);
+    auto kern = pool ? gibbs_r_kernel<true> : gibbs_r_kernel<false>;
+    CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, RT, smem, st>>>(D, lcap, t0, t1, last_sweep, scratch);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
