@@ -768,8 +768,8 @@ __device__ __forceinline__ void op_load_g8(const int32_t *__restrict__ p, int (&
         asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]), "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7])
                      : "l"(p));
-    else // (read again by the fill a column later: keep the line in L2)
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]), "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7])
                      : "l"(p));
 }
@@ -1459,13 +1459,11 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         // (CS_BIN_OP_CTAS = 2 | 3 | 4 CTAs per SM: registers per thread against warps in flight)
         // (CS_BIN_OP_SMAP=0: the 256-thread CTAs that read the map through L1)
         int ctas = getenv("CS_BIN_OP_CTAS") ? atoi(getenv("CS_BIN_OP_CTAS")) : 3;
-        int sthreads = getenv("CS_BIN_OP_SMAP_THREADS") ? atoi(getenv("CS_BIN_OP_SMAP_THREADS")) : OP_SMAP_THREADS;
-        if (sthreads != 384) sthreads = OP_SMAP_THREADS;
+        const int sthreads = OP_SMAP_THREADS;
         const size_t smap_bytes = (size_t)(sthreads / 32) * OP_CAP * sizeof(int2) + sizeof(uint32_t) * (size_t)p->G;
         const bool smap = smap_bytes <= 227u * 1024u && !(getenv("CS_BIN_OP_SMAP") && atoi(getenv("CS_BIN_OP_SMAP")) == 0);
         int opt = getenv("CS_BIN_OP_OPT") ? (atoi(getenv("CS_BIN_OP_OPT")) & 31) : OP_DEFAULT_OPT;
-        auto kern = smap ? (sthreads == 384 ? op_pick<384>(opt, std::make_integer_sequence<int, 32>{})
-                                            : op_pick<OP_SMAP_THREADS>(opt, std::make_integer_sequence<int, 32>{}))
+        auto kern = smap ? op_pick<OP_SMAP_THREADS>(opt, std::make_integer_sequence<int, 32>{})
                          : (ctas == 2 ? bin_onepass_kernel<OP_THREADS, 2, false, 2> : bin_onepass_kernel<OP_THREADS, 3, false, 2>);
         const int threads = smap ? sthreads : OP_THREADS;
         const size_t smem = smap ? smap_bytes : (size_t)OP_WARPS * OP_CAP * sizeof(int2);
