@@ -883,7 +883,7 @@ bin_onepass_kernel(int N, int G, const int64_t *__restrict__ colptr, const int32
                    const double *__restrict__ x, const uint32_t *__restrict__ gmap,
                    int64_t *__restrict__ out_colptr, int32_t *__restrict__ out_rowidx, double *__restrict__ out_x,
                    int64_t out_cap, int do_fill, unsigned long long *__restrict__ status, int *__restrict__ ticket,
-                   int *__restrict__ counts_actual, int *__restrict__ flags)
+                   int *__restrict__ counts_actual, int *__restrict__ flags, long long *__restrict__ total_out)
 {
     extern __shared__ __align__(16) unsigned char s_op_raw[];
     int2 *s_buf_all = reinterpret_cast<int2 *>(s_op_raw);
@@ -1002,7 +1002,10 @@ bin_onepass_kernel(int N, int G, const int64_t *__restrict__ colptr, const int32
             if (lane == 0) {
                 op_st_status(status + c, OP_FLAG_P | (unsigned long long)(excl + cnt));
                 out_colptr[c] = excl;
-                if (c == N - 1) out_colptr[N] = excl + cnt;
+                if (c == N - 1) {
+                    out_colptr[N] = excl + cnt;
+                    *total_out = excl + cnt;
+                }
             }
         };
         if (!do_fill) {
@@ -1447,15 +1450,18 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
     }
     CS_CUDA(p->counts.reserve(N));
     CS_CUDA(p->counts2.reserve(N));
-    CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
     if (d_out_rowidx) CS_REQUIRE(d_out_x != nullptr, "cs_bin_counts_dev: d_out_x is NULL");
     // one pass (count, look-back and fill in one kernel) when the map is regular and the slots are
     // aligned for 256-bit loads; CS_BIN_ONEPASS=0 keeps the count / scan / fill kernels
     const bool onepass_env = !(getenv("CS_BIN_ONEPASS") && atoi(getenv("CS_BIN_ONEPASS")) == 0);
     if (p->onepass && p->stream_fill && onepass_env && ((uintptr_t)d_rowidx % 32 == 0) && ((uintptr_t)d_x % 32 == 0)) {
-        CS_CUDA(p->status.reserve(N));
-        CS_CUDA(cudaMemsetAsync(p->status.p, 0, sizeof(unsigned long long) * (size_t)N, st));
-        CS_CUDA(cudaMemsetAsync(p->ticket.p, 0, sizeof(int), st));
+        // one memset and one copy back per call: the flags, the total and the ticket live behind the
+        // per-column status words, laid out like p->h_pinned (NFLAGS ints, then the int64 total)
+        CS_CUDA(p->status.reserve((size_t)N + 4));
+        CS_CUDA(cudaMemsetAsync(p->status.p, 0, sizeof(unsigned long long) * ((size_t)N + 4), st));
+        int *d_flags = reinterpret_cast<int *>(p->status.p + N);
+        long long *d_total = reinterpret_cast<long long *>(p->status.p + N) + NFLAGS / 2;
+        int *d_ticket = reinterpret_cast<int *>(d_total + 1);
         // (CS_BIN_OP_CTAS = 2 | 3 | 4 CTAs per SM: registers per thread against warps in flight)
         // (CS_BIN_OP_SMAP=0: the 256-thread CTAs that read the map through L1)
         int ctas = getenv("CS_BIN_OP_CTAS") ? atoi(getenv("CS_BIN_OP_CTAS")) : 3;
@@ -1478,12 +1484,11 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         CS_CUDA(cudaEventRecord(p->ev[1], st));
         CS_CUDA(cudaEventRecord(p->ev[2], st));
         kern<<<grid, threads, smem, st>>>(N, p->G, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr, d_out_rowidx, d_out_x, out_cap,
-                                          d_out_rowidx ? 1 : 0, p->status.p, p->ticket.p, p->counts2.p, p->flags.p);
+                                          d_out_rowidx ? 1 : 0, p->status.p, d_ticket, p->counts2.p, d_flags, d_total);
         CS_CUDA(cudaGetLastError());
         CS_CUDA(cudaEventRecord(p->ev[3], st));
         int64_t *h_nnz1 = reinterpret_cast<int64_t *>(p->h_pinned + NFLAGS);
-        CS_CUDA(cudaMemcpyAsync(h_nnz1, d_out_colptr + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        CS_CUDA(cudaMemcpyAsync(p->h_pinned, p->flags.p, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaMemcpyAsync(p->h_pinned, d_flags, sizeof(int) * NFLAGS + sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CS_CUDA(cudaStreamSynchronize(st));
         *nnz_out = *h_nnz1;
         if (p->h_pinned[FLAG_IRREG]) { // a column with unsorted rows (or a gene too wide): the generic kernels from now on
@@ -1501,6 +1506,7 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         }
         return finish_fill(p, N, d_colptr, d_rowidx, d_x, d_out_colptr, d_out_rowidx, d_out_x, out_cap, nnz_out, st, true);
     }
+    CS_CUDA(cudaMemsetAsync(p->flags.p, 0, sizeof(int) * NFLAGS, st));
     const int words = (p->B + 31) / 32;
     int grid1 = cs_num_sms() * 16;
     if (grid1 > N) grid1 = N;
