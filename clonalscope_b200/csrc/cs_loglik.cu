@@ -142,17 +142,15 @@ __global__ void transpose_kernel(int rows, int cols, const T *__restrict__ in, T
 // two or three per cell); a cell with more distinct labels than that falls back to counting each
 // first occurrence against the whole column.  Most frequent label, ties -> the smallest label
 // (names(table(x))[which.max(table(x))], R/AssignCluster.R:37).
-constexpr int MV_SLOTS = 6;
+constexpr int MV_SLOTS = 6, MV_SLOTS2 = 24;
 
-__global__ void __launch_bounds__(128)
-majority_vote_kernel(int T, int N, const int *__restrict__ Z, int64_t st, int64_t si, int *__restrict__ out)
+// counts of up to SLOTS distinct labels of one cell in registers; false when there are more
+template <int SLOTS>
+__device__ __forceinline__ bool mv_tally(int T, const int *__restrict__ z, int64_t st, int &best_out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int *z = Z + (size_t)i * si;
-    int lab[MV_SLOTS], cnt[MV_SLOTS];
+    int lab[SLOTS], cnt[SLOTS];
 #pragma unroll
-    for (int s = 0; s < MV_SLOTS; s++) {
+    for (int s = 0; s < SLOTS; s++) {
         lab[s] = 0;
         cnt[s] = 0;
     }
@@ -163,34 +161,54 @@ majority_vote_kernel(int T, int N, const int *__restrict__ Z, int64_t st, int64_
         const int l = __ldcs(z + (size_t)t * st);
         bool hit = false;
 #pragma unroll
-        for (int s = 0; s < MV_SLOTS; s++) {
+        for (int s = 0; s < SLOTS; s++) {
             const bool m = s < used && lab[s] == l;
             cnt[s] += m ? 1 : 0;
             hit |= m;
         }
         if (!hit) {
 #pragma unroll
-            for (int s = 0; s < MV_SLOTS; s++)
+            for (int s = 0; s < SLOTS; s++)
                 if (s == used) {
                     lab[s] = l;
                     cnt[s] = 1;
                 }
-            overflow |= used >= MV_SLOTS;
-            used = min(used + 1, MV_SLOTS);
+            overflow |= used >= SLOTS;
+            used = min(used + 1, SLOTS);
         }
     }
-    if (!overflow) {
-        int best = lab[0], bc = cnt[0];
+    if (overflow) return false;
+    int best = lab[0], bc = cnt[0];
 #pragma unroll
-        for (int s = 1; s < MV_SLOTS; s++)
-            if (s < used && (cnt[s] > bc || (cnt[s] == bc && lab[s] < best))) {
-                bc = cnt[s];
-                best = lab[s];
-            }
+    for (int s = 1; s < SLOTS; s++)
+        if (s < used && (cnt[s] > bc || (cnt[s] == bc && lab[s] < best))) {
+            bc = cnt[s];
+            best = lab[s];
+        }
+    best_out = best;
+    return true;
+}
+
+// thread per cell.  A cell of a converged chain visits a handful of labels: six register slots
+// decide it in one pass over its T labels; a cell with more takes a second pass with 24 slots,
+// and only beyond that the quadratic count of every first occurrence against the whole column.
+__global__ void __launch_bounds__(128)
+majority_vote_kernel(int T, int N, const int *__restrict__ Z, int64_t st, int64_t si, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int *z = Z + (size_t)i * si;
+    int best = 0;
+    if (mv_tally<MV_SLOTS>(T, z, st, best)) {
         out[i] = best;
         return;
     }
-    int best = 0, bc = 0;
+    if (mv_tally<MV_SLOTS2>(T, z, st, best)) {
+        out[i] = best;
+        return;
+    }
+    int bc = 0;
+    best = 0;
     for (int a = 0; a < T; a++) {
         const int la = z[(size_t)a * st];
         int c = 0;
