@@ -17,10 +17,13 @@ from .api import (  # noqa: F401
     loglik_matrix,
     ClonalscopeError,
 )
+from .segtable import Createobj_bulk, Segmentation_bulk, CreateSegtableNoWGS  # noqa: F401
+from .rio import readMM, saveRDS, RDataFrame  # noqa: F401
 from ._lib import lib, build_library, library_path  # noqa: F401
 
 __all__ = [
     "Gen_bin_cell_rna_filtered", "EstRegionCov", "PrepCovMatrix", "BayesNonparCluster", "BayesNonparAlleleCluster",
-    "MCMCtrim", "AssignCluster", "majority_vote", "loglik_matrix", "ClonalscopeError", "lib", "build_library",
+    "MCMCtrim", "AssignCluster", "majority_vote", "loglik_matrix", "ClonalscopeError", "Createobj_bulk",
+    "Segmentation_bulk", "CreateSegtableNoWGS", "readMM", "saveRDS", "RDataFrame", "lib", "build_library",
     "library_path",
 ]
