@@ -90,6 +90,21 @@ def test_binning_synthetic_geometry_bit_exact(cs, oracle):
         assert got[:, c].sum() == (x[colptr[c]:colptr[c + 1]] * nh[rowidx[colptr[c]:colptr[c + 1]]]).sum()
 
 
+@pytest.mark.parametrize("env", [{"CS_BIN_OP_SMAP": "0"}, {"CS_BIN_OP_SMAP": "0", "CS_BIN_OP_CTAS": "2"},
+                                 {"CS_BIN_ONEPASS": "0"}, {"CS_BIN_OP_OPT": "0"}, {"CS_BIN_OP_OPT": "31"}])
+def test_binning_alternative_kernels_bit_exact(cs, oracle, monkeypatch, env):
+    """The kernels behind the default one-pass path — the map read through L1 instead of shared memory
+    (what a gene table too large for shared memory takes), the count / scan / fill kernels, and the
+    one-pass kernel with none / all of its optional stages — give the same bytes."""
+    from clonalscope_b200 import synth
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    bins, genes = synth.geometry(G=3000, seed=7)
+    map_ptr, map_bin = synth.geometry_map(bins, genes)
+    colptr, rowidx, x = synth.counts_csc(700, G=3000, seed=9, mean_genes=400)
+    _check_bins(cs, oracle, 3000, 700, len(bins["chr"]), colptr, rowidx, x, map_ptr, map_bin)
+
+
 def test_binning_real_geometry_api(cs, oracle):
     """Gen_bin_cell_rna_filtered end to end on the reference's real tiles and gene table."""
     import scipy.sparse as sp
@@ -308,6 +323,21 @@ def test_sampler_philox_vs_oracle_synthetic(cs, oracle, N, R, na, niter):
     _assert_same_chain(got, want, niter)
     # the default Z0 of the shim (device log-likelihood argmax, :91-108) is the same vector
     assert np.array_equal(cs.BayesNonparCluster(s["X"], U0=s["U0"], sigmas0=s["sigmas0"], niter=1)["priors"]["Z0"], Z0)
+
+
+def test_sampler_philox_extreme_values_clamp_like_the_oracle(cs, oracle):
+    """A segment's fixed-point term is clamped at 2^62 (standardised distances beyond 2^15: here
+    outliers of 1e7 against sigma 0.05); the clamped sums must give the oracle's chain all the same."""
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(700, R=40, seed=77, K_true=5)
+    X = s["X"].copy()
+    rng = np.random.default_rng(3)
+    idx = rng.choice(X.size, size=60, replace=False)
+    X.ravel()[idx] = rng.choice([1e7, 5e8, 3e4], size=60)
+    sig0 = np.full(40, 0.05)
+    Z0 = oracle.loglik_matrix(X, s["U0"], sig0).argmax(axis=1).astype(np.int32) + 1
+    got, want = _philox_pair(cs, oracle, X, s["U0"], Z0, sig0, 6)
+    _assert_same_chain(got, want, 6)
 
 
 @pytest.mark.parametrize("N,R,K,noise,alpha", [(1200, 12, 45, 0.08, 8.0), (1500, 6, 48, 0.05, 2.0)])
