@@ -1267,6 +1267,9 @@ struct cs_bin_plan {
     DevBuf<int32_t> tmp_i;
     DevBuf<double> tmp_x;
     int *h_pinned = nullptr; // NFLAGS ints + 1 int64 (nnz)
+    const void *op_kern = nullptr; // launch configuration of the one-pass kernel, found once
+    size_t op_smem = 0;
+    int op_per_sm = 1;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // count | scan | fill boundaries
     bool timed = false;
     ~cs_bin_plan()
@@ -1473,11 +1476,15 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
                          : (ctas == 2 ? bin_onepass_kernel<OP_THREADS, 2, false, 2> : bin_onepass_kernel<OP_THREADS, 3, false, 2>);
         const int threads = smap ? sthreads : OP_THREADS;
         const size_t smem = smap ? smap_bytes : (size_t)OP_WARPS * OP_CAP * sizeof(int2);
-        CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-        if (per_sm < 1) per_sm = 1;
-        int grid = cs_num_sms() * per_sm;
+        if (p->op_kern != (const void *)kern || p->op_smem != smem) { // (the attribute and the occupancy query once per plan)
+            CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int q = 0;
+            CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
+            p->op_per_sm = q < 1 ? 1 : q;
+            p->op_kern = (const void *)kern;
+            p->op_smem = smem;
+        }
+        int grid = cs_num_sms() * p->op_per_sm;
         if (grid > (N + threads / 32 - 1) / (threads / 32)) grid = (N + threads / 32 - 1) / (threads / 32);
         p->timed = false;
         CS_CUDA(cudaEventRecord(p->ev[0], st));

@@ -261,8 +261,8 @@ __device__ __forceinline__ int draw_cell_warp(const double *Qc, double *Ec, size
 }
 
 // ---------------------------------------------------------------- prepare (all SMs)
-template <int NCH>
-__global__ void __launch_bounds__(PREP_THREADS, 4)
+template <int NCH, int CTAS = 4>
+__global__ void __launch_bounds__(PREP_THREADS, CTAS)
 prepare_kernel(ChainDev D, int tt, int *__restrict__ rej)
 {
     extern __shared__ double s_dyn[];
@@ -1447,7 +1447,15 @@ int launch_sweep(const ChainDev &D, int tt, int flags, int *rej, int nsm, cudaSt
     } else {
         int grid = (D.N + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
         if (grid > nsm * 8) grid = nsm * 8;
-        prepare_kernel<NCH><<<grid, PREP_THREADS, smem_prep, st>>>(D, tt, rej);
+        static const int prep_ctas = getenv("CS_PREP_CTAS") ? atoi(getenv("CS_PREP_CTAS")) : 4;
+        if (prep_ctas == 3) {
+            if (grid > nsm * 6) grid = nsm * 6;
+            prepare_kernel<NCH, 3><<<grid, PREP_THREADS, smem_prep, st>>>(D, tt, rej);
+        } else if (prep_ctas == 2) {
+            if (grid > nsm * 4) grid = nsm * 4;
+            prepare_kernel<NCH, 2><<<grid, PREP_THREADS, smem_prep, st>>>(D, tt, rej);
+        } else
+            prepare_kernel<NCH><<<grid, PREP_THREADS, smem_prep, st>>>(D, tt, rej);
         if (ev) CS_CUDA(cudaEventRecord(ev[1], st));
         if (reject_live) {
             seq_scan_kernel<NCH><<<1, SCAN_THREADS, smem_scan, st>>>(D, tt, 0, rej);
