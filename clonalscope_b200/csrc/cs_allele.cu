@@ -92,21 +92,6 @@ __device__ __forceinline__ double dn_log(double x, double m, double s)
     return -(CS_LN_SQRT_2PI + 0.5 * z * z + log(s));
 }
 
-// sum over non-NA segments of the coverage and the allele log-densities of one cell at the
-// grid states of one row
-__device__ double cell_ll_states(int R, const double *xc, const double *xa, const int *st, const double *gc,
-                                 const double *ga, int G, const double *sc, const double *sa)
-{
-    double s1 = 0.0, s2 = 0.0;
-    for (int r = 0; r < R; r++) {
-        const int s = st[r];
-        const bool ok = s >= 1 && s <= G;
-        if (!cs_isna(xc[r])) s1 += dn_log(xc[r], ok ? gc[s - 1] : NAN, sc[r]);
-        if (!cs_isna(xa[r])) s2 += dn_log(xa[r], ok ? ga[s - 1] : NAN, sa[r]);
-    }
-    return s1 + s2;
-}
-
 __device__ int nearest_state(double cov, double allele, const double *gc, const double *ga, int G6)
 {
     int best = 0;
@@ -136,6 +121,11 @@ gibbs_allele_kernel(AlleleDev D)
     double *sa = d; d += R;
     double *gc = d; d += GMAX; // grid: coverage (maxcp of the call, then the maxcp = 6 grid for snapping)
     double *ga = d; d += GMAX;
+    double *lsc = d; d += R;   // log(sigma) of both modalities (constant within a sweep)
+    double *lsa = d; d += R;
+    double *termc = d; d += (size_t)(AT / 32) * R; // one row of terms per warp and modality
+    double *terma = d; d += (size_t)(AT / 32) * R;
+    unsigned long long *s_used = reinterpret_cast<unsigned long long *>(d); d += R; // grid states in use, per segment
     int *p = reinterpret_cast<int *>(d);
     int *permc = p; p += lcap + 1;
     int *np = p; p += lcap;
@@ -151,6 +141,8 @@ gibbs_allele_kernel(AlleleDev D)
     for (int r = tid; r < R; r += AT) {
         sc[r] = D.sig0c[r];
         sa[r] = D.sig0a[r];
+        lsc[r] = log(sc[r]);
+        lsa[r] = log(sa[r]);
     }
     for (int k = tid; k < 624; k += AT) mt[k] = D.mt[k];
     if (tid == 0) {
@@ -215,6 +207,15 @@ gibbs_allele_kernel(AlleleDev D)
                     permc[k] = k + 1;
                 }
             }
+            // the grid states some cluster row holds, per segment (all threads; the draws below are thread 0's)
+            for (int r = tid; r < R; r += AT) {
+                unsigned long long used = 0;
+                for (int k = 0; k < kt; k++) {
+                    const int st = D.Ut[(size_t)k * R + r];
+                    if (st >= 1 && st <= G) used |= 1ull << (st - 1);
+                }
+                s_used[r] = used;
+            }
             __syncthreads();
             // ---- :158-166 proposal: an unused grid state per segment, or a live cluster's state
             if (tid == 0) {
@@ -224,11 +225,7 @@ gibbs_allele_kernel(AlleleDev D)
                     s_valid = 1;
                 }
                 for (int r = 0; r < R && !s_err; r++) {
-                    unsigned long long used = 0;
-                    for (int k = 0; k < kt; k++) {
-                        const int s = D.Ut[(size_t)k * R + r];
-                        if (s >= 1 && s <= G) used |= 1ull << (s - 1);
-                    }
+                    const unsigned long long used = s_used[r];
                     const unsigned long long all = (G >= 64) ? ~0ull : ((1ull << G) - 1ull);
                     unsigned long long freeb = all & ~used;
                     const int nc = __popcll(freeb);
@@ -254,28 +251,59 @@ gibbs_allele_kernel(AlleleDev D)
             if (s_err) break;
             // ---- :179-183 scores of the occupied clusters and of the new table
             const int nocc = s_nocc;
-            for (int e = tid; e <= nocc; e += AT) {
-                if (e < nocc) {
-                    const int k = occ[e];
-                    const int n = np[k];
-                    prob[e] = (n != 0) ? cell_ll_states(R, xc, xa, D.Ut + (size_t)k * R, gc, ga, G, sc, sa) + log((double)n)
-                                       : -INFINITY;
-                } else {
-                    prob[e] = cell_ll_states(R, xc, xa, mu_new, gc, ga, G, sc, sa) + log(D.beta);
+            { // a warp per candidate: the terms of all segments at once, then the two sums in segment
+              // order by one lane (cell_ll_states' order of additions)
+                const int lane = tid & 31, wid = tid >> 5;
+                double *tc = termc + (size_t)wid * R, *ta = terma + (size_t)wid * R;
+                for (int e = wid; e <= nocc; e += AT / 32) {
+                    const int k = e < nocc ? occ[e] : -1;
+                    const int n = e < nocc ? np[k] : 1;
+                    if (n == 0) {
+                        if (lane == 0) prob[e] = -INFINITY;
+                        continue;
+                    }
+                    const int *st = e < nocc ? D.Ut + (size_t)k * R : mu_new;
+                    for (int r = lane; r < R; r += 32) {
+                        const int sidx = st[r];
+                        const bool ok = sidx >= 1 && sidx <= G;
+                        const double zc = fabs((xc[r] - (ok ? gc[sidx - 1] : NAN)) / sc[r]);
+                        const double za = fabs((xa[r] - (ok ? ga[sidx - 1] : NAN)) / sa[r]);
+                        tc[r] = -(CS_LN_SQRT_2PI + 0.5 * zc * zc + lsc[r]);
+                        ta[r] = -(CS_LN_SQRT_2PI + 0.5 * za * za + lsa[r]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        double s1 = 0.0, s2 = 0.0;
+                        for (int r = 0; r < R; r++) {
+                            if (!cs_isna(xc[r])) s1 += tc[r];
+                            if (!cs_isna(xa[r])) s2 += ta[r];
+                        }
+                        prob[e] = (s1 + s2) + log(e < nocc ? (double)n : D.beta);
+                    }
+                    __syncwarp();
                 }
             }
             __syncthreads();
             // ---- :185-190 categorical draw: sample.int(kt + 1, prob = c(p_k, p_new))
-            if (tid == 0) {
+            { // the maximum and the exponentials by all threads; the sum in candidate order by thread 0
                 double mx = -INFINITY;
-                for (int e = 0; e <= nocc; e++)
+                for (int e = tid; e <= nocc; e += AT)
                     if (e == nocc || np[occ[e]] != 0) mx = fmax(mx, prob[e]);
-                double sum = 0.0;
-                for (int e = 0; e <= nocc; e++) {
-                    const double pe = (e == nocc || np[occ[e]] != 0) ? exp(prob[e] - mx) : 0.0;
-                    prob[e] = pe;
-                    if (pe > 0) sum += pe;
+                s_red[tid] = mx;
+                __syncthreads();
+                for (int off = AT / 2; off >= 1; off >>= 1) {
+                    if (tid < off) s_red[tid] = fmax(s_red[tid], s_red[tid + off]);
+                    __syncthreads();
                 }
+                mx = s_red[0];
+                __syncthreads();
+                for (int e = tid; e <= nocc; e += AT) prob[e] = (e == nocc || np[occ[e]] != 0) ? exp(prob[e] - mx) : 0.0;
+                __syncthreads();
+            }
+            if (tid == 0) {
+                double sum = 0.0;
+                for (int e = 0; e <= nocc; e++)
+                    if (prob[e] > 0) sum += prob[e];
                 // the full kt+1 vector (zeros for empty clusters) goes through revsort like in R
                 for (int k = 0; k <= kt; k++) {
                     cumc[k] = 0.0;
@@ -390,6 +418,8 @@ gibbs_allele_kernel(AlleleDev D)
                 double v1 = sqrt(1.0 / (double)c1 * s1), v2 = sqrt(1.0 / (double)c2 * s2);
                 sc[r] = (v1 == 0.0) ? 0.01 : v1;
                 sa[r] = (v2 == 0.0) ? 0.01 : v2;
+                lsc[r] = log(sc[r]);
+                lsa[r] = log(sa[r]);
             }
             __syncthreads();
         }
@@ -490,7 +520,7 @@ extern "C" int cs_ncrp_gibbs_allele(int N, int R, const double *Xcov, const doub
         }
     }
     np0[lcap] = K0;
-    const size_t smem = sizeof(double) * (2 * ((size_t)lcap + 1) + 4 * (size_t)R + 2 * GMAX) +
+    const size_t smem = sizeof(double) * (2 * ((size_t)lcap + 1) + 4 * (size_t)R + 2 * GMAX + 2 * (size_t)R + 2 * (size_t)(AT / 32) * R + (size_t)R) +
                         sizeof(int) * (((size_t)lcap + 1) + 2 * (size_t)lcap + R) + sizeof(uint32_t) * 624 + 64;
     if (smem > 227 * 1024) {
         cs_set_error("cs_ncrp_gibbs_allele: label capacity %d with R=%d needs %zu B of shared memory", lcap, R, smem);
