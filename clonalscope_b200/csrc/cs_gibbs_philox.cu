@@ -81,10 +81,15 @@ __device__ __forceinline__ void load_row(const double *__restrict__ xrow, int R,
 // one segment's contribution, 2^-32 fixed point: llrint(((x - u) * 65536 / sigma)^2)
 __device__ __forceinline__ long long tint(double x, double u, double isig16)
 {
+    // llrint(min(d*d, 2^62)), NaN -> 2^62.  The clamp is taken on the integer: the conversion
+    // saturates above 2^63 and gives 0x8000000000000000 for a NaN, so "high word >= 0x40000000
+    // as unsigned" is exactly "d*d >= 2^62 or NaN" (three integer instructions instead of the
+    // seven of a double-precision minimum)
     const double d = __dmul_rn(__dsub_rn(x, u), isig16);
-    double t = __dmul_rn(d, d);
-    if (!(t < 4611686018427387904.0)) t = 4611686018427387904.0;
-    return __double2ll_rn(t);
+    const long long v = __double2ll_rn(__dmul_rn(d, d));
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const bool big = hi >= 0x40000000u;
+    return (long long)(((unsigned long long)(big ? 0x40000000u : hi) << 32) | (big ? 0u : lo));
 }
 
 __device__ __forceinline__ long long warp_sum_ll(long long v)
