@@ -1461,6 +1461,7 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         // one memset and one copy back per call: the flags, the total and the ticket live behind the
         // per-column status words, laid out like p->h_pinned (NFLAGS ints, then the int64 total)
         CS_CUDA(p->status.reserve((size_t)N + 4));
+        CS_CUDA(cudaEventRecord(p->ev[0], st)); // (the timing of the call's device work starts with its memset)
         CS_CUDA(cudaMemsetAsync(p->status.p, 0, sizeof(unsigned long long) * ((size_t)N + 4), st));
         int *d_flags = reinterpret_cast<int *>(p->status.p + N);
         long long *d_total = reinterpret_cast<long long *>(p->status.p + N) + NFLAGS / 2;
@@ -1487,7 +1488,6 @@ extern "C" int cs_bin_counts_dev(cs_bin_plan *p, int N, const int64_t *d_colptr,
         int grid = cs_num_sms() * p->op_per_sm;
         if (grid > (N + threads / 32 - 1) / (threads / 32)) grid = (N + threads / 32 - 1) / (threads / 32);
         p->timed = false;
-        CS_CUDA(cudaEventRecord(p->ev[0], st));
         CS_CUDA(cudaEventRecord(p->ev[1], st));
         CS_CUDA(cudaEventRecord(p->ev[2], st));
         kern<<<grid, threads, smem, st>>>(N, p->G, d_colptr, d_rowidx, d_x, p->gmap.p, d_out_colptr, d_out_rowidx, d_out_x, out_cap,
