@@ -44,8 +44,8 @@ sys.path.insert(0, ROOT)
 METRIC = "nCRP Gibbs cell-updates/sec at 100k cells x 300 segs; bin-count GB/s vs HBM"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures of sweep 10 of this workload (profiles/r2_prepare_full.txt, profiles/r2_fix_walk_full.txt)
-PREPARE_TRAFFIC_BYTES = 244183296 + 37528064   # 1.17x the 240 MB of X: the Q / E / J write-back
-WALK_TRAFFIC_BYTES = 605909760 + 59104000      # sweep 10 is event-dense; a stationary sweep touches far less
+PREPARE_TRAFFIC_BYTES = 243742208 + 36662016   # 1.17x the 240 MB of X: the Q / E / J write-back
+WALK_TRAFFIC_BYTES = 606408960 + 60434176      # sweep 10 is event-dense; a stationary sweep touches far less
 KERNELS_PER_SWEEP = 10  # prepare, fix_walk, 8 end-of-sweep kernels
 
 
@@ -628,7 +628,7 @@ def run_ours(a):
                    frac_of_hbm_peak=bin_bytes / (bms * 1e-3) / 1e9 / hbm_peak,
                    fill_kernel_gbs=(12 * nnz_in + 12 * cap) / (fms * 1e-3) / 1e9,
                    l2_note="inputs+outputs (~5 GB) exceed the 126 MB L2",
-                   traffic=3106368000 + 2904438000 if NB == 100000 else None,
+                   traffic=3105289000 + 2905120000 if NB == 100000 else None,
                    traffic_note="dram__bytes_read.sum + dram__bytes_write.sum of one bin_onepass_kernel launch at 100k cells "
                                 "(profiles/r2_bin_onepass_full.txt): 1.08x the algorithmic bytes (rows read by the count and, "
                                 "a column later, by the fill)")

@@ -24,7 +24,7 @@ SYMBOLS = [
     "cs_majority_vote", "cs_majority_vote_dev",
     "cs_cluster_stats_dev", "cs_sigma_stats_dev", "cs_cluster_stats", "cs_sigma_stats", "cs_gene_moments",
     "cs_rowsum_by_label", "cs_rowsum_by_label_dev", "cs_bin_job_rowsum_by_label", "cs_segment_hmm",
-    "cs_csc_upload", "cs_csc_free", "cs_csc_gene_moments", "cs_csc_region_cov",
+    "cs_csc_upload", "cs_csc_free", "cs_csc_gene_moments", "cs_csc_region_cov", "cs_csc_region_sums_dev", "cs_region_ratios_dev",
     "cs_mm_read_begin", "cs_mm_read_fetch", "cs_mm_read_free",
 ]
 

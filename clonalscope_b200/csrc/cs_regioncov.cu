@@ -312,12 +312,16 @@ extern "C" int cs_csc_gene_moments(cs_csc *m, double *sum, double *sumsq)
     return CS_OK;
 }
 
-extern "C" int cs_csc_region_cov(cs_csc *m, int S, const int32_t *map_ptr, const int32_t *map_seg,
-                                 const unsigned char *lib_flag, const int *celltype, int include, double *deltas,
-                                 double *sums, double *alpha, int *nsel)
+// ---- device-resident halves of cs_csc_region_cov, for cell-sharded runs (the medians need every
+// cell: the shards' sums and library sizes are all-gathered in between, clonalscope_b200/distributed.py)
+
+// per-segment column sums (d_sums: S x N, row s contiguous) and library sizes (d_alpha: N) of the
+// handle's cells
+extern "C" int cs_csc_region_sums_dev(cs_csc *m, int S, const int32_t *map_ptr, const int32_t *map_seg,
+                                      const unsigned char *lib_flag, double *d_sums, double *d_alpha, void *stream)
 {
-    CS_REQUIRE(m && S >= 1 && map_ptr && lib_flag && celltype && deltas && alpha && nsel, "cs_csc_region_cov: NULL argument");
-    CS_REQUIRE(include >= 0 && include <= 2, "cs_csc_region_cov: include must be 0 (tumor), 1 (control) or 2 (all)");
+    CS_REQUIRE(m && S >= 1 && map_ptr && lib_flag && d_sums && d_alpha, "cs_csc_region_sums_dev: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
     const int N = m->N, G = m->G;
     if (N == 0) return CS_OK;
     cs_bin_plan *plan = nullptr;
@@ -329,17 +333,16 @@ extern "C" int cs_csc_region_cov(cs_csc *m, int S, const int32_t *map_ptr, const
     } guard{plan};
     DevBuf<int64_t> d_ocp;
     DevBuf<int32_t> d_ori;
-    DevBuf<double> d_ox, d_sums, d_deltas, d_alpha;
+    DevBuf<double> d_ox;
     DevBuf<unsigned char> d_flag;
-    DevBuf<int> d_type, d_nsel;
     CS_CUDA(d_ocp.alloc((size_t)N + 1));
     int64_t need = 0;
-    if ((rc = cs_bin_counts_dev(plan, N, m->colptr.p, m->rowidx.p, m->x.p, d_ocp.p, nullptr, nullptr, 0, &need, nullptr))) return rc;
+    if ((rc = cs_bin_counts_dev(plan, N, m->colptr.p, m->rowidx.p, m->x.p, d_ocp.p, nullptr, nullptr, 0, &need, stream))) return rc;
     for (int attempt = 0;; attempt++) {
         CS_CUDA(d_ori.alloc((size_t)need));
         CS_CUDA(d_ox.alloc((size_t)need));
         int64_t got = 0;
-        rc = cs_bin_counts_dev(plan, N, m->colptr.p, m->rowidx.p, m->x.p, d_ocp.p, d_ori.p, d_ox.p, need, &got, nullptr);
+        rc = cs_bin_counts_dev(plan, N, m->colptr.p, m->rowidx.p, m->x.p, d_ocp.p, d_ori.p, d_ox.p, need, &got, stream);
         if (rc == CS_ERR_UCAP && got > need && attempt == 0) { // (columns with unsorted rows: the first count was void)
             need = got;
             continue;
@@ -347,21 +350,50 @@ extern "C" int cs_csc_region_cov(cs_csc *m, int S, const int32_t *map_ptr, const
         if (rc) return rc;
         break;
     }
+    CS_CUDA(d_flag.alloc((size_t)(G ? G : 1)));
+    CS_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * (size_t)S * N, st));
+    if (G) CS_CUDA(cudaMemcpyAsync(d_flag.p, lib_flag, (size_t)G, cudaMemcpyHostToDevice, st));
+    const int grid = cs_num_sms() * 8;
+    rc_scatter_dense_kernel<<<grid, 256, 0, st>>>(N, d_ocp.p, d_ori.p, d_ox.p, d_sums);
+    rc_library_kernel<<<grid, 256, 0, st>>>(N, m->colptr.p, m->rowidx.p, m->x.p, d_flag.p, d_alpha);
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaStreamSynchronize(st)); // (the scratch above is freed on return)
+    return CS_OK;
+}
+
+// R/EstRegionCov.R:141-159 for S segments over N cells whose sums and library sizes lie on the device
+extern "C" int cs_region_ratios_dev(int S, int N, const double *d_sums, const double *d_alpha, const int *d_celltype,
+                                    int include, double *d_deltas, int *d_nsel, void *stream)
+{
+    CS_REQUIRE(S >= 1 && N >= 0 && d_sums && d_alpha && d_celltype && d_deltas && d_nsel, "cs_region_ratios_dev: NULL argument");
+    CS_REQUIRE(include >= 0 && include <= 2, "cs_region_ratios_dev: include must be 0 (tumor), 1 (control) or 2 (all)");
+    if (N == 0) return CS_OK;
+    rc_segment_kernel<<<S < 4 * cs_num_sms() ? S : 4 * cs_num_sms(), RC_THREADS, 0, (cudaStream_t)stream>>>(
+        S, N, d_sums, d_alpha, d_celltype, include, d_deltas, d_nsel);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+extern "C" int cs_csc_region_cov(cs_csc *m, int S, const int32_t *map_ptr, const int32_t *map_seg,
+                                 const unsigned char *lib_flag, const int *celltype, int include, double *deltas,
+                                 double *sums, double *alpha, int *nsel)
+{
+    CS_REQUIRE(m && S >= 1 && map_ptr && lib_flag && celltype && deltas && alpha && nsel, "cs_csc_region_cov: NULL argument");
+    CS_REQUIRE(include >= 0 && include <= 2, "cs_csc_region_cov: include must be 0 (tumor), 1 (control) or 2 (all)");
+    const int N = m->N;
+    if (N == 0) return CS_OK;
     const size_t SN = (size_t)S * N;
+    DevBuf<double> d_sums, d_deltas, d_alpha;
+    DevBuf<int> d_type, d_nsel;
     CS_CUDA(d_sums.alloc(SN));
     CS_CUDA(d_deltas.alloc(SN));
     CS_CUDA(d_alpha.alloc((size_t)N));
-    CS_CUDA(d_flag.alloc((size_t)(G ? G : 1)));
     CS_CUDA(d_type.alloc((size_t)N));
     CS_CUDA(d_nsel.alloc((size_t)S));
-    CS_CUDA(cudaMemset(d_sums.p, 0, sizeof(double) * SN));
-    if (G) CS_CUDA(cudaMemcpy(d_flag.p, lib_flag, (size_t)G, cudaMemcpyHostToDevice));
     CS_CUDA(cudaMemcpy(d_type.p, celltype, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
-    const int grid = cs_num_sms() * 8;
-    rc_scatter_dense_kernel<<<grid, 256>>>(N, d_ocp.p, d_ori.p, d_ox.p, d_sums.p);
-    rc_library_kernel<<<grid, 256>>>(N, m->colptr.p, m->rowidx.p, m->x.p, d_flag.p, d_alpha.p);
-    rc_segment_kernel<<<S < 4 * cs_num_sms() ? S : 4 * cs_num_sms(), RC_THREADS>>>(S, N, d_sums.p, d_alpha.p, d_type.p, include,
-                                                                                   d_deltas.p, d_nsel.p);
+    int rc;
+    if ((rc = cs_csc_region_sums_dev(m, S, map_ptr, map_seg, lib_flag, d_sums.p, d_alpha.p, nullptr))) return rc;
+    if ((rc = cs_region_ratios_dev(S, N, d_sums.p, d_alpha.p, d_type.p, include, d_deltas.p, d_nsel.p, nullptr))) return rc;
     CS_CUDA(cudaGetLastError());
     CS_CUDA(cudaDeviceSynchronize());
     if ((rc = cs_d2h_staged(deltas, d_deltas.p, sizeof(double) * SN))) return rc;

@@ -250,6 +250,14 @@ int cs_csc_gene_moments(cs_csc *m, double *sum, double *sumsq);
 int cs_csc_region_cov(cs_csc *m, int S, const int32_t *map_ptr, const int32_t *map_seg,
                       const unsigned char *lib_flag, const int *celltype, int include, double *deltas,
                       double *sums, double *alpha, int *nsel);
+/* The two halves of cs_csc_region_cov with device-resident results, for cell-sharded runs: the
+ * medians of :141,:153 need every cell, so the shards' sums and library sizes are all-gathered in
+ * between (clonalscope_b200/distributed.py region_cov_sharded).  d_sums: S x N row-major (row s =
+ * segment s), d_alpha: N; map_ptr / map_seg / lib_flag are host pointers as above. */
+int cs_csc_region_sums_dev(cs_csc *m, int S, const int32_t *map_ptr, const int32_t *map_seg,
+                           const unsigned char *lib_flag, double *d_sums, double *d_alpha, void *stream);
+int cs_region_ratios_dev(int S, int N, const double *d_sums, const double *d_alpha, const int *d_celltype,
+                         int include, double *d_deltas, int *d_nsel, void *stream);
 
 /* ------------------------------------------------------------------------
  * the caller side of the gene -> bin aggregation (CreateSegtableNoWGS + Segmentation_bulk)

@@ -748,6 +748,32 @@ def test_est_region_cov_vs_oracle(cs, oracle, include, alpha_source, seed):
     np.testing.assert_allclose(got["alpha"], want["alpha"], rtol=0, atol=0)
 
 
+def test_region_cov_device_halves_equal_the_one_call_form(cs):
+    """cs_csc_region_sums_dev + cs_region_ratios_dev (what the cell-sharded form runs around its
+    all-gather, here at world size 1) == cs_csc_region_cov, bit for bit."""
+    import scipy.sparse as sp
+    from clonalscope_b200 import distributed as D
+    from clonalscope_b200.api import _CscHandle
+    rng = np.random.default_rng(13)
+    G, N, S = 300, 800, 7
+    m = sp.random(G, N, density=0.2, random_state=3, format="csc", data_rvs=lambda k: rng.integers(1, 9, k).astype(float))
+    m.sort_indices()
+    hits = [sorted(set(rng.integers(0, S, size=rng.integers(0, 3)).tolist())) for _ in range(G)]
+    map_ptr = np.zeros(G + 1, dtype=np.int32)
+    map_ptr[1:] = np.cumsum([len(h) for h in hits])
+    map_seg = np.array([s_ for h in hits for s_ in h], dtype=np.int32)
+    lib_flag = (rng.random(G) < 0.8).astype(np.uint8)
+    code = rng.choice([0, 1, 2], size=N, p=[0.3, 0.6, 0.1]).astype(np.int32)
+    h = _CscHandle(m)
+    for include in (0, 1, 2):
+        want_d, want_s, want_a, want_n = h.region_cov(S, map_ptr, map_seg, lib_flag, code, include)
+        got = D.region_cov_sharded(h, S, map_ptr, map_seg, lib_flag, code, include)
+        assert np.array_equal(got["deltas"].cpu().numpy(), want_d, equal_nan=True)
+        assert np.array_equal(got["sums"].cpu().numpy(), want_s) and np.array_equal(got["alpha"].cpu().numpy(), want_a)
+        assert np.array_equal(got["nsel"].cpu().numpy(), want_n) and got["offset"] == 0 and got["n_total"] == N
+    h.free()
+
+
 def test_est_region_cov_default_segments_and_errors(cs, oracle):
     import scipy.sparse as sp
     from clonalscope_b200.api import EstRegionCov

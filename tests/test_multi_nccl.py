@@ -52,6 +52,32 @@ def _worker(rank, world, port, tmp):
     gathered = [torch.zeros_like(out["sigma"]) for _ in range(world)]
     dist.all_gather(gathered, out["sigma"])
     ok = ok and all(torch.equal(g, gathered[0]) for g in gathered)     # every rank holds the same reduced result
+    # ---- EstRegionCov sharded by cells: local sums + library sizes, one all-gather, medians over all
+    # cells on every rank == the one-GPU computation on the whole matrix (bit for bit)
+    import scipy.sparse as sp
+    from clonalscope_b200.api import _CscHandle
+    rng = np.random.default_rng(11)
+    G, Nc, S = 400, 1501, 9
+    m = sp.random(G, Nc, density=0.15, random_state=5, format="csc", data_rvs=lambda k: rng.integers(1, 9, k).astype(float))
+    m.sort_indices()
+    map_ptr = np.zeros(G + 1, dtype=np.int32)
+    hits = [sorted(set(rng.integers(0, S, size=rng.integers(0, 3)).tolist())) for _ in range(G)]
+    map_ptr[1:] = np.cumsum([len(h) for h in hits])
+    map_seg = np.array([s_ for h in hits for s_ in h], dtype=np.int32)
+    lib_flag = (rng.random(G) < 0.8).astype(np.uint8)
+    code = rng.choice([0, 1, 2], size=Nc, p=[0.3, 0.6, 0.1]).astype(np.int32)
+    whole = _CscHandle(m)
+    want_d, want_s, want_a, want_n = whole.region_cov(S, map_ptr, map_seg, lib_flag, code, 0)
+    whole.free()
+    clo, chi = D.shard_range(Nc, world, rank)
+    local = _CscHandle(m[:, clo:chi].tocsc())
+    got = D.region_cov_sharded(local, S, map_ptr, map_seg, lib_flag, code[clo:chi], 0, device=dev)
+    local.free()
+    ok = ok and got["offset"] == clo and got["n_total"] == Nc
+    ok = ok and np.array_equal(got["nsel"].cpu().numpy(), want_n)
+    ok = ok and np.array_equal(got["alpha"].cpu().numpy(), want_a[clo:chi])
+    ok = ok and np.array_equal(got["sums"].cpu().numpy(), want_s[:, clo:chi])
+    ok = ok and np.array_equal(got["deltas"].cpu().numpy(), want_d[:, clo:chi], equal_nan=True)
     with open(os.path.join(tmp, f"ok{rank}"), "w") as fh:
         fh.write("1" if ok else "0")
     dist.destroy_process_group()
