@@ -289,6 +289,29 @@ def test_sampler_r_mode_reproduces_reference_outputs(cs, name, niter):
         assert _ari(zm, zr) >= 0.95 and len(np.unique(zm)) == len(np.unique(zr))
 
 
+@pytest.mark.parametrize("N,R,na,single", [(400, 300, 0.0, False), (350, 311, 0.02, False), (300, 330, 0.0, False),
+                                           (500, 37, 0.03, True), (64, 1, 0.0, False)])
+def test_sampler_r_mode_vs_oracle_wide_matrices(cs, oracle, N, R, na, single):
+    """R-compatible mode against the oracle's R mode beyond the fixtures' 4-38 segments: with 2R + 1
+    draws per cell the pooled stream crosses a Mersenne-Twister block almost every cell (R = 300,
+    311: the widest the pool takes), R = 330 runs on the draw-by-draw kernel, and a single-cluster
+    start exercises the first sweep's rejection loop.  Labels, sigmas and likelihoods must agree."""
+    from clonalscope_b200 import synth
+    s = synth.sampler_input(N, R=R, seed=2000 + R, K_true=5, na_frac=na)
+    U0 = s["U0"][:1] if single else s["U0"]
+    Z0 = oracle.loglik_matrix(s["X"], U0, s["sigmas0"]).argmax(axis=1).astype(np.int32) + 1
+    niter = 4
+    want = oracle.gibbs(s["X"], U0, Z0, s["sigmas0"], 2.0, 2.0, niter, 200, rng_mode=oracle.RNG_R, ucap_rows=niter * 512)
+    got = cs.BayesNonparCluster(s["X"], alpha=2.0, beta=2.0, niter=niter, sigmas0=s["sigmas0"], U0=U0, Z0=Z0, seed=200,
+                                rng="R")
+    res = got["results"]
+    assert np.array_equal(res["Zall"], want["Zall"])
+    assert [u.shape[0] for u in res["Uall"]] == list(want["kt"])
+    k = niter - 1                                                     # (the last sweep of a run is re-recorded noise-free)
+    np.testing.assert_allclose(np.array(res["sigma_all"][:k]), want["sigma_all"][:k], rtol=1e-9)
+    np.testing.assert_allclose(res["Likelihood"][:k], want["LL"][:k], rtol=1e-9)
+
+
 # ------------------------------------------------------------------ sampler, Philox
 def _philox_pair(cs, oracle, X, U0, Z0, sig0, niter, seed=200, alpha=2.0, beta=2.0, flags=0):
     want = oracle.gibbs(X, U0, Z0, sig0, alpha, beta, niter, seed, rng_mode=oracle.RNG_PHILOX,
