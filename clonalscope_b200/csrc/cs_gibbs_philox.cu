@@ -13,21 +13,12 @@
 //       have seen (a cell that re-draws its own label leaves counts and rows untouched), so
 //       every draw up to and including the first label change ("event") is already the
 //       sequential result.
-//   index kernels (all SMs; skipped when the sweep has no event)
-//       inverse source index: for every cell f the (cell, segment) pairs whose proposal
-//       copies f's cluster state — what an event at f invalidates.
-//   scan_ring_kernel / scan_kernel (one CTA walks, thread per cell)
-//       resumes at the first event and walks the rest of the sweep in windows of 256
-//       cells: each thread re-draws its cell against the committed state from the cached
-//       exponentials (no exp, no gathers: counts are the only thing an event changes for
-//       almost every cell) and keeps a margin — how far its sums may move before the draw
-//       could change; the window's events are committed in order for as long as every draw
-//       in front of the next one provably still holds, their dependents' proposal
-//       distances are corrected in place (fixed-point, so the correction is exact), and
-//       the walk continues behind the last one.  scan_ring_kernel (<= 32 live clusters)
-//       keeps what a re-draw needs in a shared-memory ring filled by asynchronous copies
-//       and runs as a cluster of CTAs whose other members score the column of a newly
-//       opened cluster; scan_kernel is the generic walk against global memory.
+//   fix_walk_kernel (cooperative, all SMs; skipped when the sweep has no event)
+//       the rest of the sweep as the fixed point of a parallel map: a hypothesis for the outcome
+//       of every cell is re-drawn against the state it induces itself, for all cells behind the
+//       last settled one at once, until nothing changes (a handful of steps); a cell that opens
+//       a cluster stops the prefix, its row is appended and scored by the whole grid, and the
+//       iteration goes on behind it.  See the comment above the kernel.
 //   seq_scan_kernel (one CTA, warp per cell): the plain sequential evaluation, used for the
 //       first sweep of a single-cluster start (rejection loop live, :174) and as the
 //       test hook that proves the speculative path draws the same chain.
