@@ -322,3 +322,37 @@ def test_saverds_known_bytes_and_round_trip(tmp_path):
     assert list(r["seg"]["chr"].data) == ["1", "2"] and list(r["seg"]["start"].data) == [0.0, 6e5]
     saveRDS(np.arange(3.0), str(tmp_path / "plain.rds"), compress=False)
     assert list(rr.read_rds(str(tmp_path / "plain.rds")).data) == [0.0, 1.0, 2.0]
+
+
+def test_createobj_bulk_orders_chromosomes_and_sizes():
+    """Createobj_bulk (R/Createobj_bulk.R:57-90): count vectors whose chromosomes are not in numeric
+    order are reordered by (chromosome, start); `size` is cut to the chromosomes present and ordered."""
+    from clonalscope_b200.api import NamedMatrix
+    from clonalscope_b200.segtable import Createobj_bulk
+    names = ["chr2-1-100", "chr2-101-200", "chr10-1-100", "chr1-101-200", "chr1-1-100"]
+    raw = NamedMatrix(np.array([[1.0], [2.0], [3.0], [4.0], [5.0]]), names, ["V1"])
+    ref = NamedMatrix(np.ones((5, 1)), names, ["V1"])
+    size = np.array([["chr10", 500], ["chr1", 300], ["chr2", 400], ["chrX", 900]], dtype=object)
+    obj = Createobj_bulk(raw, ref, size=size)
+    assert obj["raw_counts"].rownames == ["chr1-1-100", "chr1-101-200", "chr2-1-100", "chr2-101-200", "chr10-1-100"]
+    assert list(obj["raw_counts"].values[:, 0]) == [5.0, 4.0, 1.0, 2.0, 3.0]
+    assert list(obj["size"].items()) == [("1", 300.0), ("2", 400.0), ("10", 500.0)]
+    with pytest.raises(ValueError, match="chr1-1-20000"):
+        Createobj_bulk(NamedMatrix(np.ones((2, 1)), ["a", "b"], ["V1"]), ref, size=size)
+
+
+def test_r_stream_sample_int_and_kmeans_known_answers():
+    """sample.int without prob (R >= 3.6 rejection sampling) against base R's documented outputs, and
+    Hartigan-Wong on a separable vector: set.seed(42); sample.int(10, 3) is 1 5 10; set.seed(1);
+    sample.int(5, 2) is 1 4; set.seed(123); sample.int(10, 3) is 3 10 2."""
+    from clonalscope_b200.rrng import RStream, kmeans_hartigan_wong, sample_int_noreplace
+    assert sample_int_noreplace(RStream(42), 10, 3) == [1, 5, 10]
+    assert sample_int_noreplace(RStream(1), 5, 2) == [1, 4]
+    assert sample_int_noreplace(RStream(123), 10, 3) == [3, 10, 2]
+    for seed in range(5):
+        cen = sorted(kmeans_hartigan_wong(RStream(seed), [0.1, 0.15, 0.9, 1.0, 0.05, 0.8, 0.95]))
+        assert abs(cen[0] - 0.1) < 1e-12 and abs(cen[1] - 0.9125) < 1e-12
+    with pytest.raises(ValueError, match="between 1 and nrow"):
+        kmeans_hartigan_wong(RStream(1), [0.3, 0.4], 2)
+    with pytest.raises(ValueError, match="distinct data points"):
+        kmeans_hartigan_wong(RStream(1), [0.3, 0.3, 0.3], 2)
