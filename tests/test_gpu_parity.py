@@ -832,9 +832,11 @@ def test_chains_on_two_devices_from_one_process(cs):
     assert np.array_equal(a["results"]["Likelihood"], b["results"]["Likelihood"])
 
 
-def test_region_cov_feeds_prep_and_the_sampler(cs):
-    """a7 -> a2 -> a3 on one synthetic sample: EstRegionCov's output is what PrepCovMatrix takes, and
-    the coverage matrix it builds separates a planted gain when clustered."""
+def test_region_cov_feeds_prep_and_the_sampler(cs, tmp_path):
+    """The tutorial's chain on one synthetic sample, file to file: matrix.mtx.gz -> readMM -> EstRegionCov
+    (a7) -> PrepCovMatrix (a2) -> BayesNonparCluster (a3) -> MCMCtrim -> AssignCluster -> saveRDS; the
+    coverage matrix separates a planted gain when clustered and the saved object reads back."""
+    import gzip
     import scipy.sparse as sp
     rng = np.random.default_rng(12)
     G, N = 1200, 600
@@ -852,7 +854,14 @@ def test_region_cov_feeds_prep_and_the_sampler(cs):
     ct[:, 0], ct[:, 1] = bars, np.where(tumor, "tumor", "normal")
     seg = dict(chr=["1", "2", "3"], start=[0.0, 0.0, 0.0], end=[4e6, 4e6, 4e6], chrr=["chr1", "chr2", "chr3"],
                states=[1, 1.5, 1])
-    est = cs.EstRegionCov(sp.csc_matrix(mtx), bars, feats, bed, ct, seg_table_filtered=seg)
+    coo = sp.coo_matrix(sp.csc_matrix(mtx))
+    order = np.lexsort((coo.row, coo.col))
+    with gzip.open(tmp_path / "matrix.mtx.gz", "wt") as f:                 # what cellranger writes
+        f.write(f"%%MatrixMarket matrix coordinate integer general\n%metadata_json: {{}}\n{G} {N} {coo.nnz}\n")
+        f.write("".join(f"{r + 1} {c + 1} {int(v)}\n" for r, c, v in zip(coo.row[order], coo.col[order], coo.data[order])))
+    m = cs.readMM(tmp_path / "matrix.mtx.gz")
+    assert (m != sp.csc_matrix(mtx)).nnz == 0
+    est = cs.EstRegionCov(m, bars, feats, bed, ct, seg_table_filtered=seg)
     prep = cs.PrepCovMatrix(est, ngene_filter=50)
     X = prep["df"]
     assert X.values.shape == (400, 3) and X.colnames == ["chr1-0-4e+06", "chr2-0-4e+06", "chr3-0-4e+06"]
@@ -864,6 +873,16 @@ def test_region_cov_feeds_prep_and_the_sampler(cs):
     purity = sum(max(int(((z == k) & (planted == 1)).sum()), int(((z == k) & (planted == 0)).sum()))
                  for k in np.unique(z)) / len(z)
     assert purity > 0.9                                                    # clusters do not mix the two groups
+    final = cs.AssignCluster(cs.MCMCtrim(out), mincell=20)
+    assert set(np.unique(final["annot"])) <= {"T", "N"} and len(final["Zest"]) == 400
+    import rds_reader as rr
+    obj = dict(clustering=dict(results=dict(Zall=out["results"]["Zall"], Likelihood=out["results"]["Likelihood"]),
+                               data=X), result=dict(Zest=final["Zest"], annot=list(final["annot"]), Uest=final["Uest"]))
+    cs.saveRDS(obj, str(tmp_path / "nonpara_clustering.rds"))
+    back = rr.read_rds(str(tmp_path / "nonpara_clustering.rds"))
+    assert np.array_equal(back["clustering"]["results"]["Zall"].data.reshape(400, 40).T, out["results"]["Zall"])
+    assert list(back["clustering"]["data"].attrs["dimnames"][1].data) == X.colnames
+    assert list(back["result"]["annot"].data) == list(final["annot"])
 
 
 # ------------------------------------------------------------------ AssignCluster
