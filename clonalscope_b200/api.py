@@ -315,14 +315,16 @@ def _est_region_cov_on(handle, G, N, features, bchr, bstart, bend, bgene, ct_bar
     all_idx = np.nonzero(out_mask)[0]
     all_names = names_a[all_idx].tolist()
     deltas_all, ngenes, sel_ind = {}, {}, []
-    last = -1
+    last, dsel = -1, None
     for si, name in enumerate(uniq):                                    # :80
         if S == 0 or nsel[si] == 0:                                     # :93 no cell with a positive sum
             continue
         sel_ind.append(name)
         last = si
-        if nsel[si] == N:
-            deltas_all[est_name + name] = (all_names, deltas[si, all_idx])
+        if nsel[si] == N:                                               # every cell reports: one gather for all such segments
+            if dsel is None:
+                dsel = deltas[:, all_idx]
+            deltas_all[est_name + name] = (all_names, dsel[si])
         else:
             idx = np.nonzero((sums[si] > 0) & out_mask)[0]
             deltas_all[est_name + name] = (names_a[idx].tolist(), deltas[si, idx])
