@@ -170,7 +170,7 @@ def run_reference(a):
                 cpu_baseline=dict(value=value, unit="cell-updates/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------ GPU arm
@@ -771,12 +771,29 @@ def run_ours(a):
             line["region_cov"] = region
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout (see main())."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries write to stdout behind our back (NCCL prints its version banner there at N > 1): file
+    # descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the
+    # original stdout, so stdout carries exactly one line.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
