@@ -6,10 +6,13 @@
 // the (K*R*2 + K + 2R) doubles across ranks (NCCL over NVLink; latency-bound, ~100 KB).
 #include "cs_common.cuh"
 
+#include <math_constants.h>
+
 namespace {
 
 constexpr int ST_THREADS = 256;
 constexpr int ST_CHUNK = 512;
+constexpr int ST_UNROLL = 8;
 
 // grid: cell chunks.  Shared accumulators when K*R fits, global atomics otherwise.
 __global__ void __launch_bounds__(ST_THREADS)
@@ -22,22 +25,33 @@ cluster_stats_kernel(int N, int R, int K, const double *__restrict__ X, const in
         for (int e = threadIdx.x; e < 2 * K * R; e += ST_THREADS) s_acc[e] = 0.0;
         __syncthreads();
     }
-    for (int i = i0; i < i1; i++) {
-        const int k = Z[i] - 1;
-        if (k < 0 || k >= K) continue;
-        const double *x = X + (size_t)i * R;
-        for (int r = threadIdx.x; r < R; r += ST_THREADS) {
-            const double v = x[r];
-            if (cs_isna(v)) continue;
-            if (use_smem) {
-                s_acc[k * R + r] += v; // thread owns column r: no race
-                s_acc[K * R + k * R + r] += 1.0;
-            } else {
-                atomicAdd(sum_x + (size_t)k * R + r, v);
-                atomicAdd(cnt_x + (size_t)k * R + r, 1.0);
+    // a thread owns segment r; ST_UNROLL cells' values are in flight at a time (cells still in order)
+    for (int r = threadIdx.x; r < R; r += ST_THREADS) {
+        for (int i = i0; i < i1; i += ST_UNROLL) {
+            int k[ST_UNROLL];
+            double v[ST_UNROLL];
+#pragma unroll
+            for (int u = 0; u < ST_UNROLL; u++) {
+                const bool in = i + u < i1;
+                k[u] = in ? Z[i + u] - 1 : -1;
+                v[u] = in ? X[(size_t)(i + u) * R + r] : CUDART_NAN;
+            }
+#pragma unroll
+            for (int u = 0; u < ST_UNROLL; u++) {
+                if ((unsigned)k[u] >= (unsigned)K || cs_isna(v[u])) continue;
+                if (use_smem) {
+                    s_acc[k[u] * R + r] += v[u]; // thread owns column r: no race
+                    s_acc[K * R + k[u] * R + r] += 1.0;
+                } else {
+                    atomicAdd(sum_x + (size_t)k[u] * R + r, v[u]);
+                    atomicAdd(cnt_x + (size_t)k[u] * R + r, 1.0);
+                }
             }
         }
-        if (threadIdx.x == 0) atomicAdd(nk + k, 1.0);
+    }
+    for (int i = i0 + threadIdx.x; i < i1; i += ST_THREADS) { // cluster sizes
+        const int k = Z[i] - 1;
+        if (k >= 0 && k < K) atomicAdd(nk + k, 1.0);
     }
     if (use_smem) {
         __syncthreads();
@@ -57,14 +71,25 @@ sigma_stats_kernel(int N, int R, int K, const double *__restrict__ X, const int 
     const int i0 = blockIdx.x * ST_CHUNK, i1 = min(N, i0 + ST_CHUNK);
     for (int r = threadIdx.x; r < R; r += ST_THREADS) {
         double s = 0.0, c = 0.0;
-        for (int i = i0; i < i1; i++) {
-            const double x = X[(size_t)i * R + r];
-            if (cs_isna(x)) continue;
-            c += 1.0;
-            const int k = Z[i] - 1;
-            if (k < 0 || k >= K) continue;
-            const double d = x - U[(size_t)k * R + r];
-            if (!cs_isna(d)) s += d * d;
+        for (int i = i0; i < i1; i += ST_UNROLL) { // ST_UNROLL (x, u) pairs in flight, cells in order
+            double x[ST_UNROLL], u[ST_UNROLL];
+            bool lab[ST_UNROLL];
+#pragma unroll
+            for (int q = 0; q < ST_UNROLL; q++) {
+                const bool in = i + q < i1;
+                const int k = in ? Z[i + q] - 1 : -1;
+                lab[q] = (unsigned)k < (unsigned)K;
+                x[q] = in ? X[(size_t)(i + q) * R + r] : CUDART_NAN;
+                u[q] = lab[q] ? U[(size_t)k * R + r] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < ST_UNROLL; q++) {
+                if (cs_isna(x[q])) continue;
+                c += 1.0;
+                if (!lab[q]) continue;
+                const double d = x[q] - u[q];
+                if (!cs_isna(d)) s += d * d;
+            }
         }
         atomicAdd(sq + r, s);
         atomicAdd(cnt + r, c);
