@@ -10,23 +10,24 @@
 
 namespace {
 
-constexpr int ST_THREADS = 256;
 constexpr int ST_CHUNK = 512;
 constexpr int ST_UNROLL = 8;
+// a thread per segment: one warp-multiple that covers R (no thread with two segments while its neighbours idle)
+inline int st_threads(int R) { return R >= 1024 ? 1024 : (R < 64 ? 64 : ((R + 31) / 32) * 32); }
 
 // grid: cell chunks.  Shared accumulators when K*R fits, global atomics otherwise.
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(1024)
 cluster_stats_kernel(int N, int R, int K, const double *__restrict__ X, const int *__restrict__ Z,
                      double *__restrict__ sum_x, double *__restrict__ cnt_x, double *__restrict__ nk, int use_smem)
 {
     extern __shared__ double s_acc[]; // K*R sums, K*R counts
     const int i0 = blockIdx.x * ST_CHUNK, i1 = min(N, i0 + ST_CHUNK);
     if (use_smem) {
-        for (int e = threadIdx.x; e < 2 * K * R; e += ST_THREADS) s_acc[e] = 0.0;
+        for (int e = threadIdx.x; e < 2 * K * R; e += blockDim.x) s_acc[e] = 0.0;
         __syncthreads();
     }
     // a thread owns segment r; ST_UNROLL cells' values are in flight at a time (cells still in order)
-    for (int r = threadIdx.x; r < R; r += ST_THREADS) {
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
         for (int i = i0; i < i1; i += ST_UNROLL) {
             int k[ST_UNROLL];
             double v[ST_UNROLL];
@@ -49,13 +50,13 @@ cluster_stats_kernel(int N, int R, int K, const double *__restrict__ X, const in
             }
         }
     }
-    for (int i = i0 + threadIdx.x; i < i1; i += ST_THREADS) { // cluster sizes
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) { // cluster sizes
         const int k = Z[i] - 1;
         if (k >= 0 && k < K) atomicAdd(nk + k, 1.0);
     }
     if (use_smem) {
         __syncthreads();
-        for (int e = threadIdx.x; e < K * R; e += ST_THREADS) {
+        for (int e = threadIdx.x; e < K * R; e += blockDim.x) {
             if (s_acc[K * R + e] != 0.0) {
                 atomicAdd(sum_x + e, s_acc[e]);
                 atomicAdd(cnt_x + e, s_acc[K * R + e]);
@@ -64,12 +65,12 @@ cluster_stats_kernel(int N, int R, int K, const double *__restrict__ X, const in
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(1024)
 sigma_stats_kernel(int N, int R, int K, const double *__restrict__ X, const int *__restrict__ Z,
                    const double *__restrict__ U, double *__restrict__ sq, double *__restrict__ cnt)
 {
     const int i0 = blockIdx.x * ST_CHUNK, i1 = min(N, i0 + ST_CHUNK);
-    for (int r = threadIdx.x; r < R; r += ST_THREADS) {
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
         double s = 0.0, c = 0.0;
         for (int i = i0; i < i1; i += ST_UNROLL) { // ST_UNROLL (x, u) pairs in flight, cells in order
             double x[ST_UNROLL], u[ST_UNROLL];
@@ -152,7 +153,7 @@ extern "C" int cs_cluster_stats_dev(int N, int R, int K, const double *d_X, cons
     const int use_smem = smem <= 160 * 1024;
     if (use_smem && smem > 48 * 1024)
         CS_CUDA(cudaFuncSetAttribute(cluster_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cluster_stats_kernel<<<(N + ST_CHUNK - 1) / ST_CHUNK, ST_THREADS, use_smem ? smem : 0, st>>>(
+    cluster_stats_kernel<<<(N + ST_CHUNK - 1) / ST_CHUNK, st_threads(R), use_smem ? smem : 0, st>>>(
         N, R, K, d_X, d_Z, d_sum_x, d_cnt_x, d_nk, use_smem);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
@@ -166,7 +167,7 @@ extern "C" int cs_sigma_stats_dev(int N, int R, int K, const double *d_X, const 
     CS_CUDA(cudaMemsetAsync(d_sq, 0, sizeof(double) * (size_t)R, st));
     CS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(double) * (size_t)R, st));
     if (N == 0) return CS_OK;
-    sigma_stats_kernel<<<(N + ST_CHUNK - 1) / ST_CHUNK, ST_THREADS, 0, st>>>(N, R, K, d_X, d_Z, d_U, d_sq, d_cnt);
+    sigma_stats_kernel<<<(N + ST_CHUNK - 1) / ST_CHUNK, st_threads(R), 0, st>>>(N, R, K, d_X, d_Z, d_U, d_sq, d_cnt);
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
