@@ -168,6 +168,33 @@ def test_binning_edge_cases(cs, oracle):
         bin_counts_csc(G, 1, B, np.array([0, 1], np.int32), np.array([G], np.int32), np.ones(1), map_ptr, map_bin)
 
 
+@pytest.mark.parametrize("widths,step", [([1, 1, 1, 2, 3], 2), ([1, 2, 5, 20, 32], 6), ([30, 31, 32], 3), ([1, 1, 2, 32], 10)])
+def test_binning_onepass_overlapping_and_wide_genes(cs, oracle, widths, step):
+    """The one-pass kernel's own limits: genes of up to 32 bins whose intervals overlap heavily (most
+    hits fall on bins an earlier entry opened: the red.shared path, entries reaching over several old
+    bins), tiles that open more ranks than a warp's staging buffer holds (the kernel gives up on the
+    column and the plan falls back to the generic kernels), next to ordinary narrow genes."""
+    rng = np.random.default_rng(31 + step)
+    G = 5000
+    nh = rng.choice(widths, size=G)
+    b0 = np.cumsum(rng.integers(0, step + 1, size=G))
+    B = int(b0[-1] + 40)
+    map_ptr = np.zeros(G + 1, np.int32)
+    map_ptr[1:] = np.cumsum(nh)
+    map_bin = np.concatenate([np.arange(f, f + n) for f, n in zip(b0, nh)]).astype(np.int32)
+    cols = [np.arange(G, dtype=np.int32), np.zeros(0, np.int32)]
+    for m in (1, 7, 8, 9, 255, 256, 257, 1000, 2500, 4000, 4999):
+        cols.append(np.sort(rng.choice(G, size=m, replace=False)).astype(np.int32))
+    cols += [np.arange(G, dtype=np.int32)] * 3 + [np.arange(0, G, 2, dtype=np.int32)] * 40      # enough columns for every warp
+    colptr = np.zeros(len(cols) + 1, np.int32)
+    colptr[1:] = np.cumsum([len(c) for c in cols])
+    rowidx = np.concatenate(cols)
+    x = rng.integers(1, 9, size=len(rowidx)).astype(np.float64)
+    _check_bins(cs, oracle, G, len(cols), B, colptr, rowidx, x, map_ptr, map_bin)
+    x[rng.random(len(x)) < 0.3] = 0.0                                    # explicit zeros: sums that vanish are dropped
+    _check_bins(cs, oracle, G, len(cols), B, colptr, rowidx, x, map_ptr, map_bin)
+
+
 def test_binning_streaming_path_edge_cases(cs, oracle):
     """Regular map (contiguous bins, non-decreasing first bin in gene order) -> the warp-per-column
     streaming kernels: ragged / empty / very sparse columns whose batches span more bins than a
