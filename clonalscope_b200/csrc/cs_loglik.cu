@@ -9,6 +9,7 @@
 #include "cs_common.cuh"
 
 #include <math_constants.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -115,6 +116,86 @@ loglik_matrix_kernel(int N, int R, int K, const double *__restrict__ X, const do
             b += __shfl_xor_sync(CS_FULL, b, 1);
             const int k = k0 + kslot;
             if ((lane & 7) == 0 && k < K) LL[(size_t)i * K + k] = -(cpart + 0.5 * b);
+        }
+    }
+}
+
+// Two cells per warp pass: every cluster value loaded from L1 serves both cells (with many clusters
+// the one-cell kernel is bound by its load instructions as much as by the FP64 pipe).  Per cell the
+// additions happen in the same order as in loglik_matrix_kernel: the results are bit-identical.
+template <int NCH>
+__global__ void __launch_bounds__(LL_THREADS)
+loglik_matrix2_kernel(int N, int R, int K, const double *__restrict__ X, const double *__restrict__ U,
+                      const double *__restrict__ sigma, double *__restrict__ LL)
+{
+    extern __shared__ double s_ll[];
+    double *s_isig = s_ll, *s_c = s_ll + R;
+    for (int r = threadIdx.x; r < R; r += LL_THREADS) {
+        const double s = sigma[r];
+        s_isig[r] = 1.0 / s;
+        s_c[r] = CS_LN_SQRT_2PI + log(s);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = LL_THREADS / 32;
+    const int kslot = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const int npairs = (N + 1) / 2;
+    auto fold = [&](const double (&q)[LL_KT]) {
+        const bool up16 = lane & 16, up8 = lane & 8;
+        const double s0 = up16 ? q[0] : q[2], s1 = up16 ? q[1] : q[3];
+        double a0 = (up16 ? q[2] : q[0]) + __shfl_xor_sync(CS_FULL, s0, 16);
+        double a1 = (up16 ? q[3] : q[1]) + __shfl_xor_sync(CS_FULL, s1, 16);
+        double b = (up8 ? a1 : a0) + __shfl_xor_sync(CS_FULL, up8 ? a0 : a1, 8);
+        b += __shfl_xor_sync(CS_FULL, b, 4);
+        b += __shfl_xor_sync(CS_FULL, b, 2);
+        b += __shfl_xor_sync(CS_FULL, b, 1);
+        return b;
+    };
+    for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < npairs; p += gridDim.x * warps_per_block) {
+        const int i0 = 2 * p, i1 = min(2 * p + 1, N - 1); // (an odd N: the last pair scores its cell twice, writes it once)
+        const double *xr0 = X + (size_t)i0 * R, *xr1 = X + (size_t)i1 * R;
+        double x0[NCH], x1[NCH], is[NCH];
+        double c0 = 0.0, c1 = 0.0;
+        unsigned ok0 = 0u, ok1 = 0u;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int r = lane + 32 * c;
+            x0[c] = (r < R) ? __ldcs(xr0 + r) : CUDART_NAN;
+            x1[c] = (r < R) ? __ldcs(xr1 + r) : CUDART_NAN;
+            is[c] = (r < R) ? s_isig[r] : 0.0;
+            if (!cs_isna(x0[c])) {
+                c0 += s_c[r];
+                ok0 |= 1u << c;
+            }
+            if (!cs_isna(x1[c])) {
+                c1 += s_c[r];
+                ok1 |= 1u << c;
+            }
+        }
+        c0 = cs_warp_sum_bfly(c0);
+        c1 = cs_warp_sum_bfly(c1);
+        for (int k0 = 0; k0 < K; k0 += LL_KT) {
+            double q0[LL_KT], q1[LL_KT];
+#pragma unroll
+            for (int j = 0; j < LL_KT; j++) q0[j] = q1[j] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int r = min(lane + 32 * c, R - 1);
+#pragma unroll
+                for (int j = 0; j < LL_KT; j++) {
+                    const int k = min(k0 + j, K - 1);
+                    const double u = __ldg(U + (size_t)k * R + r);
+                    const double d0 = (x0[c] - u) * is[c], d1 = (x1[c] - u) * is[c];
+                    if (ok0 >> c & 1u) q0[j] = fma(d0, d0, q0[j]);
+                    if (ok1 >> c & 1u) q1[j] = fma(d1, d1, q1[j]);
+                }
+            }
+            const double b0 = fold(q0), b1 = fold(q1);
+            const int k = k0 + kslot;
+            if ((lane & 7) == 0 && k < K) {
+                LL[(size_t)i0 * K + k] = -(c0 + 0.5 * b0);
+                if (i1 != i0) LL[(size_t)i1 * K + k] = -(c1 + 0.5 * b1);
+            }
         }
     }
 }
@@ -262,6 +343,16 @@ extern "C" int cs_loglik_matrix_dev(int N, int R, int K, const double *d_X, cons
     else if (R <= 320) kern = loglik_matrix_kernel<10>;
     else if (R <= 384) kern = loglik_matrix_kernel<12>;
     else if (R <= 512) kern = loglik_matrix_kernel<16>;
+    // many clusters: two cells per pass (CS_LL_PAIR=0 keeps the one-cell kernel)
+    static const bool pair_ok = !(getenv("CS_LL_PAIR") && atoi(getenv("CS_LL_PAIR")) == 0);
+    if (pair_ok && K >= 8 && N >= 2) {
+        if (R <= 32) kern = loglik_matrix2_kernel<1>;
+        else if (R <= 64) kern = loglik_matrix2_kernel<2>;
+        else if (R <= 128) kern = loglik_matrix2_kernel<4>;
+        else if (R <= 192) kern = loglik_matrix2_kernel<6>;
+        else if (R <= 256) kern = loglik_matrix2_kernel<8>;
+        else if (R <= 320) kern = loglik_matrix2_kernel<10>;
+    }
     CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, LL_THREADS, smem, (cudaStream_t)stream>>>(N, R, K, d_X, d_U, d_sigma, d_LL);
     CS_CUDA(cudaGetLastError());
