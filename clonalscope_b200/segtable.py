@@ -351,11 +351,10 @@ def CreateSegtableNoWGS(mtx=None, barcodes=None, features=None, Cov_obj=None, Ze
         Zest = Cov_obj["result_final"]["result"]["Zest"]
     Zest = list(np.asarray(Zest).tolist())
     levels = _table_levels(Zest)
-    label = np.full(len(Zest), -1, dtype=np.int32)
-    for k, lev in enumerate(levels):
-        for i, v in enumerate(Zest):
-            if not (isinstance(v, float) and math.isnan(v)) and (int(v) if isinstance(lev, int) else str(v)) == lev:
-                label[i] = k
+    index_of = {lev: k for k, lev in enumerate(levels)}                # one pass over the cells (NA -> no pool)
+    numeric = bool(levels) and isinstance(levels[0], int)
+    label = np.asarray([-1 if (isinstance(v, float) and math.isnan(v)) else index_of[int(v) if numeric else str(v)]
+                        for v in Zest], dtype=np.int32)
     K = len(levels)
     normal = np.array([0 if c == "normal" else -1 for c in ctype], dtype=np.int32)        # (:77) pool 0 = the normal cells
     chrom, start, end = _bed_columns(bin_bed)
