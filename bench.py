@@ -649,6 +649,42 @@ def run_ours(a):
                           ms_reps=[round(r * 1e3, 1) for r in reps],
                           note="median of 3 calls through the host API: pageable inputs, freshly allocated outputs",
                           h2d_bytes=int(cp_h.nbytes + ri_h.nbytes + x_h.nbytes), d2h_bytes=int(ocp.nbytes + ori.nbytes + ox.nbytes))
+    # ---------------- the caller of the aggregation (CreateSegtableNoWGS): bin x cluster pooling of the
+    # device-resident result, then running mean + 4-state Viterbi of every (cluster, chromosome) sequence
+    segtable = None
+    if rank == 0 and world == 1 and not a.no_extra:
+        Kc = 4
+        labels = torch.randint(0, Kc, (NB,), device=dev, dtype=torch.int32)
+        pooled = torch.zeros((Kc, B), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            assert L.cs_rowsum_by_label_dev(B, NB, vp(out_colptr), vp(out_rowidx), vp(out_x), vp(labels), Kc, vp(pooled),
+                                            C.c_void_p(st)) == 0, L.cs_last_error()
+        e0.record()
+        for _ in range(5):
+            L.cs_rowsum_by_label_dev(B, NB, vp(out_colptr), vp(out_rowidx), vp(out_x), vp(labels), Kc, vp(pooled), C.c_void_p(st))
+        e1.record()
+        torch.cuda.synchronize()
+        pool_ms = e0.elapsed_time(e1) / 5
+        prof_h = pooled.cpu().numpy()
+        chrom_of_bin = np.asarray(bins["chr"])
+        seqs = []
+        for k in range(Kc):
+            v = prof_h[k] / max(np.median(prof_h[k]), 1.0)
+            for c in range(1, 23):
+                seqs.append(v[chrom_of_bin == c])
+        from clonalscope_b200.segtable import segment_hmm
+        t_pi = 1e-6
+        Pi = np.full((4, 4), t_pi)
+        np.fill_diagonal(Pi, 1 - 3 * t_pi)
+        segment_hmm(seqs, 100, [1.8, 1.5, 1.0, 0.5], [0.2] * 4, [0.1, 0.2, 0.5, 0.2], Pi)
+        t0 = time.perf_counter()
+        segment_hmm(seqs, 100, [1.8, 1.5, 1.0, 0.5], [0.2] * 4, [0.1, 0.2, 0.5, 0.2], Pi)
+        hmm_ms = (time.perf_counter() - t0) * 1e3
+        segtable = dict(pooling_ms=pool_ms, pooling_gbs=12.0 * cap / (pool_ms * 1e-3) / 1e9,
+                        pooling_frac_of_hbm_peak=12.0 * cap / (pool_ms * 1e-3) / 1e9 / hbm_peak, clusters=Kc, cells=NB, bins=B,
+                        hmm_ms=hmm_ms, hmm_sequences=len(seqs), hmm_bins=int(sum(len(q) for q in seqs)),
+                        note="cs_rowsum_by_label_dev on the binning leg's device-resident output (12 B per stored count, "
+                             "FP64 atomics); cs_segment_hmm through the host API (one launch for every cluster and chromosome)")
     L.cs_bin_plan_destroy(plan)
 
     # ---------------- EstRegionCov (a7) end to end with host buffers on the same count matrix
@@ -761,6 +797,8 @@ def run_ours(a):
             line["fixtures"] = fixtures
         if kernels:
             line["kernels"] = kernels
+        if segtable:
+            line["segtable"] = segtable
         if allele:
             line["allele_sampler"] = allele
         if config5:
